@@ -1,0 +1,258 @@
+/* ndsb200.h -- C ABI of the B200-native multi-walker engine for NDSimulator.
+ *
+ * The reference (mir-group/NDSimulator, pure Python) has no FFI boundary; its hot path sits behind a
+ * duck-typed plugin protocol.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  Conventions:
+ *   - C linkage, plain pointers and sizes, no exceptions across the boundary;
+ *   - every function returns 0 on success, non-zero on error; nds_last_error() gives the message;
+ *   - the caller owns all HOST buffers, the engine owns device memory and its CUDA stream;
+ *   - one host thread per engine handle; distinct handles on distinct devices are independent;
+ *   - all host-side arrays are fp64 ("double") whatever the engine's compute precision, laid out
+ *     structure-of-arrays with the walker index fastest:  x[d * M + w].
+ *   - there is NO CPU fallback: without a CUDA device nds_create() fails.
+ */
+#ifndef NDSB200_H
+#define NDSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDS_ABI_VERSION 1
+#define NDS_MAX_DIM 5     /* ndim of the built-in potentials is 1, 2 or 5                       */
+#define NDS_MAX_CV 5      /* colvardim <= ndim for every built-in colvar                         */
+#define NDS_MAX_UMB 4     /* harmonic restraints acting on one walker (umb_n, bias/__init__.py:31) */
+#define NDS_MAX_BASINS 8  /* committor basin boxes (engines/committor.py:31-42)                   */
+
+/* compute precision of the kernels ("precision" key, new) */
+enum { NDS_F32 = 0, NDS_F64 = 1 };
+
+/* method: engines/__init__.py:11-31 (md, committor with temperature != 0) */
+enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1 };
+
+/* integrate: engines/md.py:59 */
+enum { NDS_INT_LANGEVIN = 0, NDS_INT_LANGEVIN2 = 1, NDS_INT_NVE = 2, NDS_INT_RESCALE = 3 };
+
+/* potential: class names of ndsimulator/potentials (potentials/_build.py:12-18) */
+enum {
+  NDS_POT_MUELLER2D = 0,   /* potentials/mueller.py:6-45     ndim 2 */
+  NDS_POT_MUELLER5D = 1,   /* potentials/mueller.py:108-142  ndim 5, needs true_colvar (cd 2) */
+  NDS_POT_MUELLER5DSHL = 2,/* potentials/mueller.py:155-157  A/5 */
+  NDS_POT_DOUBLEWELL1D = 3,/* potentials/double_well.py:6-25 ndim 1 */
+  NDS_POT_DOUBLEWELL = 4,  /* potentials/double_well.py:34-53 ndim 2 */
+  NDS_POT_THREEHOLE2D = 5, /* potentials/three_hole.py:6-57  ndim 2, needs true_colvar (cd 2) */
+  NDS_POT_THREEHOLE5D = 6, /* potentials/three_hole.py:72-125 ndim 5, needs true_colvar (cd 2) */
+  NDS_POT_GAUSSIAN2D = 7,  /* potentials/misc.py:7-26 */
+  NDS_POT_GAUSSIAN = 8,    /* potentials/misc.py:32-43 (factory default, _build.py:10) */
+  NDS_POT_FLAT1D = 9,      /* potentials/flat.py:17-24 */
+  NDS_POT_FLAT2D = 10,     /* potentials/flat.py:5-14 */
+  NDS_POT_COUNT = 11
+};
+
+/* colvar / true_colvar: class names of ndsimulator/colvars (colvars/_build.py:10-19) */
+enum {
+  NDS_CV_ORIGINAL = 0,     /* colvars/misc.py:6-16  identity, colvardim = ndim */
+  NDS_CV_EXTRACTX = 1,     /* colvars/two.py:17-25 */
+  NDS_CV_EXTRACTY = 2,     /* colvars/two.py:6-14 */
+  NDS_CV_XMY = 3,          /* colvars/two.py:28-36 */
+  NDS_CV_XPY = 4,          /* colvars/two.py:39-47 */
+  NDS_CV_ROTATE2D = 5,     /* colvars/two.py:50-61 */
+  NDS_CV_PROJ2DTO1D = 6,   /* colvars/two.py:64-73 */
+  NDS_CV_PROJ5DTO1DX0 = 7, /* colvars/five.py:5-15 */
+  NDS_CV_PROJ5DTO1DX2 = 8, /* colvars/five.py:18-28 */
+  NDS_CV_PROJ5DTO1D = 9,   /* colvars/five.py:31-44 (Jacobian quirk 2e-7) */
+  NDS_CV_PROJ5DTO2D = 10,  /* colvars/five.py:47-71 */
+  NDS_CV_PROJ5DTO2DV2 = 11,/* colvars/five.py:74-98 */
+  NDS_CV_COUNT = 12
+};
+
+/* where the per-step Gaussian numbers come from */
+enum {
+  NDS_NOISE_PHILOX = 0,    /* Philox4x32-10, key = seed, counter = (stream index, global walker id) */
+  NDS_NOISE_EXTERNAL = 1   /* read from a caller-provided table (nds_set_noise); parity tests only   */
+};
+
+/* POD configuration.  Every numeric field mirrors a YAML / kwargs key of the reference
+ * (SURVEY.md section 8b); the Python front-end fills it with the reference's prefix rules. */
+typedef struct nds_config {
+  int32_t abi_version;        /* must be NDS_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t precision;          /* NDS_F32 | NDS_F64 */
+  int32_t ndim;               /* ndrun.py:79 */
+  int32_t method;             /* ndrun.py:86 */
+  int32_t integrator;         /* md.py:52 "integrate" */
+  int32_t potential;          /* potentials/_build.py:10 */
+  int32_t colvar;             /* colvars/_build.py:10 "colvar_name" */
+  int32_t true_colvar;        /* "true_colvar_name" */
+  int32_t noise_mode;         /* NDS_NOISE_* */
+  int32_t steps_per_launch;   /* K: MD steps fused into one kernel launch (new key) */
+  int32_t reserved0;
+
+  int64_t n_walkers;          /* M: walkers owned by this engine (new key n_walkers)         */
+  int64_t walker_offset;      /* global id of local walker 0 (multi-GPU sharding)            */
+  int64_t n_walkers_global;   /* total walkers over all ranks (shared-hill table layout)     */
+  uint64_t seed;              /* ndrun.py:88; Philox key */
+
+  double temperature;         /* ndrun.py:80 */
+  double initial_temperature; /* ndrun.py:149 */
+  double mass;                /* ndrun.py:81; m = au_mass * mass (data.py:27-28) */
+  double dt;                  /* md.py:50 */
+  double gamma;               /* md.py:51 */
+  double rescale_freq;        /* md.py:53 (time units); <= 0 means "None" */
+
+  /* potential parameters.  Mueller2d/5d: [0..3] x_center, [4..7] y_center (mueller.py:15-16).
+   * DoubleWell1d: K1, K2, x1, x2, sigma.  DoubleWell: K1, K2, x1[2], x2[2], sigma.            */
+  double pot_params[16];
+
+  /* umbrella sampling, bias/umb.py:9-40: V = 1/2 sum k (R-R0)^2 */
+  int32_t n_umb;              /* number of harmonic restraints on each walker (umb_n) */
+  int32_t umb_per_walker;     /* 1: restraint 0 takes k, r0 per walker from nds_set_walker_bias */
+  double umb_k[NDS_MAX_UMB][NDS_MAX_CV];
+  double umb_r0[NDS_MAX_UMB][NDS_MAX_CV];
+
+  /* well-tempered metadynamics, bias/gaus.py:48-128 (fixed sigma) */
+  int32_t mtd_enabled;
+  int32_t mtd_shared;         /* 1: all walkers (all ranks) share one hill table; 0: one table per walker */
+  double mtd_w;               /* initial height */
+  double mtd_sigma[NDS_MAX_CV];
+  double mtd_dep_freq;        /* deposition period in TIME units (gaus.py:134) */
+  double mtd_biasf;           /* bias factor, must be > 1 */
+  int64_t mtd_capacity;       /* hills the table can hold (per walker when !mtd_shared) */
+
+  /* potential-energy bias, bias/pe.py:30-51 */
+  int32_t pe_enabled;
+  int32_t reserved1;
+  double pe_thred;
+
+  /* committor, engines/committor.py:31-42,118-142 */
+  int32_t n_basins;
+  int32_t reserved2;
+  int64_t diffusion_time;
+  double criteria[NDS_MAX_BASINS][NDS_MAX_CV][2];
+
+  /* observable sampling, io/stat.py:57-74 + io/dump.py:76-102 */
+  int64_t dump_freq;          /* frame every dump_freq steps; 0 = no frames */
+  int64_t dump_walkers;       /* frames are recorded for local walkers [0, dump_walkers) */
+  int64_t dump_capacity;      /* frames the device ring can hold between two drains */
+  int64_t stat_freq;          /* io/stat.py:10; defines which thermo sample a dump row shows (A16) */
+} nds_config;
+
+typedef struct nds_engine nds_engine;
+
+/* message of the last failure on this handle (or of the last failed nds_create when e == NULL) */
+const char* nds_last_error(const nds_engine* e);
+
+/* fills cfg with the reference's defaults (ndrun.py:77-97, md.py:48-55, gaus.py:48-57, ...) */
+void nds_config_defaults(nds_config* cfg);
+
+/* colvardim of a colvar id at a given ndim, or -1 when the pair is invalid */
+int nds_colvar_dim(int colvar, int ndim);
+
+/* replaces NDRun.__init__ (ndrun.py:77-171): validates cfg (the reference's assertions become error
+ * codes), allocates SoA walker state on cfg->device.  All walkers start at x = 0, v unset.       */
+int nds_create(const nds_config* cfg, nds_engine** out);
+void nds_destroy(nds_engine* e);
+
+/* replaces Atom.initialize (data.py:69-76) + Modify.set_velocity (modify.py:38-63).
+ * x: [ndim][M].  v: [ndim][M] or NULL => Maxwell-Boltzmann at initial_temperature drawn from Philox
+ * at nds_begin() (per-walker stream).                                                           */
+int nds_set_state(nds_engine* e, const double* x, const double* v);
+
+/* per-walker umbrella windows (new; the reference runs one window per process).
+ * k, r0: [colvardim][M].  Requires cfg.umb_per_walker.                                          */
+int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0);
+
+/* external noise table for parity tests (NDS_NOISE_EXTERNAL): noise[step][j][w], j < normals per
+ * step (ndim for langevin: xi; 2*ndim for 2nd-langevin: xi then eta, md.py:120,127-128).
+ * Covers steps [first_step, first_step + nsteps).                                               */
+int nds_set_noise(nds_engine* e, const double* noise, int64_t first_step, int64_t nsteps);
+
+/* replaces NDRun.begin (ndrun.py:182-206) + MD.begin (md.py:101-110): initial potential / bias
+ * evaluation, velocities if unset, ke, T, frame 0.                                              */
+int nds_begin(nds_engine* e);
+
+/* replaces the NDRun.run loop (ndrun.py:214-251) for nsteps more steps: fix.update (metadynamics
+ * deposition schedule, gaus.py:130-146) -> engine.update (md.py:112-231 / committor.py:82-116)
+ * -> step += 1, time += dt -> frames.  Stream-ordered; returns after enqueueing unless the
+ * deposition exchange callback or the frame ring needs the host.                                */
+int nds_run(nds_engine* e, int64_t nsteps);
+int nds_sync(nds_engine* e);
+
+/* current state -> host.  Any pointer may be NULL.  x, v, f (potential force, atoms.forces),
+ * fixf (bias force, atoms.fixf): [ndim][M];  colv: [colvardim][M];
+ * thermo: [5][M] = T, pe, ke, biase, totale (data.py:77-81, md.py:226-229).                     */
+int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv,
+                  double* thermo);
+int64_t nds_step(const nds_engine* e);   /* NDRun.step  */
+double nds_time(const nds_engine* e);    /* NDRun.time (accumulated in fp64 like ndrun.py:240) */
+
+/* deterministic parity entry: replaces potential.compute(x) (potentials/potential.py:14),
+ * colvar.compute / jacobian (colvars/colvar.py:16-20) and the sum of fix.compute(x0, col0)
+ * (md.py:182-188) at n given configurations x[ndim][n], using the engine's current hill table
+ * and uniform umbrella parameters.  Outputs (any may be NULL): V[n], F[ndim][n], colv[cd][n],
+ * J[cd][ndim][n], Vb[n], Fb[ndim][n].                                                           */
+int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, double* F, double* colv,
+                double* J, double* Vb, double* Fb);
+
+/* hill table (bias/gaus.py _history, _w).  Shared table: centers[n][cd], heights[n].
+ * Per-walker tables (!mtd_shared): `walker` selects the table.                                  */
+int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* centers, double* heights,
+                  int64_t capacity);
+int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* centers,
+                  const double* heights);
+/* stale bias energy per walker used by the well-tempered height (fix.VR): [M] */
+int nds_get_vr(nds_engine* e, double* vr);
+
+/* multi-GPU shared-hill exchange.  When set, every deposition writes this rank's new hill records
+ * into its slot of the table and then calls  cb(user, dev_ptr_table_segment, bytes_per_rank)  on
+ * the engine's stream-ordered host path; the callback performs the allgather IN PLACE over the
+ * segment [n_hills, n_hills + n_walkers_global) (e.g. torch.distributed / NCCL).               */
+typedef int (*nds_exchange_fn)(void* user, void* dev_segment, int64_t bytes_per_rank,
+                               int64_t rank_offset_bytes);
+int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
+
+/* committor outcome (engines/committor.py:103-111; ndrun.py:261-264): basin[M] (-1 = none),
+ * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */
+int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);
+int64_t nds_count_alive(nds_engine* e);
+
+/* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
+ * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],
+ * T, pe, ke, biase, totale, VR, then the lagged thermo sample (A16): time, T, pe, ke, biase, totale.
+ * out: [n_frames][nds_frame_width()][dump_walkers].                                             */
+int nds_frame_width(const nds_engine* e);
+int64_t nds_frames_pending(const nds_engine* e);
+int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n_frames);
+
+/* free-energy estimate of the reference: sum of hills on a grid (bias/gaus.py:365-393 with the
+ * grid of io/plot.py:517-519).  grid[ny][nx], X = x0 + i*dx, Y = y0 + j*dy.                     */
+int nds_fes_grid(nds_engine* e, int64_t walker, double x0, double dx, int64_t nx, double y0,
+                 double dy, int64_t ny, double* grid);
+
+/* on-device histogram of the current colvar values of all local walkers (io/plot.py:562-572).
+ * counts[ny][nx] (ny = 1 for colvardim 1).                                                       */
+int nds_colvar_histogram(nds_engine* e, double x0, double dx, int64_t nx, double y0, double dy,
+                         int64_t ny, int64_t* counts);
+
+/* raw device pointers for zero-copy plumbing (torch / NCCL): positions, velocities (engine
+ * precision, SoA [ndim][M]) and the hill table (records of (colvardim + 1) reals, padded to 4). */
+int nds_device_pointers(nds_engine* e, void** x, void** v, void** hills, int64_t* hill_stride);
+void* nds_stream(nds_engine* e);          /* cudaStream_t of the engine */
+int64_t nds_n_hills(const nds_engine* e, int64_t walker);
+
+/* launches issued since creation (bench.py "gpu_launches") and duration of the last nds_run in
+ * milliseconds measured with CUDA events on the engine's stream.                                */
+int64_t nds_launch_count(const nds_engine* e);
+double nds_last_run_ms(nds_engine* e);
+/* name of the kernel variant selected for the hot loop ("md_block<f32,2,Mueller2d,...>") */
+const char* nds_kernel_name(const nds_engine* e);
+
+/* Philox4x32-10 known-answer hook (tests): out[4] = philox(ctr[4], key[2]) computed ON DEVICE.  */
+int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDSB200_H */

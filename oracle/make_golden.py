@@ -1,0 +1,305 @@
+"""TEST INFRASTRUCTURE ONLY: generate ``tests/golden/*.json`` by running the UNMODIFIED Python reference.
+
+Run in the authoring container (where ``/root/reference`` exists):
+
+    python oracle/make_golden.py
+
+The reference is imported through ``oracle/ref_stub.py`` (stand-ins for ``pyfile_utils`` and
+``matplotlib`` only -- no arithmetic is replaced).  The fixtures pin the C oracle
+(``tests/test_oracle_golden.py``) and, through it, the CUDA path.  NumPy 2.3.5 / Python 3.12.3 were used
+for the committed files; floats are written with ``repr`` so they round-trip bit-exactly.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_stub  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+EXAMPLES = os.path.join(ref_stub.REFERENCE_ROOT, "examples")
+TMP = tempfile.mkdtemp()
+
+
+def tolist(a):
+    return np.asarray(a, dtype=float).reshape(-1).tolist()
+
+
+def dump(name, obj):
+    os.makedirs(GOLDEN, exist_ok=True)
+    with open(os.path.join(GOLDEN, name), "w") as f:
+        json.dump(obj, f, indent=1)
+    print("wrote", name)
+
+
+def unshadow(sim):
+    """``AllData.__init__`` (data.py:34) stores ``run.x0`` (the initial position) on every component,
+    which shadows the CLASS attribute ``x0`` (well centres) of ``Gaussian2d`` / ``ThreeHole2d/5d``
+    (misc.py:12, three_hole.py:17,83): under ``NDRun`` those potentials crash (2-D) or silently use the
+    start position as centres (5-D).  The fixtures pin the class-attribute behaviour that the
+    reference's own unit test exercises (tests/unit/test_potential.py:19-33, instances built without
+    a run), so the shadowing instance attribute is removed here.  Nothing else is touched."""
+    pot = sim.potential
+    if "x0" in vars(pot) and hasattr(type(pot), "x0"):
+        del pot.x0
+    return sim
+
+
+def base_cfg(**kw):
+    cfg = dict(root=TMP, run_name="g", dump=False, screen=False, mass=1.0, temperature=300, dt=1.0,
+               method="md", seed=0, steps=10)
+    cfg.update(kw)
+    return cfg
+
+
+# --------------------------------------------------------------------------- point evaluations
+def eval_points():
+    rng = np.random.RandomState(2024)
+    out = []
+    combos = [
+        # potential, ndim, colvar, true_colvar, box for sample points
+        ("Mueller2d", 2, "Original", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "ExtractX", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "ExtractY", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "XmY", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "XpY", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "Rotate2d", "Original", (5.0, 45.0)),
+        ("Mueller2d", 2, "Proj2dto1d", "Original", (5.0, 45.0)),
+        ("DoubleWell", 2, "Original", "Original", (0.0, 40.0)),
+        ("DoubleWell1d", 1, "Original", "Original", (0.0, 40.0)),
+        ("Gaussian2d", 2, "Original", "Original", (5.0, 35.0)),
+        ("Gaussian", 2, "Original", "Original", (-5.0, 5.0)),
+        ("Flat2d", 2, "Original", "Original", (0.0, 10.0)),
+        ("Flat1d", 1, "Original", "Original", (0.0, 10.0)),
+        ("ThreeHole2d", 2, "Original", "Original", (2.0, 13.0)),
+        ("ThreeHole2d", 2, "Rotate2d", "Rotate2d", (2.0, 13.0)),
+        ("Mueller5d", 5, "Proj5dto2d", "Proj5dto2d", (5.0, 30.0)),
+        ("Mueller5d", 5, "Original", "Proj5dto2d", (5.0, 30.0)),
+        ("Mueller5d", 5, "Proj5dto1d", "Proj5dto2dv2", (5.0, 30.0)),
+        ("Mueller5d", 5, "Proj5dto1dx0", "Proj5dto2d", (5.0, 30.0)),
+        ("Mueller5d", 5, "Proj5dto1dx2", "Proj5dto2d", (5.0, 30.0)),
+        ("Mueller5d", 5, "Proj5dto2dv2", "Proj5dto2dv2", (5.0, 30.0)),
+        ("Mueller5dshl", 5, "Proj5dto2d", "Proj5dto2d", (5.0, 30.0)),
+        ("ThreeHole5d", 5, "Proj5dto2d", "Proj5dto2d", (1.0, 9.0)),
+    ]
+    for pot, ndim, cv, tcv, (lo, hi) in combos:
+        cfg = base_cfg(ndim=ndim, potential=pot, colvar_name=cv, true_colvar_name=tcv,
+                       x0=[lo + 1.0] * ndim, integrate="nve")
+        sim = unshadow(ref_stub.make_run(cfg))
+        pts = rng.uniform(lo, hi, size=(6, ndim))
+        rec = dict(config={k: cfg[k] for k in ("ndim", "potential", "colvar_name", "true_colvar_name")},
+                   points=[], V=[], F=[], colv=[], J=[])
+        for x in pts:
+            V, f = sim.potential.compute(x=np.array(x))
+            c = np.asarray(sim.colvar.compute(np.array(x)), dtype=float).reshape(-1)
+            J = np.asarray(sim.colvar.jacobian(np.array(x)), dtype=float).reshape(len(c), ndim)
+            rec["points"].append(tolist(x))
+            rec["V"].append(float(V))
+            rec["F"].append(tolist(f))
+            rec["colv"].append(tolist(c))
+            rec["J"].append(tolist(J))
+        out.append(rec)
+    # the survey's spot values are regenerated here as well
+    dump("eval_points.json", out)
+
+
+def bias_points():
+    rng = np.random.RandomState(77)
+    out = []
+    # umbrella: 2-D Original, 5-D Proj5dto2d, 1-output colvar, two restraints
+    umb_cases = [
+        dict(ndim=2, potential="Mueller2d", biases=["umb"], umb_k=0.1, umb_r0=[18, 18], x0=[18.0, 18.0]),
+        dict(ndim=2, potential="Mueller2d", biases=["umb"], umb_k=[0.1, 0.3], umb_r0=[20, 25],
+             colvar_name="Rotate2d", x0=[18.0, 18.0]),
+        dict(ndim=2, potential="Mueller2d", biases=["umb"], umb_k=0.2, umb_r0=[3.0],
+             colvar_name="XmY", x0=[18.0, 18.0]),
+        dict(ndim=5, potential="Mueller5d", biases=["umb"], umb_k=0.1, umb_r0=[18, 18],
+             colvar_name="Proj5dto2d", true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0]),
+        dict(ndim=2, potential="Mueller2d", biases=["umb"], umb_n=2, umb_0_k=0.1, umb_0_r0=[18, 18],
+             umb_1_k=0.05, umb_1_r0=[25, 10], x0=[18.0, 18.0]),
+    ]
+    for case in umb_cases:
+        cfg = base_cfg(integrate="nve", **case)
+        if isinstance(cfg.get("umb_k"), list):  # Harmonic needs an ndarray for per-CV k (umb.py:29)
+            cfg["umb_k"] = np.array(cfg["umb_k"])
+        sim = ref_stub.make_run(cfg)
+        ndim = cfg["ndim"]
+        pts = rng.uniform(8.0, 30.0, size=(5, ndim))
+        rec = dict(config={k: v for k, v in case.items()}, points=[], Vb=[], Fb=[])
+        for x in pts:
+            col = sim.colvar.compute(np.array(x))
+            Vb, Fb = 0.0, np.zeros(ndim)
+            for fix in sim.fixes:
+                v, f = fix.compute(x0=np.array(x), col0=col)
+                Vb += v
+                Fb = Fb + f
+            rec["points"].append(tolist(x))
+            rec["Vb"].append(float(Vb))
+            rec["Fb"].append(tolist(Fb))
+        out.append(rec)
+    # metadynamics with a given hill table (bias/gaus.py:236-261)
+    mtd_cases = [
+        dict(ndim=2, potential="Mueller2d", biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0],
+             mtd_dep_freq=100, mtd_biasf=10.0, x0=[22.0, 30.0]),
+        dict(ndim=2, potential="Mueller2d", biases=["mtd"], mtd_w=0.05, mtd_sigma=[1.5],
+             mtd_dep_freq=100, mtd_biasf=10.0, colvar_name="XpY", x0=[22.0, 30.0]),
+        dict(ndim=5, potential="Mueller5d", biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 3.0],
+             mtd_dep_freq=100, mtd_biasf=10.0, colvar_name="Proj5dto2d",
+             true_colvar_name="Proj5dto2d", x0=[12.0] * 5),
+        dict(ndim=2, potential="Mueller2d", biases=["mtd", "umb"], mtd_w=0.05, mtd_sigma=[2.0, 2.0],
+             mtd_dep_freq=100, mtd_biasf=10.0, umb_k=0.1, umb_r0=[20, 20], x0=[22.0, 30.0]),
+        dict(ndim=2, potential="Mueller2d", biases=["pe"], pe_thred=-0.3, x0=[22.0, 30.0]),
+    ]
+    for case in mtd_cases:
+        cfg = base_cfg(integrate="nve", **case)
+        sim = ref_stub.make_run(cfg)
+        ndim = cfg["ndim"]
+        cd = sim.colvar.colvardim
+        nh = 37
+        centers = rng.uniform(10.0, 30.0, size=(nh, cd))
+        heights = rng.uniform(0.01, 0.05, size=nh)
+        for fix in sim.fixes:
+            if type(fix).__name__ == "Gaussian":
+                fix._history = centers.copy()
+                fix._w = heights.copy()
+        pts = rng.uniform(10.0, 30.0, size=(5, ndim))
+        rec = dict(config={k: v for k, v in case.items()}, hills_centers=centers.tolist(),
+                   hills_heights=heights.tolist(), points=[], Vb=[], Fb=[])
+        for x in pts:
+            col = sim.colvar.compute(np.array(x))
+            Vb, Fb = 0.0, np.zeros(ndim)
+            for fix in sim.fixes:
+                v, f = fix.compute(x0=np.array(x), col0=col)
+                Vb += v
+                Fb = Fb + np.asarray(f).reshape(-1)
+            rec["points"].append(tolist(x))
+            rec["Vb"].append(float(Vb))
+            rec["Fb"].append(tolist(Fb))
+        out.append(rec)
+    dump("bias_points.json", out)
+
+
+# ------------------------------------------------------------------------------- trajectories
+def run_traj(cfg, sample_every, v0=None):
+    sim = unshadow(ref_stub.make_run(cfg, v0=v0))
+    sim.begin()
+    a = sim.atoms
+    rec = dict(config={k: v for k, v in cfg.items() if k not in ("root", "run_name")},
+               v0=tolist(a.velocities), begin=dict(pe=float(a.pe), ke=float(a.ke), T=float(a.T),
+                                                   totale=float(a.totale)),
+               sample_every=sample_every, steps=[], x=[], v=[], f=[], fixf=[], colv=[], pe=[], ke=[],
+               biase=[], totale=[], T=[])
+    steps = cfg["steps"]
+    sim.steps = 0
+    done = 0
+    while done < steps:
+        n = min(sample_every, steps - done)
+        sim.steps = done + n
+        sim.run()
+        done = sim.step
+        rec["steps"].append(int(sim.step))
+        rec["x"].append(tolist(a.positions))
+        rec["v"].append(tolist(a.velocities))
+        rec["f"].append(tolist(a.forces))
+        rec["fixf"].append(tolist(a.fixf))
+        rec["colv"].append(tolist(a.colv))
+        for k in ("pe", "ke", "biase", "totale", "T"):
+            rec[k].append(float(getattr(a, k)))
+        if sim.method == "committor" and sim.commit_basin != -1:
+            break
+    rec["final_time"] = float(sim.time)
+    for fix in sim.fixes:
+        if type(fix).__name__ == "Gaussian" and fix._history is not None:
+            rec["hills_centers"] = np.asarray(fix._history, dtype=float).tolist()
+            rec["hills_heights"] = tolist(fix._w)
+            rec["VR"] = float(fix.VR)
+    if sim.method == "committor":
+        rec["commit_basin"] = int(sim.commit_basin)
+        rec["final_step"] = int(sim.step)
+    return rec
+
+
+def trajectories():
+    out = {}
+    md2d = yaml.safe_load(open(os.path.join(EXAMPLES, "2d-md.yaml")))
+    md2d.update(root=TMP, run_name="g", dump=False, screen=False)
+    out["2d_nve_seed7"] = run_traj(dict(md2d, integrate="nve", seed=7, steps=10000), 500)
+    out["2d_langevin_gamma0_seed7"] = run_traj(dict(md2d, integrate="langevin", gamma=0.0, seed=7,
+                                                    steps=2000), 500)
+    out["2d_langevin_gamma0.1_seed0"] = run_traj(dict(md2d, gamma=0.1, seed=0, steps=20000), 1000)
+    out["2d_md_yaml_as_shipped_seed0"] = run_traj(dict(md2d, seed=0, steps=2000), 200)
+    out["2d_langevin2_seed3"] = run_traj(dict(md2d, integrate="2nd-langevin", gamma=0.01, seed=3,
+                                              steps=3000), 300)
+    out["2d_rescale_seed3"] = run_traj(dict(md2d, integrate="rescale", rescale_freq=3, seed=3,
+                                            x0=[12.0, 12.0], steps=300), 30)
+    umb5 = yaml.safe_load(open(os.path.join(EXAMPLES, "5d-umb.yaml")))
+    umb5.update(root=TMP, run_name="g", dump=False, screen=False, seed=0, steps=5000)
+    out["5d_umb_seed0"] = run_traj(umb5, 500)
+    umb2 = yaml.safe_load(open(os.path.join(EXAMPLES, "2d-umb.yaml")))
+    umb2.update(root=TMP, run_name="g", dump=False, screen=False, seed=1, steps=3000)
+    out["2d_umb_seed1"] = run_traj(umb2, 300)
+    mtd = yaml.safe_load(open(os.path.join(EXAMPLES, "2d-mtd.yaml")))
+    mtd.update(root=TMP, run_name="g", dump=False, screen=False, seed=0, steps=3000)
+    out["2d_mtd_seed0"] = run_traj(mtd, 300)
+    out["5d_mtd_seed2"] = run_traj(
+        base_cfg(ndim=5, potential="Mueller5d", colvar_name="Proj5dto2d",
+                 true_colvar_name="Proj5dto2d", integrate="langevin", gamma=0.1, biases=["mtd"],
+                 mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0,
+                 x0=[12.0] * 5, seed=2, steps=1500), 150)
+    out["1d_doublewell_nve_seed4"] = run_traj(
+        base_cfg(ndim=1, potential="DoubleWell1d", x0=30.0, integrate="nve", seed=4, steps=2000,
+                 plot_boundary=[[0.0, 40.0]]), 200)
+    out["1d_doublewell_langevin_seed4"] = run_traj(
+        base_cfg(ndim=1, potential="DoubleWell1d", potential_K1=1.5, x0=30.0, gamma=0.1, seed=4,
+                 steps=2000, plot_boundary=[[0.0, 40.0]]), 200)
+    out["2d_threehole_nve_seed5"] = run_traj(
+        base_cfg(ndim=2, potential="ThreeHole2d", x0=[7.0, 9.0], integrate="nve", seed=5, dt=0.5,
+                 temperature=3000, steps=2000), 200)
+    out["2d_doublewell_pe_seed6"] = run_traj(
+        base_cfg(ndim=2, potential="DoubleWell", x0=[20.0, 12.0], gamma=0.05, seed=6, biases=["pe"],
+                 pe_thred=-0.45, steps=1500), 150)
+    dump("trajectories.json", out)
+
+
+def committor():
+    cm = yaml.safe_load(open(os.path.join(EXAMPLES, "2d-committor.yaml")))
+    cm.update(root=TMP, run_name="g", dump=False, screen=False)
+    out = dict(config={k: v for k, v in cm.items() if k not in ("root", "run_name")}, shots=[])
+    for seed in range(24):
+        sim = ref_stub.make_run(dict(cm, seed=seed))
+        sim.begin()
+        v0 = tolist(sim.atoms.velocities)
+        sim.run()
+        out["shots"].append(dict(seed=seed, v0=v0, basin=int(sim.commit_basin), step=int(sim.step),
+                                 x=tolist(sim.atoms.positions)))
+        print(seed, sim.commit_basin, sim.step)
+    dump("committor.json", out)
+
+
+def constants():
+    """integrator constants (md.py:81-99) and units for the BASELINE configs."""
+    out = {}
+    for name, kw in {
+        "C2_langevin_gamma0.1": dict(ndim=2, potential="Mueller2d", x0=[22.0, 24.0], gamma=0.1),
+        "C4_5d_umb": dict(yaml.safe_load(open(os.path.join(EXAMPLES, "5d-umb.yaml")))),
+    }.items():
+        cfg = base_cfg(**kw)
+        cfg.update(root=TMP, run_name="g", dump=False, screen=False)
+        sim = ref_stub.make_run(cfg)
+        e = sim.engine
+        out[name] = dict(m=float(e.m), kBT=float(e.kBT),
+                         **{k: float(getattr(e, k)) for k in ("c1", "c2", "c3", "c4", "c5") if hasattr(e, k)})
+    dump("constants.json", out)
+
+
+if __name__ == "__main__":
+    eval_points()
+    bias_points()
+    constants()
+    trajectories()
+    committor()
