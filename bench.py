@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: walker-steps/s of the fused multi-walker MD kernel (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c5] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: ONE fused launch block of `md_steps_per_step` MD
+steps over all walkers of the rank (C2: 2^20 walkers x 1000 MD steps = 1.05e9 walker-steps).  The default
+K=100 is the whole C2 job (10^5 MD steps).  value = walker-steps/s with the walker state resident in
+HBM; e2e = the same metric through the public API with HOST buffers (pinned H2D of x, v and D2H of
+x, v, thermo inside the timed region, every step).
+
+N > 1: launched by torchrun, one rank per GPU; walkers shard with no data-path collective (weak scaling,
+C2/C4) or share a hill table through one NCCL allgather per deposition stride (C5).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c4": 289.0}  # SURVEY.md section 8d (algorithmic, fixed)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def workload_cfg(name, n_walkers, precision):
+    if name == "c2":  # BASELINE.json configs[1]
+        return dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
+                    integrate="langevin", gamma=0.1, temperature=300, dt=1.0, seed=0, dump=False,
+                    n_walkers=n_walkers, precision=precision, steps_per_launch=1000)
+    if name == "c4":  # examples/5d-umb.yaml, windows x walkers as one batch
+        return dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+                    true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0], biases=["umb"],
+                    umb_k=0.1, umb_r0=[18, 18], umb_per_walker=True, integrate="2nd-langevin",
+                    md_gamma=0.01, temperature=300.0, dt=1.0, seed=0, dump=False, n_walkers=n_walkers,
+                    precision=precision, steps_per_launch=1000)
+    if name == "c5":  # 5-D multiple-walker metadynamics (derived config)
+        return dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+                    true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1,
+                    temperature=300, dt=1.0, seed=0, dump=False, biases=["mtd"], mtd_w=0.05,
+                    mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0, mtd_shared=True,
+                    n_walkers=n_walkers, precision=precision, steps_per_launch=100)
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [t.strip() for t in s.split(",")]
+            try:
+                sm.append(float(p[0]))
+                smax.append(float(p[1]))
+                for n, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(max(smax)) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def initial_state(name, spec, M, rank_offset):
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    extra = {}
+    if name == "c4":
+        # 16 x 16 windows: r0 on xi1 in {10..40} x xi2 in {6..36}
+        gid = rank_offset + np.arange(M)
+        win = gid % 256
+        r1 = 10.0 + 2.0 * (win % 16)
+        r2 = 6.0 + 2.0 * (win // 16)
+        x0 = np.stack([r1, np.zeros(M), r2, np.zeros(M), np.full(M, 100.0)])
+        extra["k"] = np.full((2, M), 0.1)
+        extra["r0"] = np.stack([r1, r2])
+    return x0, extra
+
+
+def cpu_baseline(name, threads, target_seconds=12.0):
+    """The oracle (scalar fp64 C port of the reference path) timed on the host cores of this box."""
+    from oracle import oracle
+    from ndsimulator_b200 import config
+    threads = threads or oracle.max_threads()
+    M = 64 * threads
+    spec = config.parse(workload_cfg(name, M, "f64"))
+    x0, extra = initial_state(name, spec, M, 0)
+
+    def run(nsteps):
+        o = oracle.OracleSim(spec.to_struct(), seeds=np.arange(M))
+        o.set_threads(threads)
+        o.set_state(x0)
+        if extra:
+            o.set_walker_bias(extra["k"], extra["r0"])
+        o.begin()
+        t = time.perf_counter()
+        o.run(nsteps)
+        return time.perf_counter() - t
+
+    probe_steps = 200
+    dt = run(probe_steps)
+    nsteps = int(max(probe_steps, min(200000, probe_steps * target_seconds / max(dt, 1e-6))))
+    dt = run(nsteps)
+    return dict(value=M * nsteps / dt, unit="walker-steps/s", cores=threads, kind="port",
+                sample=f"{M} walkers x {nsteps} MD steps of workload {name} (fp64 scalar C oracle, "
+                       f"OpenMP over walkers, {dt:.1f} s)")
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path (C oracle port; the Python reference itself cannot
+    travel to the GPU box) on all host cores, same config / metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from ndsimulator_b200 import config
+    name = args.workload
+    threads = oracle.max_threads()
+    M = 64 * threads
+    md_steps = 1000 if name != "c5" else 100
+    spec = config.parse(workload_cfg(name, M, "f64"))
+    x0, extra = initial_state(name, spec, M, 0)
+    o = oracle.OracleSim(spec.to_struct(), seeds=np.arange(M))
+    o.set_threads(threads)
+    o.set_state(x0)
+    if extra:
+        o.set_walker_bias(extra["k"], extra["r0"])
+    o.begin()
+    for _ in range(args.warmup):
+        o.run(md_steps)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.run(md_steps)
+    dt = time.perf_counter() - t
+    value = M * md_steps * args.steps / dt
+    sample = f"{M} walkers x {md_steps} MD steps per step (fp64 scalar C oracle, {threads} OpenMP threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": "walker-steps/s", "value": value, "unit": "walker-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "walkers": M, "md_steps_per_step": md_steps},
+        "cpu_baseline": dict(value=value, unit="walker-steps/s", cores=threads, kind="port", sample=sample),
+        "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: per workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ndsimulator_b200 import config
+    from ndsimulator_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.workload
+    M = args.walkers or {"c2": 1 << 20, "c4": 1 << 17, "c5": 8192}[name]
+    cfg = workload_cfg(name, M, args.precision)
+    cfg.update(device=local_rank, walker_offset=rank * M, n_walkers_global=world * M)
+    md_steps = cfg["steps_per_launch"]
+    if name == "c5":
+        cfg["steps"] = md_steps * (args.steps + args.warmup + (0 if args.no_e2e else args.steps)) + md_steps
+    spec = config.parse(cfg)
+    eng = Engine(spec.to_struct())
+    if name == "c5" and world > 1:
+        from ndsimulator_b200.distributed import attach_hill_exchange
+        attach_hill_exchange(eng)
+    x0, extra = initial_state(name, spec, M, rank * M)
+    eng.set_state(x0)
+    if extra:
+        eng.set_walker_bias(extra["k"], extra["r0"])
+    eng.begin()
+
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.run(md_steps)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- device-resident timing: K steps, CUDA events on the engine's stream, L2 flushed between steps
+    barrier()
+    launches0 = eng.launch_count
+    dev_ms = 0.0
+    hills_evals = 0
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if name == "c5":
+            hills_evals += M * md_steps * (eng.n_hills() + world * M)  # table after this step's deposit
+        eng.run(md_steps, sync=True)
+        dev_ms += eng.last_run_ms()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    launches = eng.launch_count - launches0
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    value = world * M * md_steps * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (pinned), every step
+    e2e = None
+    if not args.no_e2e:
+        nd = spec.ndim
+        hx = torch.empty((nd, M), dtype=torch.float64).pin_memory()
+        hv = torch.empty((nd, M), dtype=torch.float64).pin_memory()
+        st = eng.get_state(fields=("x", "v"))
+        hx.numpy()[:] = st["x"]
+        hv.numpy()[:] = st["v"]
+        ox = torch.empty((nd, M), dtype=torch.float64).pin_memory()
+        ov = torch.empty((nd, M), dtype=torch.float64).pin_memory()
+        oth = torch.empty((5, M), dtype=torch.float64).pin_memory()
+        import ctypes as C
+        dp = C.POINTER(C.c_double)
+
+        def ptr(tens):
+            return C.cast(tens.data_ptr(), dp)
+
+        def e2e_step():
+            # positions AND velocities are supplied, so the run continues (no re-draw, no re-begin)
+            eng._check(eng.lib.nds_set_state(eng.h, ptr(hx), ptr(hv)))
+            eng._check(eng.lib.nds_run(eng.h, md_steps))
+            eng._check(eng.lib.nds_get_state(eng.h, ptr(ox), ptr(ov), None, None, None, ptr(oth)))
+            hx.copy_(ox)
+            hv.copy_(ov)
+
+        e2e_n = max(3, min(args.steps, 20))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_n):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+        e2e = {"value": world * M * md_steps * e2e_n / e2e_s, "unit": "walker-steps/s",
+               "h2d_bytes_per_step": 2 * nd * M * 8, "d2h_bytes_per_step": (2 * nd + 5) * M * 8,
+               "steps": e2e_n}
+
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = measured_peaks()
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_count = props.multi_processor_count
+        sm_max_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp32_peak_tflops = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+        per_gpu = value / world
+        out = {
+            "metric": "walker-steps/s", "value": value, "unit": "walker-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": {"c2": "C2: 2-D Mueller-Brown Langevin gamma=0.1, 2^20 walkers/GPU",
+                                    "c4": "C4: 5-D umbrella windows (5d-umb.yaml), 256 windows, 2nd-order Langevin",
+                                    "c5": "C5: 5-D multiple-walker metadynamics, shared hill table"}[name],
+                       "walkers_per_gpu": M, "md_steps_per_step": md_steps,
+                       "kernel": eng.kernel_name, "l2": "flushed between steps (256 MiB memset)",
+                       "timing": "CUDA events on the engine stream per step, summed; max over ranks",
+                       "wall_ms_total": wall_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if name in FLOPS_PER_WALKER_STEP:
+            ach = per_gpu * FLOPS_PER_WALKER_STEP[name] / 1e12
+            out["roofline"] = {
+                "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak_tflops, "traffic": None,
+                "note": f"algorithmic {FLOPS_PER_WALKER_STEP[name]:.0f} flop/walker-step (SURVEY 8d) x "
+                        f"walker-steps/s per GPU; peak = {sm_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
+                        "(nvidia-smi clocks.max.sm); MEASURED_PEAKS.json holds no FP32 figure. HBM traffic is "
+                        "negligible (state is register-resident for 1000 steps)."}
+        else:
+            he = world * hills_evals / (dev_ms * 1e-3)
+            mufu_peak = sm_count * 16 * sm_max_mhz * 1e6
+            out["roofline"] = {
+                "bound": "mufu_ex2", "achieved": he / 1e12, "peak": mufu_peak / 1e12 * world,
+                "unit": "T hill-evals/s", "frac": he / (mufu_peak * world), "traffic": None,
+                "note": "one MUFU.EX2 per walker-hill pair; peak = SMs x 16 lanes x clocks.max.sm"}
+            out["hill_evals_per_s"] = he
+        if e2e:
+            out["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(name, 0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

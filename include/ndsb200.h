@@ -20,6 +20,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define NDS_API __attribute__((visibility("default")))
+#else
+#define NDS_API
+#endif
+
 #define NDS_ABI_VERSION 1
 #define NDS_MAX_DIM 5     /* ndim of the built-in potentials is 1, 2 or 5                       */
 #define NDS_MAX_CV 5      /* colvardim <= ndim for every built-in colvar                         */
@@ -142,68 +148,68 @@ typedef struct nds_config {
 typedef struct nds_engine nds_engine;
 
 /* message of the last failure on this handle (or of the last failed nds_create when e == NULL) */
-const char* nds_last_error(const nds_engine* e);
+NDS_API const char* nds_last_error(const nds_engine* e);
 
 /* fills cfg with the reference's defaults (ndrun.py:77-97, md.py:48-55, gaus.py:48-57, ...) */
-void nds_config_defaults(nds_config* cfg);
+NDS_API void nds_config_defaults(nds_config* cfg);
 
 /* colvardim of a colvar id at a given ndim, or -1 when the pair is invalid */
-int nds_colvar_dim(int colvar, int ndim);
+NDS_API int nds_colvar_dim(int colvar, int ndim);
 
 /* replaces NDRun.__init__ (ndrun.py:77-171): validates cfg (the reference's assertions become error
  * codes), allocates SoA walker state on cfg->device.  All walkers start at x = 0, v unset.       */
-int nds_create(const nds_config* cfg, nds_engine** out);
-void nds_destroy(nds_engine* e);
+NDS_API int nds_create(const nds_config* cfg, nds_engine** out);
+NDS_API void nds_destroy(nds_engine* e);
 
 /* replaces Atom.initialize (data.py:69-76) + Modify.set_velocity (modify.py:38-63).
  * x: [ndim][M].  v: [ndim][M] or NULL => Maxwell-Boltzmann at initial_temperature drawn from Philox
  * at nds_begin() (per-walker stream).                                                           */
-int nds_set_state(nds_engine* e, const double* x, const double* v);
+NDS_API int nds_set_state(nds_engine* e, const double* x, const double* v);
 
 /* per-walker umbrella windows (new; the reference runs one window per process).
  * k, r0: [colvardim][M].  Requires cfg.umb_per_walker.                                          */
-int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0);
+NDS_API int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0);
 
 /* external noise table for parity tests (NDS_NOISE_EXTERNAL): noise[step][j][w], j < normals per
  * step (ndim for langevin: xi; 2*ndim for 2nd-langevin: xi then eta, md.py:120,127-128).
  * Covers steps [first_step, first_step + nsteps).                                               */
-int nds_set_noise(nds_engine* e, const double* noise, int64_t first_step, int64_t nsteps);
+NDS_API int nds_set_noise(nds_engine* e, const double* noise, int64_t first_step, int64_t nsteps);
 
 /* replaces NDRun.begin (ndrun.py:182-206) + MD.begin (md.py:101-110): initial potential / bias
  * evaluation, velocities if unset, ke, T, frame 0.                                              */
-int nds_begin(nds_engine* e);
+NDS_API int nds_begin(nds_engine* e);
 
 /* replaces the NDRun.run loop (ndrun.py:214-251) for nsteps more steps: fix.update (metadynamics
  * deposition schedule, gaus.py:130-146) -> engine.update (md.py:112-231 / committor.py:82-116)
  * -> step += 1, time += dt -> frames.  Stream-ordered; returns after enqueueing unless the
  * deposition exchange callback or the frame ring needs the host.                                */
-int nds_run(nds_engine* e, int64_t nsteps);
-int nds_sync(nds_engine* e);
+NDS_API int nds_run(nds_engine* e, int64_t nsteps);
+NDS_API int nds_sync(nds_engine* e);
 
 /* current state -> host.  Any pointer may be NULL.  x, v, f (potential force, atoms.forces),
  * fixf (bias force, atoms.fixf): [ndim][M];  colv: [colvardim][M];
  * thermo: [5][M] = T, pe, ke, biase, totale (data.py:77-81, md.py:226-229).                     */
-int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv,
+NDS_API int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv,
                   double* thermo);
-int64_t nds_step(const nds_engine* e);   /* NDRun.step  */
-double nds_time(const nds_engine* e);    /* NDRun.time (accumulated in fp64 like ndrun.py:240) */
+NDS_API int64_t nds_step(const nds_engine* e);   /* NDRun.step  */
+NDS_API double nds_time(const nds_engine* e);    /* NDRun.time (accumulated in fp64 like ndrun.py:240) */
 
 /* deterministic parity entry: replaces potential.compute(x) (potentials/potential.py:14),
  * colvar.compute / jacobian (colvars/colvar.py:16-20) and the sum of fix.compute(x0, col0)
  * (md.py:182-188) at n given configurations x[ndim][n], using the engine's current hill table
  * and uniform umbrella parameters.  Outputs (any may be NULL): V[n], F[ndim][n], colv[cd][n],
  * J[cd][ndim][n], Vb[n], Fb[ndim][n].                                                           */
-int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, double* F, double* colv,
+NDS_API int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, double* F, double* colv,
                 double* J, double* Vb, double* Fb);
 
 /* hill table (bias/gaus.py _history, _w).  Shared table: centers[n][cd], heights[n].
  * Per-walker tables (!mtd_shared): `walker` selects the table.                                  */
-int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* centers, double* heights,
+NDS_API int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* centers, double* heights,
                   int64_t capacity);
-int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* centers,
+NDS_API int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* centers,
                   const double* heights);
 /* stale bias energy per walker used by the well-tempered height (fix.VR): [M] */
-int nds_get_vr(nds_engine* e, double* vr);
+NDS_API int nds_get_vr(nds_engine* e, double* vr);
 
 /* multi-GPU shared-hill exchange.  When set, every deposition writes this rank's new hill records
  * into its slot of the table and then calls  cb(user, dev_ptr_table_segment, bytes_per_rank)  on
@@ -211,46 +217,46 @@ int nds_get_vr(nds_engine* e, double* vr);
  * segment [n_hills, n_hills + n_walkers_global) (e.g. torch.distributed / NCCL).               */
 typedef int (*nds_exchange_fn)(void* user, void* dev_segment, int64_t bytes_per_rank,
                                int64_t rank_offset_bytes);
-int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
+NDS_API int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
 
 /* committor outcome (engines/committor.py:103-111; ndrun.py:261-264): basin[M] (-1 = none),
  * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */
-int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);
-int64_t nds_count_alive(nds_engine* e);
+NDS_API int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);
+NDS_API int64_t nds_count_alive(nds_engine* e);
 
 /* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
  * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],
  * T, pe, ke, biase, totale, VR, then the lagged thermo sample (A16): time, T, pe, ke, biase, totale.
  * out: [n_frames][nds_frame_width()][dump_walkers].                                             */
-int nds_frame_width(const nds_engine* e);
-int64_t nds_frames_pending(const nds_engine* e);
-int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n_frames);
+NDS_API int nds_frame_width(const nds_engine* e);
+NDS_API int64_t nds_frames_pending(const nds_engine* e);
+NDS_API int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n_frames);
 
 /* free-energy estimate of the reference: sum of hills on a grid (bias/gaus.py:365-393 with the
  * grid of io/plot.py:517-519).  grid[ny][nx], X = x0 + i*dx, Y = y0 + j*dy.                     */
-int nds_fes_grid(nds_engine* e, int64_t walker, double x0, double dx, int64_t nx, double y0,
+NDS_API int nds_fes_grid(nds_engine* e, int64_t walker, double x0, double dx, int64_t nx, double y0,
                  double dy, int64_t ny, double* grid);
 
 /* on-device histogram of the current colvar values of all local walkers (io/plot.py:562-572).
  * counts[ny][nx] (ny = 1 for colvardim 1).                                                       */
-int nds_colvar_histogram(nds_engine* e, double x0, double dx, int64_t nx, double y0, double dy,
+NDS_API int nds_colvar_histogram(nds_engine* e, double x0, double dx, int64_t nx, double y0, double dy,
                          int64_t ny, int64_t* counts);
 
 /* raw device pointers for zero-copy plumbing (torch / NCCL): positions, velocities (engine
  * precision, SoA [ndim][M]) and the hill table (records of (colvardim + 1) reals, padded to 4). */
-int nds_device_pointers(nds_engine* e, void** x, void** v, void** hills, int64_t* hill_stride);
-void* nds_stream(nds_engine* e);          /* cudaStream_t of the engine */
-int64_t nds_n_hills(const nds_engine* e, int64_t walker);
+NDS_API int nds_device_pointers(nds_engine* e, void** x, void** v, void** hills, int64_t* hill_stride);
+NDS_API void* nds_stream(nds_engine* e);          /* cudaStream_t of the engine */
+NDS_API int64_t nds_n_hills(const nds_engine* e, int64_t walker);
 
 /* launches issued since creation (bench.py "gpu_launches") and duration of the last nds_run in
  * milliseconds measured with CUDA events on the engine's stream.                                */
-int64_t nds_launch_count(const nds_engine* e);
-double nds_last_run_ms(nds_engine* e);
+NDS_API int64_t nds_launch_count(const nds_engine* e);
+NDS_API double nds_last_run_ms(nds_engine* e);
 /* name of the kernel variant selected for the hot loop ("md_block<f32,2,Mueller2d,...>") */
-const char* nds_kernel_name(const nds_engine* e);
+NDS_API const char* nds_kernel_name(const nds_engine* e);
 
 /* Philox4x32-10 known-answer hook (tests): out[4] = philox(ctr[4], key[2]) computed ON DEVICE.  */
-int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+NDS_API int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 
 #ifdef __cplusplus
 }

@@ -322,6 +322,7 @@ def parse(config: dict) -> RunSpec:
     spec.precision = cfg.get("precision", "f64")
     spec.steps_per_launch = int(cfg.get("steps_per_launch", 1000))
     spec.device = int(cfg.get("device", 0))
+    spec.noise_mode = int(cfg.get("noise_mode", _abi.NDS_NOISE_PHILOX))
     spec.dump_walkers = int(cfg.get("dump_walkers", 1))
     spec.mtd_shared = bool(cfg.get("mtd_shared", True))
     spec.umb_per_walker = bool(cfg.get("umb_per_walker", False))

@@ -1,0 +1,91 @@
+// nds_common.cuh -- shared host/device definitions of the B200 multi-walker engine.
+//
+// Device-side constants, kernel argument blocks and the compile-time "Spec" that selects a kernel
+// variant.  A Spec field equal to DYN means "read the choice from the constant block at run time"
+// (generic kernels); a non-negative value bakes the choice into the kernel (hot-path variants).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/ndsb200.h"
+
+namespace nds {
+
+constexpr int DYN = -1;
+
+// bias bit mask
+constexpr int BIAS_UMB = 1;         // >= 1 harmonic restraint (bias/umb.py)
+constexpr int BIAS_MTD = 2;         // metadynamics hill sum (bias/gaus.py)
+constexpr int BIAS_PE = 4;          // potential-energy bias (bias/pe.py)
+constexpr int BIAS_UMB_WALKER = 8;  // restraint 0 takes (k, r0) per walker
+
+template <typename R_, int ND_, int POT_ = DYN, int CV_ = DYN, int TCV_ = DYN, int INTEG_ = DYN,
+          int BIAS_ = DYN, int METHOD_ = DYN, int NOISE_ = DYN, int DUMP_ = DYN>
+struct Spec {
+  using R = R_;
+  static constexpr int ND = ND_;
+  static constexpr int POT = POT_;
+  static constexpr int CV = CV_;
+  static constexpr int TCV = TCV_;
+  static constexpr int INTEG = INTEG_;
+  static constexpr int BIAS = BIAS_;
+  static constexpr int METHOD = METHOD_;
+  static constexpr int NOISE = NOISE_;
+  static constexpr int DUMP = DUMP_;
+};
+
+// Uniform constants of a run (one copy per engine, passed by value to every kernel).
+template <typename R>
+struct Consts {
+  int ndim, cd, tcd;
+  int pot, cv, tcv, integ, method, noise, bias_mask, n_umb, n_basins;
+  int mtd_shared, hill_stride;  // reals per hill record (cd + 1, padded to 4 when cd == 2)
+  // units / integrator (engines/md.py:81-99, data.py:26-28, constant.py)
+  R m, inv_m, dt, kB, kBT;
+  R c1, c2, c3, c4, c5, v_target;
+  R hdtm;           // dt / (2 m): fused half-kick factor of the fp32 path
+  R vel_scale;      // sqrt(kB * T_init / m)  (engines/modify.py:45)
+  double dt64, rescale_freq;
+  // four-Gaussian surfaces (Mueller*: potentials/mueller.py:8-16; ThreeHole*: three_hole.py:10-22)
+  R gA[4], ga[4], gb[4], gc[4], gx[4], gy[4];
+  // fp32 fast form: G = k*grad (k = log2(e)/2), A2 = A / k  (see nds_physics.cuh)
+  R fa[4], fb[4], fc[4], fA[4];
+  R th_D, th_E, th_x1, th_y1, th_ref;
+  R rot;            // 1/sqrt(2) as NumPy computes it (colvars/two.py:53)
+  // DoubleWell(1d): K1, K2, x1[2], x2[2], invsigma2 (double_well.py:9-53)
+  R dw_K1, dw_K2, dw_x1[2], dw_x2[2], dw_invsig2;
+  // biases
+  R umb_k[NDS_MAX_UMB][NDS_MAX_CV], umb_r0[NDS_MAX_UMB][NDS_MAX_CV];
+  R mtd_w, mtd_invsig2[NDS_MAX_CV], mtd_kBdT;  // kB*(biasf-1)*T, gaus.py:102-103
+  R mtd_pre[NDS_MAX_CV];  // fp32 fast form: sqrt(log2(e) / 2) / sigma
+  R pe_thred;
+  R crit[NDS_MAX_BASINS][NDS_MAX_CV][2];
+  long long diffusion_time;
+  long long dump_freq, stat_freq, dump_walkers;
+  unsigned int key0, key1;  // Philox key = seed
+};
+
+// Per-launch arguments of the fused step kernel.
+template <typename R>
+struct BlockArgs {
+  long long M;             // local walkers
+  long long walker_offset; // global id of local walker 0
+  long long step0;         // NDRun.step before the first step of this launch
+  long long nsteps;        // steps to run in this launch
+  double time0;            // NDRun.time before the first step (fp64 accumulation, ndrun.py:240)
+  long long rescale_count; // MD.rescale_count at launch start (md.py:77,220-222)
+  // state, SoA [d][M]
+  R* x; R* v; R* f; R* fixf; R* colv; R* thermo; R* vr;
+  const R* umb_k; const R* umb_r0;     // per-walker window [cd][M] or null
+  unsigned char* alive; int* basin; long long* exit_step;  // committor
+  // hills
+  const R* hills; long long n_hills;
+  int refresh_vr;          // 1: the launch follows a deposition (or begin): store V_mtd into vr[]
+  int need_init_v;         // 1: draw Maxwell-Boltzmann velocities first (modify.py:44-54)
+  int begin_mode;          // 1: NDRun.begin semantics: totale = ke + pe, bias omitted (ndrun.py:196)
+  // external noise table [step - noise_first][j][M] (parity tests)
+  const double* noise; long long noise_first;
+  // frames
+  double* frames; long long frame_base; long long frame_cap; int frame_width;
+};
+
+}  // namespace nds

@@ -1,0 +1,873 @@
+// nds_engine.cu -- host side of the C ABI (include/ndsb200.h): configuration checks, device memory,
+// the launch loop that replaces NDRun.run (ndrun.py:214-251) with fused K-step launches, the
+// metadynamics deposition schedule (bias/gaus.py:130-146) and the data movers.
+//
+// There is no CPU path in this file: every entry point that computes launches a kernel.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nds_variants.h"
+
+using namespace nds;
+
+// ---------------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+struct nds_engine {
+  std::string err;
+  virtual ~nds_engine() {}
+  virtual int set_state(const double* x, const double* v) = 0;
+  virtual int set_walker_bias(const double* k, const double* r0) = 0;
+  virtual int set_noise(const double* noise, int64_t first, int64_t nsteps) = 0;
+  virtual int begin() = 0;
+  virtual int run(int64_t nsteps) = 0;
+  virtual int sync() = 0;
+  virtual int get_state(double* x, double* v, double* f, double* fixf, double* colv, double* thermo) = 0;
+  virtual int eval_at(const double* x, int64_t n, double* V, double* F, double* colv, double* J,
+                      double* Vb, double* Fb) = 0;
+  virtual int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) = 0;
+  virtual int set_hills(int64_t walker, int64_t n, const double* centers, const double* heights) = 0;
+  virtual int get_vr(double* vr) = 0;
+  virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
+  virtual int64_t count_alive() = 0;
+  virtual int drain_frames(double* out, int64_t max_frames, int64_t* n_frames) = 0;
+  virtual int fes_grid(int64_t walker, double x0, double dx, int64_t nx, double y0, double dy,
+                       int64_t ny, double* grid) = 0;
+  virtual int histogram(double x0, double dx, int64_t nx, double y0, double dy, int64_t ny,
+                        int64_t* counts) = 0;
+  virtual int device_pointers(void** x, void** v, void** hills, int64_t* stride) = 0;
+  virtual double last_run_ms() = 0;
+
+  nds_config cfg;
+  int cd = 0, tcd = 0;
+  int64_t step = 0;
+  double time = 0.0;
+  int64_t n_hills = 0;
+  int64_t launches = 0;
+  int64_t frames_written = 0;  // frames in the ring since the last drain
+  int frame_width = 0;
+  cudaStream_t stream = nullptr;
+  const char* kernel_name = "";
+  nds_exchange_fn exchange = nullptr;
+  void* exchange_user = nullptr;
+};
+
+static int fail(nds_engine* e, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (e) e->err = buf;
+  return 1;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(this, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, \
+                  __LINE__, #call);                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------ validation
+static const int kPotNdim[NDS_POT_COUNT] = {2, 5, 5, 1, 2, 2, 5, 2, 2, 1, 2};
+static const bool kPotNeedsTcv[NDS_POT_COUNT] = {false, true, true, false, false, true, true,
+                                                 false, false, false, false};
+
+extern "C" int nds_colvar_dim(int cv, int ndim) {
+  switch (cv) {
+    case NDS_CV_ORIGINAL: return (ndim == 1 || ndim == 2 || ndim == 5) ? ndim : -1;
+    case NDS_CV_EXTRACTX: case NDS_CV_EXTRACTY: case NDS_CV_XMY: case NDS_CV_XPY:
+    case NDS_CV_PROJ2DTO1D: return ndim == 2 ? 1 : -1;
+    case NDS_CV_ROTATE2D: return ndim == 2 ? 2 : -1;
+    case NDS_CV_PROJ5DTO1DX0: case NDS_CV_PROJ5DTO1DX2: case NDS_CV_PROJ5DTO1D:
+      return ndim == 5 ? 1 : -1;
+    case NDS_CV_PROJ5DTO2D: case NDS_CV_PROJ5DTO2DV2: return ndim == 5 ? 2 : -1;
+    default: return -1;
+  }
+}
+
+static int validate(const nds_config* c) {
+  if (!c) return fail(nullptr, "nds_create: null config");
+  if (c->abi_version != NDS_ABI_VERSION)
+    return fail(nullptr, "nds_create: abi_version %d != %d", c->abi_version, NDS_ABI_VERSION);
+  if (c->precision != NDS_F32 && c->precision != NDS_F64) return fail(nullptr, "bad precision");
+  if (c->ndim != 1 && c->ndim != 2 && c->ndim != 5)
+    return fail(nullptr, "ndim=%d: the built-in potentials have ndim 1, 2 or 5", c->ndim);
+  if (c->potential < 0 || c->potential >= NDS_POT_COUNT) return fail(nullptr, "unknown potential id %d", c->potential);
+  if (kPotNdim[c->potential] != c->ndim)  // potentials/potential.py:12 (assert pointer.ndim == self.ndim)
+    return fail(nullptr, "potential %d has ndim=%d, run has ndim=%d", c->potential, kPotNdim[c->potential], c->ndim);
+  if (nds_colvar_dim(c->colvar, c->ndim) < 0) return fail(nullptr, "colvar %d is not defined for ndim=%d", c->colvar, c->ndim);
+  if (nds_colvar_dim(c->true_colvar, c->ndim) < 0) return fail(nullptr, "true_colvar %d is not defined for ndim=%d", c->true_colvar, c->ndim);
+  if (kPotNeedsTcv[c->potential] && nds_colvar_dim(c->true_colvar, c->ndim) != 2)
+    return fail(nullptr, "potential %d is evaluated in a 2-D true_colvar space", c->potential);
+  if (c->integrator < 0 || c->integrator > NDS_INT_RESCALE)  // md.py:59
+    return fail(nullptr, "unknown integrator %d", c->integrator);
+  if (c->integrator == NDS_INT_RESCALE && !(c->rescale_freq > 0))  // md.py:220 (TypeError on None)
+    return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
+  if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR) return fail(nullptr, "unknown method %d", c->method);
+  if (c->n_walkers <= 0) return fail(nullptr, "n_walkers must be positive");
+  if (c->n_walkers_global < c->walker_offset + c->n_walkers) return fail(nullptr, "n_walkers_global too small");
+  if (!(c->mass > 0) || !(c->dt > 0)) return fail(nullptr, "mass and dt must be positive");
+  if (c->n_umb < 0 || c->n_umb > NDS_MAX_UMB) return fail(nullptr, "n_umb out of range");
+  if (c->umb_per_walker && c->n_umb < 1) return fail(nullptr, "umb_per_walker needs n_umb >= 1");
+  if (c->mtd_enabled) {
+    if (!(c->mtd_biasf > 1.0))  // gaus.py:102-103,187 divide by kB*(biasf-1)*T
+      return fail(nullptr, "mtd_biasf must be > 1");
+    if (!(c->mtd_dep_freq > 0)) return fail(nullptr, "mtd_dep_freq must be positive");
+    if (c->mtd_capacity <= 0) return fail(nullptr, "mtd_capacity must be positive");
+    for (int k = 0; k < nds_colvar_dim(c->colvar, c->ndim); k++)
+      if (!(c->mtd_sigma[k] > 0)) return fail(nullptr, "mtd_sigma[%d] must be positive", k);
+  }
+  if (c->method == NDS_METHOD_COMMITTOR) {
+    if (c->n_basins < 1 || c->n_basins > NDS_MAX_BASINS) return fail(nullptr, "n_basins out of range");
+    if (c->temperature == 0) return fail(nullptr, "committor at temperature 0 (Minimize engine) is out of scope");
+  }
+  if (c->steps_per_launch <= 0) return fail(nullptr, "steps_per_launch must be positive");
+  if (c->dump_freq > 0 && c->dump_walkers > 0 && c->dump_capacity <= 0)
+    return fail(nullptr, "dump_capacity must be positive when frames are recorded");
+  return 0;
+}
+
+// ------------------------------------------------------------------------- constant block
+static const double kB_ = 8.6173303e-5;  // constant.py:2
+static double au_mass_() {               // constant.py:12
+  const double eV = 1.60217733e-19, angstrom = 1.0e-10, fs = 1e-15;
+  return 1.67e-27 / (eV / angstrom * fs / angstrom * fs);
+}
+
+template <typename R>
+static void fill_consts(const nds_config& c, Consts<R>& K) {
+  memset(&K, 0, sizeof K);
+  const double kcal = 0.04337209302, escale = 0.2, lscale = 16.0;  // constant.py:10-15
+  K.ndim = c.ndim;
+  K.cd = nds_colvar_dim(c.colvar, c.ndim);
+  K.tcd = nds_colvar_dim(c.true_colvar, c.ndim);
+  K.pot = c.potential; K.cv = c.colvar; K.tcv = c.true_colvar; K.integ = c.integrator;
+  K.method = c.method; K.noise = c.noise_mode; K.n_umb = c.n_umb; K.n_basins = c.n_basins;
+  K.bias_mask = (c.n_umb > 0 ? BIAS_UMB : 0) | (c.mtd_enabled ? BIAS_MTD : 0) |
+                (c.pe_enabled ? BIAS_PE : 0) | ((c.n_umb > 0 && c.umb_per_walker) ? BIAS_UMB_WALKER : 0);
+  K.mtd_shared = c.mtd_shared;
+  K.hill_stride = (K.cd == 2) ? 4 : K.cd + 1;
+  const double m = au_mass_() * c.mass;        // data.py:27-28
+  const double kBT = kB_ * c.temperature;      // data.py:26
+  const double dt = c.dt, gamma = c.gamma;
+  K.m = (R)m; K.inv_m = (R)(1.0 / m); K.dt = (R)dt; K.kB = (R)kB_; K.kBT = (R)kBT;
+  K.dt64 = dt; K.rescale_freq = c.rescale_freq;
+  K.hdtm = (R)(dt / (2.0 * m));
+  K.vel_scale = (R)std::sqrt(kB_ * c.initial_temperature / m);  // modify.py:45
+  if (c.integrator == NDS_INT_LANGEVIN) {      // md.py:83-86
+    const double c1 = std::exp(-gamma * dt / 2.0);
+    K.c1 = (R)c1; K.c2 = (R)std::sqrt((1 - c1 * c1) * kBT / m);
+  } else if (c.integrator == NDS_INT_LANGEVIN2) {  // md.py:87-97
+    const double frdt = (1.0 - std::exp(-gamma * dt / 2.0)) * 8.0;
+    const double sigma = std::sqrt(2 * kBT * frdt / m);
+    const double c5 = std::sqrt(dt) * sigma / (2 * std::sqrt((double)c.ndim));
+    K.c1 = (R)(dt / 2.0 - dt * frdt / 8.0);
+    K.c2 = (R)(frdt / 2 - frdt * frdt / 8.0);
+    K.c3 = (R)(std::sqrt(dt) * sigma / 2.0 * (1.0 - frdt / 4.0));
+    K.c5 = (R)c5;
+    K.c4 = (R)(frdt / 2.0 * c5);
+  } else if (c.integrator == NDS_INT_RESCALE) {  // md.py:76-79
+    K.v_target = (R)std::sqrt(kBT * c.ndim / m);
+  }
+  double A[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+  double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0};
+  const int pot = c.potential;
+  if (pot == NDS_POT_MUELLER2D || pot == NDS_POT_MUELLER5D || pot == NDS_POT_MUELLER5DSHL) {
+    const double A0[4] = {-200, -100, -170, 15}, a0[4] = {-1, -1, -6.5, 0.7};  // mueller.py:8-11
+    const double b0[4] = {0, 0, 11, 0.6}, c0[4] = {-10, -10, -6.5, 0.7};
+    for (int i = 0; i < 4; i++) {
+      A[i] = A0[i] * kcal * escale;
+      if (pot == NDS_POT_MUELLER5DSHL) A[i] = A[i] / 5;  // mueller.py:157
+      a[i] = a0[i] / (lscale * lscale); b[i] = b0[i] / (lscale * lscale); cc[i] = c0[i] / (lscale * lscale);
+      gx[i] = c.pot_params[i]; gy[i] = c.pot_params[4 + i];  // mueller.py:15-16
+    }
+  } else if (pot == NDS_POT_THREEHOLE2D || pot == NDS_POT_THREEHOLE5D) {  // three_hole.py:10-22
+    const double es = 2.0, ls = 4.0;
+    const double A0[4] = {3, -3, -5, -5}, x0r[4] = {0, 0, 1, -1}, y0r[4] = {1 / 3.0, 5 / 3.0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+      A[i] = A0[i] / es; a[i] = -1 / (ls * ls); b[i] = 0 / (ls * ls); cc[i] = -1 / (ls * ls);
+      gx[i] = x0r[i] * ls + 7.5; gy[i] = y0r[i] * ls + 7.5;
+    }
+    K.th_D = (R)(0.2 / std::pow(ls, 4) / es); K.th_E = (R)(0.2 / std::pow(ls, 4) / es);
+    K.th_x1 = (R)(0 * ls + 7.5); K.th_y1 = (R)(1 / 3.0 * ls + 7.5); K.th_ref = (R)2;
+  } else if (pot == NDS_POT_GAUSSIAN2D) {  // misc.py:9-13
+    A[0] = -200.0 * kcal * escale; a[0] = -1.0 / (lscale * lscale); cc[0] = -10.0 / (lscale * lscale);
+  }
+  const double kfast = 0.5 * 1.4426950408889634;  // log2(e) / 2
+  for (int i = 0; i < 4; i++) {
+    K.gA[i] = (R)A[i]; K.ga[i] = (R)a[i]; K.gb[i] = (R)b[i]; K.gc[i] = (R)cc[i];
+    K.gx[i] = (R)gx[i]; K.gy[i] = (R)gy[i];
+    K.fa[i] = (R)(2 * a[i] * kfast); K.fb[i] = (R)(b[i] * kfast); K.fc[i] = (R)(2 * cc[i] * kfast);
+    K.fA[i] = (R)(A[i] / kfast);
+  }
+  K.rot = (R)(1.0 / std::sqrt(2.0));  // two.py:53
+  if (pot == NDS_POT_DOUBLEWELL1D) {  // double_well.py:9-14
+    K.dw_K1 = (R)c.pot_params[0]; K.dw_K2 = (R)c.pot_params[1];
+    K.dw_x1[0] = (R)c.pot_params[2]; K.dw_x2[0] = (R)c.pot_params[3];
+    K.dw_invsig2 = (R)(1.0 / c.pot_params[4] / c.pot_params[4]);
+  } else if (pot == NDS_POT_DOUBLEWELL) {  // double_well.py:37-42
+    K.dw_K1 = (R)c.pot_params[0]; K.dw_K2 = (R)c.pot_params[1];
+    K.dw_x1[0] = (R)c.pot_params[2]; K.dw_x1[1] = (R)c.pot_params[3];
+    K.dw_x2[0] = (R)c.pot_params[4]; K.dw_x2[1] = (R)c.pot_params[5];
+    K.dw_invsig2 = (R)(1.0 / c.pot_params[6] / c.pot_params[6]);
+  }
+  for (int u = 0; u < NDS_MAX_UMB; u++)
+    for (int k = 0; k < NDS_MAX_CV; k++) { K.umb_k[u][k] = (R)c.umb_k[u][k]; K.umb_r0[u][k] = (R)c.umb_r0[u][k]; }
+  if (c.mtd_enabled) {
+    K.mtd_w = (R)c.mtd_w;
+    for (int k = 0; k < K.cd; k++) {
+      K.mtd_invsig2[k] = (R)(1.0 / (c.mtd_sigma[k] * c.mtd_sigma[k]));  // gaus.py:90-91
+      K.mtd_pre[k] = (R)(std::sqrt(kfast) / c.mtd_sigma[k]);
+    }
+    K.mtd_kBdT = (R)(kB_ * ((c.mtd_biasf - 1) * c.temperature));  // gaus.py:102-103
+  }
+  K.pe_thred = (R)c.pe_thred;
+  for (int bb = 0; bb < NDS_MAX_BASINS; bb++)
+    for (int k = 0; k < NDS_MAX_CV; k++) { K.crit[bb][k][0] = (R)c.criteria[bb][k][0]; K.crit[bb][k][1] = (R)c.criteria[bb][k][1]; }
+  K.diffusion_time = c.diffusion_time;
+  const bool dumping = c.dump_freq > 0 && c.dump_walkers > 0;
+  K.dump_freq = dumping ? c.dump_freq : 0;
+  K.stat_freq = c.stat_freq > 0 ? c.stat_freq : 1;
+  K.dump_walkers = dumping ? (c.dump_walkers < c.n_walkers ? c.dump_walkers : c.n_walkers) : 0;
+  K.key0 = (unsigned)(c.seed & 0xffffffffull);
+  K.key1 = (unsigned)(c.seed >> 32);
+}
+
+// -------------------------------------------------------------------------- variant lookup
+static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dumping) {
+  typedef const Variant* (*table_fn)(int*);
+  static const table_fn tables[] = {variants_hot,
+                                    variants_generic_f32_nd1, variants_generic_f32_nd2,
+                                    variants_generic_f32_nd5, variants_generic_f64_nd1,
+                                    variants_generic_f64_nd2, variants_generic_f64_nd5};
+  const Variant* best = nullptr;
+  int best_score = -1;
+  const int want[10] = {c.precision, c.ndim, c.potential, c.colvar, c.true_colvar, c.integrator,
+                        bias_mask, c.method, c.noise_mode, dumping ? 1 : 0};
+  for (table_fn t : tables) {
+    int n = 0;
+    const Variant* v = t(&n);
+    for (int i = 0; i < n; i++) {
+      const int have[10] = {v[i].key.prec, v[i].key.nd, v[i].key.pot, v[i].key.cv, v[i].key.tcv,
+                            v[i].key.integ, v[i].key.bias, v[i].key.method, v[i].key.noise, v[i].key.dump};
+      bool ok = true;
+      int score = 0;
+      for (int k = 0; k < 10 && ok; k++) {
+        if (have[k] == DYN) continue;
+        if (have[k] != want[k]) ok = false; else score++;
+      }
+      if (ok && score > best_score) { best = &v[i]; best_score = score; }
+    }
+  }
+  return best;
+}
+
+static __global__ void philox_kat_kernel(u32x4 c, uint32_t k0, uint32_t k1, uint32_t* out) {
+  const u32x4 r = philox4x32_10(c, k0, k1);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+static __global__ void count_alive_kernel(long long M, const unsigned char* alive, unsigned long long* out) {
+  unsigned long long local = 0;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < M; w += (long long)gridDim.x * blockDim.x)
+    local += alive[w] ? 1ull : 0ull;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// ----------------------------------------------------------------------------------- engine
+template <typename R>
+struct Engine : nds_engine {
+  Consts<R> K;
+  int64_t M = 0;
+  int nd = 0;
+  BlockLaunchFn<R> launch_block = nullptr;
+  // device state
+  R *d_x = nullptr, *d_v = nullptr, *d_f = nullptr, *d_fixf = nullptr, *d_colv = nullptr;
+  R *d_thermo = nullptr, *d_vr = nullptr, *d_umb_k = nullptr, *d_umb_r0 = nullptr, *d_hills = nullptr;
+  unsigned char* d_alive = nullptr;
+  int* d_basin = nullptr;
+  long long* d_exit = nullptr;
+  double* d_frames = nullptr;
+  double* d_noise = nullptr;
+  int64_t noise_first = 0, noise_steps = 0;
+  double* d_stage = nullptr;  // fp64 staging for host <-> device conversion
+  int64_t stage_elems = 0;
+  unsigned long long* d_counter = nullptr;
+  bool have_v = false, begun = false, need_refresh_vr = true;
+  int64_t dep_count = 0, rescale_count = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+
+  ~Engine() override {
+    cudaSetDevice(cfg.device);
+    for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
+                    (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
+                    (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
+                    (void*)d_counter})
+      if (p) cudaFree(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int64_t hill_elems() const {
+    return cfg.mtd_capacity * (int64_t)K.hill_stride * (cfg.mtd_shared ? 1 : M);
+  }
+
+  int init(const nds_config& c) {
+    cfg = c;
+    M = c.n_walkers;
+    nd = c.ndim;
+    fill_consts<R>(c, K);
+    cd = K.cd; tcd = K.tcd;
+    CU(cudaSetDevice(c.device));
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    const bool dumping = K.dump_freq > 0;
+    const Variant* var = pick_variant(c, K.bias_mask, dumping);
+    if (!var) return fail(this, "no compiled md_block variant matches this configuration");
+    launch_block = (BlockLaunchFn<R>)var->launch;
+    kernel_name = var->name;
+    const size_t sM = (size_t)M;
+    CU(cudaMalloc(&d_x, sizeof(R) * nd * sM));
+    CU(cudaMalloc(&d_v, sizeof(R) * nd * sM));
+    CU(cudaMalloc(&d_f, sizeof(R) * nd * sM));
+    CU(cudaMalloc(&d_fixf, sizeof(R) * nd * sM));
+    CU(cudaMalloc(&d_colv, sizeof(R) * cd * sM));
+    CU(cudaMalloc(&d_thermo, sizeof(R) * 5 * sM));
+    CU(cudaMalloc(&d_vr, sizeof(R) * sM));
+    CU(cudaMemsetAsync(d_x, 0, sizeof(R) * nd * sM, stream));
+    CU(cudaMemsetAsync(d_v, 0, sizeof(R) * nd * sM, stream));
+    CU(cudaMemsetAsync(d_vr, 0, sizeof(R) * sM, stream));
+    if (K.bias_mask & BIAS_UMB_WALKER) {
+      CU(cudaMalloc(&d_umb_k, sizeof(R) * cd * sM));
+      CU(cudaMalloc(&d_umb_r0, sizeof(R) * cd * sM));
+      std::vector<double> k((size_t)cd * sM), r0((size_t)cd * sM);
+      for (int q = 0; q < cd; q++)
+        for (size_t w = 0; w < sM; w++) { k[q * sM + w] = c.umb_k[0][q]; r0[q * sM + w] = c.umb_r0[0][q]; }
+      if (upload(k.data(), d_umb_k, (int64_t)cd * M)) return 1;
+      if (upload(r0.data(), d_umb_r0, (int64_t)cd * M)) return 1;
+    }
+    if (c.mtd_enabled) {
+      CU(cudaMalloc(&d_hills, sizeof(R) * (size_t)hill_elems()));
+      CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)hill_elems(), stream));
+    }
+    if (c.method == NDS_METHOD_COMMITTOR) {
+      CU(cudaMalloc(&d_alive, sM));
+      CU(cudaMalloc(&d_basin, sizeof(int) * sM));
+      CU(cudaMalloc(&d_exit, sizeof(long long) * sM));
+      CU(cudaMemsetAsync(d_alive, 1, sM, stream));
+      CU(cudaMemsetAsync(d_basin, 0xff, sizeof(int) * sM, stream));
+      CU(cudaMemsetAsync(d_exit, 0, sizeof(long long) * sM, stream));
+    }
+    CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
+    frame_width = 2 + 3 * nd + cd + 6;
+    if (dumping) {
+      const size_t n = (size_t)c.dump_capacity * frame_width * (size_t)K.dump_walkers;
+      CU(cudaMalloc(&d_frames, sizeof(double) * n));
+      CU(cudaMemsetAsync(d_frames, 0xff, sizeof(double) * n, stream));  // NaN pattern
+    }
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // ---- host <-> device movers (host side is always fp64)
+  int ensure_stage(int64_t n) {
+    if (n <= stage_elems) return 0;
+    if (d_stage) CU(cudaFree(d_stage));
+    CU(cudaMalloc(&d_stage, sizeof(double) * (size_t)n));
+    stage_elems = n;
+    return 0;
+  }
+  int upload(const double* h, R* d, int64_t n) {
+    if (sizeof(R) == sizeof(double)) {
+      CU(cudaMemcpyAsync(d, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    } else {
+      if (ensure_stage(n)) return 1;
+      CU(cudaMemcpyAsync(d_stage, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream));
+      convert_kernel<R><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, d_stage, d);
+      CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(stream));  // the host buffer may be reused by the caller
+    return 0;
+  }
+  int download(const R* d, double* h, int64_t n) {
+    if (sizeof(R) == sizeof(double)) {
+      CU(cudaMemcpyAsync(h, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    } else {
+      if (ensure_stage(n)) return 1;
+      convert_back_kernel<R><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, d, d_stage);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(h, d_stage, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  int set_state(const double* x, const double* v) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!x) return fail(this, "nds_set_state: x is null");
+    if (upload(x, d_x, (int64_t)nd * M)) return 1;
+    if (v) { if (upload(v, d_v, (int64_t)nd * M)) return 1; }
+    // positions + velocities given: a running simulation continues from the new state (the next
+    // launch re-evaluates forces at entry); positions only: velocities are re-drawn by nds_begin()
+    if (!v) { have_v = false; begun = false; }
+    else have_v = true;
+    return 0;
+  }
+
+  int set_walker_bias(const double* k, const double* r0) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!(K.bias_mask & BIAS_UMB_WALKER)) return fail(this, "nds_set_walker_bias: config has umb_per_walker = 0");
+    if (upload(k, d_umb_k, (int64_t)cd * M)) return 1;
+    return upload(r0, d_umb_r0, (int64_t)cd * M);
+  }
+
+  int set_noise(const double* noise, int64_t first, int64_t nsteps) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.noise_mode != NDS_NOISE_EXTERNAL) return fail(this, "nds_set_noise: noise_mode is not NDS_NOISE_EXTERNAL");
+    const int nn = normals_per_step(cfg.integrator, nd);
+    if (d_noise) { CU(cudaFree(d_noise)); d_noise = nullptr; }
+    const size_t n = (size_t)nsteps * nn * (size_t)M;
+    if (n) {
+      CU(cudaMalloc(&d_noise, sizeof(double) * n));
+      CU(cudaMemcpyAsync(d_noise, noise, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+    }
+    noise_first = first; noise_steps = nsteps;
+    return 0;
+  }
+
+  BlockArgs<R> make_args(int64_t nsteps) {
+    BlockArgs<R> A;
+    memset(&A, 0, sizeof A);
+    A.M = M; A.walker_offset = cfg.walker_offset;
+    A.step0 = step; A.nsteps = nsteps; A.time0 = time; A.rescale_count = rescale_count;
+    A.x = d_x; A.v = d_v; A.f = d_f; A.fixf = d_fixf; A.colv = d_colv; A.thermo = d_thermo; A.vr = d_vr;
+    A.umb_k = d_umb_k; A.umb_r0 = d_umb_r0;
+    A.alive = d_alive; A.basin = d_basin; A.exit_step = d_exit;
+    A.hills = d_hills; A.n_hills = n_hills;
+    A.noise = d_noise; A.noise_first = noise_first;
+    A.frames = d_frames; A.frame_base = frames_written; A.frame_cap = cfg.dump_capacity;
+    A.frame_width = frame_width;
+    return A;
+  }
+
+  int begin() override {  // NDRun.begin (ndrun.py:182-206) + MD.begin (md.py:101-110)
+    CU(cudaSetDevice(cfg.device));
+    step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
+    BlockArgs<R> A = make_args(0);
+    A.refresh_vr = 1;
+    A.need_init_v = have_v ? 0 : 1;
+    A.begin_mode = 1;
+    cudaError_t err = launch_block(K, A, stream);
+    if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
+    launches++;
+    have_v = true; begun = true; need_refresh_vr = false;
+    if (K.dump_freq > 0) frames_written = 1;
+    return 0;
+  }
+
+  int deposit() {  // Gaussian.update -> _deposite (gaus.py:130-213), all live walkers together
+    const int64_t add = cfg.mtd_shared ? cfg.n_walkers_global : 1;
+    if (n_hills + add > cfg.mtd_capacity)
+      return fail(this, "hill table full: %lld + %lld > mtd_capacity %lld", (long long)n_hills,
+                  (long long)add, (long long)cfg.mtd_capacity);
+    deposit_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
+        K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, dep_count == 0 ? 1 : 0);
+    CU(cudaGetLastError());
+    launches++;
+    if (cfg.mtd_shared && exchange && cfg.n_walkers_global > M) {
+      // multi-GPU: complete the segment [n_hills, n_hills + n_walkers_global) with every rank's
+      // records.  The callback runs an in-place allgather on its own stream.
+      CU(cudaStreamSynchronize(stream));
+      const int64_t rec = (int64_t)K.hill_stride * (int64_t)sizeof(R);
+      const int rc = exchange(exchange_user, (void*)(d_hills + n_hills * K.hill_stride), M * rec,
+                              cfg.walker_offset * rec);
+      if (rc) return fail(this, "hill exchange callback failed (%d)", rc);
+    } else if (cfg.mtd_shared && cfg.n_walkers_global > M) {
+      return fail(this, "shared hills over several ranks need nds_set_exchange()");
+    }
+    n_hills += add;
+    dep_count += 1;
+    need_refresh_vr = true;
+    return 0;
+  }
+
+  int run(int64_t nsteps) override {  // the NDRun.run loop (ndrun.py:214-251)
+    CU(cudaSetDevice(cfg.device));
+    if (!begun) return fail(this, "nds_run before nds_begin");
+    if (cfg.noise_mode == NDS_NOISE_EXTERNAL && normals_per_step(cfg.integrator, nd) > 0) {
+      if (!d_noise || step < noise_first || step + nsteps > noise_first + noise_steps)
+        return fail(this, "external noise table does not cover steps [%lld, %lld)", (long long)step,
+                    (long long)(step + nsteps));
+    }
+    CU(cudaEventRecord(ev0, stream));
+    int64_t remaining = nsteps;
+    while (remaining > 0) {
+      int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
+      if (cfg.mtd_enabled) {
+        // fix.update(step, time) before the step (ndrun.py:227-228, gaus.py:134-136)
+        if ((int64_t)std::floor(time / cfg.mtd_dep_freq) + 1 > dep_count) {
+          if (deposit()) return 1;
+        }
+        // the launch ends right before the next step that would deposit
+        double t = time;
+        int64_t j = 0;
+        while (j < k) {
+          t += cfg.dt; j++;
+          if ((int64_t)std::floor(t / cfg.mtd_dep_freq) + 1 > dep_count) break;
+        }
+        k = j;
+      }
+      int64_t events = 0;
+      if (K.dump_freq > 0) {
+        for (int64_t s = step + 1; s <= step + k; s++) events += frame_event(s, K.dump_freq, K.stat_freq) ? 1 : 0;
+        if (frames_written + events > cfg.dump_capacity)
+          return fail(this, "frame ring full (%lld frames pending, capacity %lld): call nds_drain_frames",
+                      (long long)frames_written, (long long)cfg.dump_capacity);
+      }
+      BlockArgs<R> A = make_args(k);
+      A.refresh_vr = need_refresh_vr ? 1 : 0;
+      cudaError_t err = launch_block(K, A, stream);
+      if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
+      launches++;
+      need_refresh_vr = false;
+      for (int64_t j = 0; j < k; j++) {  // replay the walker-independent schedules on the host
+        if (cfg.integrator == NDS_INT_RESCALE) {
+          const int64_t count = (int64_t)std::floor(time / cfg.rescale_freq) + 1;  // md.py:220-222
+          if (count > rescale_count) rescale_count = count;
+        }
+        time += cfg.dt;  // ndrun.py:240
+      }
+      step += k;
+      frames_written += events;
+      remaining -= k;
+    }
+    CU(cudaEventRecord(ev1, stream));
+    timed = true;
+    return 0;
+  }
+
+  int sync() override {
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  double last_run_ms() override {
+    if (!timed) return 0.0;
+    cudaSetDevice(cfg.device);
+    if (cudaEventSynchronize(ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+  }
+
+  int get_state(double* x, double* v, double* f, double* fixf, double* colv, double* thermo) override {
+    CU(cudaSetDevice(cfg.device));
+    if (x && download(d_x, x, (int64_t)nd * M)) return 1;
+    if (v && download(d_v, v, (int64_t)nd * M)) return 1;
+    if (f && download(d_f, f, (int64_t)nd * M)) return 1;
+    if (fixf && download(d_fixf, fixf, (int64_t)nd * M)) return 1;
+    if (colv && download(d_colv, colv, (int64_t)cd * M)) return 1;
+    if (thermo && download(d_thermo, thermo, (int64_t)5 * M)) return 1;
+    return 0;
+  }
+
+  int eval_at(const double* x, int64_t n, double* V, double* F, double* colv, double* J, double* Vb,
+              double* Fb) override {
+    CU(cudaSetDevice(cfg.device));
+    if (n <= 0) return 0;
+    const size_t sn = (size_t)n;
+    const size_t total = sn * (size_t)(nd + 1 + nd + cd + cd * nd + 1 + nd);
+    R* buf = nullptr;
+    CU(cudaMalloc(&buf, sizeof(R) * total));
+    R* dx = buf; R* dV = dx + nd * sn; R* dF = dV + sn; R* dc = dF + nd * sn; R* dJ = dc + cd * sn;
+    R* dVb = dJ + (size_t)cd * nd * sn; R* dFb = dVb + sn;
+    int rc = upload(x, dx, (int64_t)nd * n);
+    if (!rc) {
+      const unsigned grid = (unsigned)((n + NDS_BLOCK - 1) / NDS_BLOCK);
+      const long long es = cfg.mtd_shared ? 1 : M;
+      if (nd == 1) eval_at_kernel<R, 1><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
+      else if (nd == 2) eval_at_kernel<R, 2><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
+      else eval_at_kernel<R, 5><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
+      cudaError_t err = cudaGetLastError();
+      if (err != cudaSuccess) rc = fail(this, "eval_at launch failed: %s", cudaGetErrorString(err));
+      launches++;
+    }
+    if (!rc && V) rc = download(dV, V, n);
+    if (!rc && F) rc = download(dF, F, (int64_t)nd * n);
+    if (!rc && colv) rc = download(dc, colv, (int64_t)cd * n);
+    if (!rc && J) rc = download(dJ, J, (int64_t)cd * nd * n);
+    if (!rc && Vb) rc = download(dVb, Vb, n);
+    if (!rc && Fb) rc = download(dFb, Fb, (int64_t)nd * n);
+    cudaStreamSynchronize(stream);
+    cudaFree(buf);
+    return rc;
+  }
+
+  int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) override {
+    CU(cudaSetDevice(cfg.device));
+    if (n) *n = n_hills;
+    if (!cfg.mtd_enabled || n_hills == 0 || (!centers && !heights)) return 0;
+    if (cap < n_hills) return fail(this, "nds_get_hills: capacity %lld < %lld hills", (long long)cap, (long long)n_hills);
+    if (!cfg.mtd_shared && (walker < 0 || walker >= M)) return fail(this, "nds_get_hills: bad walker");
+    const int rs = K.hill_stride;
+    const int64_t es = cfg.mtd_shared ? 1 : M;
+    const int64_t span = cfg.mtd_shared ? n_hills * rs : n_hills * rs * M;
+    std::vector<double> h((size_t)span);
+    if (download(d_hills, h.data(), span)) return 1;
+    const int64_t off = cfg.mtd_shared ? 0 : walker;
+    for (int64_t i = 0; i < n_hills; i++) {
+      for (int k = 0; k < cd; k++)
+        if (centers) centers[i * cd + k] = h[(size_t)((i * rs + k) * es + off)];
+      if (heights) heights[i] = h[(size_t)((i * rs + cd) * es + off)];
+    }
+    return 0;
+  }
+
+  int set_hills(int64_t walker, int64_t n, const double* centers, const double* heights) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!cfg.mtd_enabled) return fail(this, "nds_set_hills: metadynamics is not enabled");
+    if (n > cfg.mtd_capacity) return fail(this, "nds_set_hills: %lld hills > capacity", (long long)n);
+    const int rs = K.hill_stride;
+    if (cfg.mtd_shared) {
+      std::vector<double> h((size_t)(n * rs), 0.0);
+      for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
+        h[(size_t)(i * rs + cd)] = heights[i];
+      }
+      if (n && upload(h.data(), d_hills, n * rs)) return 1;
+    } else {
+      // per-walker tables: the given hills are installed for EVERY walker (walker < 0) or one walker
+      std::vector<double> h((size_t)(cfg.mtd_capacity * rs * M));
+      if (download(d_hills, h.data(), (int64_t)h.size())) return 1;
+      for (int64_t w = 0; w < M; w++) {
+        if (walker >= 0 && w != walker) continue;
+        for (int64_t i = 0; i < n; i++) {
+          for (int k = 0; k < cd; k++) h[(size_t)((i * rs + k) * M + w)] = centers[i * cd + k];
+          h[(size_t)((i * rs + cd) * M + w)] = heights[i];
+        }
+      }
+      if (upload(h.data(), d_hills, (int64_t)h.size())) return 1;
+    }
+    n_hills = n;
+    need_refresh_vr = false;
+    return 0;
+  }
+
+  int get_vr(double* vr) override {
+    CU(cudaSetDevice(cfg.device));
+    return download(d_vr, vr, M);
+  }
+
+  int get_commit(int32_t* basin, int64_t* exit_step) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_COMMITTOR) return fail(this, "nds_get_commit: method is not committor");
+    CU(cudaStreamSynchronize(stream));
+    if (basin) CU(cudaMemcpy(basin, d_basin, sizeof(int) * (size_t)M, cudaMemcpyDeviceToHost));
+    if (exit_step) {
+      std::vector<unsigned char> alive((size_t)M);
+      CU(cudaMemcpy(exit_step, d_exit, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(alive.data(), d_alive, (size_t)M, cudaMemcpyDeviceToHost));
+      for (int64_t w = 0; w < M; w++)
+        if (alive[(size_t)w]) exit_step[w] = step;  // uncommitted: ran all steps (ndrun.py:220)
+    }
+    return 0;
+  }
+
+  int64_t count_alive() override {
+    if (cfg.method != NDS_METHOD_COMMITTOR) return M;
+    cudaSetDevice(cfg.device);
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+    count_alive_kernel<<<296, 256, 0, stream>>>(M, d_alive, d_counter);
+    launches++;
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, d_counter, sizeof h, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    return (int64_t)h;
+  }
+
+  int drain_frames(double* out, int64_t max_frames, int64_t* n_frames) override {
+    CU(cudaSetDevice(cfg.device));
+    const int64_t n = frames_written < max_frames ? frames_written : max_frames;
+    if (n_frames) *n_frames = n;
+    if (n <= 0 || !out) return 0;
+    if (n != frames_written) return fail(this, "nds_drain_frames: buffer holds %lld frames, %lld pending", (long long)max_frames, (long long)frames_written);
+    const size_t cnt = (size_t)n * frame_width * (size_t)K.dump_walkers;
+    CU(cudaMemcpyAsync(out, d_frames, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemsetAsync(d_frames, 0xff, sizeof(double) * cnt, stream));
+    CU(cudaStreamSynchronize(stream));
+    frames_written = 0;
+    return 0;
+  }
+
+  int fes_grid(int64_t walker, double x0, double dx, int64_t nx, double y0, double dy, int64_t ny,
+               double* grid) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!cfg.mtd_enabled) return fail(this, "nds_fes_grid: metadynamics is not enabled");
+    if (cd > 2) return fail(this, "nds_fes_grid: colvardim %d > 2", cd);
+    if (cd == 1) ny = 1;
+    const int64_t np = nx * ny;
+    double* d_grid = nullptr;
+    CU(cudaMalloc(&d_grid, sizeof(double) * (size_t)np));
+    const R* base = cfg.mtd_shared ? d_hills : d_hills + walker;
+    fes_grid_kernel<R><<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(
+        K, base, n_hills, cfg.mtd_shared ? 1 : M, x0, dx, nx, y0, dy, ny, d_grid);
+    launches++;
+    cudaError_t err = cudaMemcpyAsync(grid, d_grid, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d_grid);
+    if (err != cudaSuccess) return fail(this, "nds_fes_grid: %s", cudaGetErrorString(err));
+    return 0;
+  }
+
+  int histogram(double x0, double dx, int64_t nx, double y0, double dy, int64_t ny, int64_t* counts) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cd > 2) return fail(this, "nds_colvar_histogram: colvardim %d > 2", cd);
+    if (cd == 1) ny = 1;
+    const int64_t nb = nx * ny;
+    if (nb <= 0 || nb * (int64_t)sizeof(unsigned) > 48 * 1024)
+      return fail(this, "nds_colvar_histogram: %lld bins do not fit the shared-memory histogram (max 12288)", (long long)nb);
+    unsigned long long* d_counts = nullptr;
+    CU(cudaMalloc(&d_counts, sizeof(unsigned long long) * (size_t)nb));
+    CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (size_t)nb, stream));
+    histogram_kernel<R><<<296, 256, sizeof(unsigned) * (size_t)nb, stream>>>(
+        M, cd, d_colv, d_alive, x0, 1.0 / dx, (int)nx, y0, 1.0 / dy, (int)ny, d_counts);
+    launches++;
+    cudaError_t err = cudaMemcpyAsync(counts, d_counts, sizeof(unsigned long long) * (size_t)nb, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d_counts);
+    if (err != cudaSuccess) return fail(this, "nds_colvar_histogram: %s", cudaGetErrorString(err));
+    return 0;
+  }
+
+  int device_pointers(void** x, void** v, void** hills, int64_t* stride) override {
+    if (x) *x = d_x;
+    if (v) *v = d_v;
+    if (hills) *hills = d_hills;
+    if (stride) *stride = K.hill_stride;
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* nds_last_error(const nds_engine* e) { return e ? e->err.c_str() : g_last_error.c_str(); }
+
+void nds_config_defaults(nds_config* c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = NDS_ABI_VERSION;
+  c->precision = NDS_F64;
+  c->ndim = 2;
+  c->method = NDS_METHOD_MD;
+  c->integrator = NDS_INT_LANGEVIN;      // md.py:52
+  c->potential = NDS_POT_GAUSSIAN;       // potentials/_build.py:10
+  c->colvar = NDS_CV_ORIGINAL;           // colvars/_build.py:10
+  c->true_colvar = NDS_CV_ORIGINAL;
+  c->noise_mode = NDS_NOISE_PHILOX;
+  c->steps_per_launch = 1000;
+  c->n_walkers = 1; c->n_walkers_global = 1;
+  c->temperature = 300.0;                // ndrun.py:80
+  c->initial_temperature = 300.0;
+  c->mass = 5;                           // ndrun.py:81
+  c->dt = 0.5; c->gamma = 0.005;         // md.py:50-51
+  c->rescale_freq = -1.0;
+  const double xc[4] = {48, 32, 24, 16}, yc[4] = {8, 16, 32, 24};  // mueller.py:15-16
+  for (int i = 0; i < 4; i++) { c->pot_params[i] = xc[i]; c->pot_params[4 + i] = yc[i]; }
+  c->mtd_dep_freq = 10; c->mtd_biasf = 1.0;  // gaus.py:52-53
+  c->mtd_shared = 1;
+  c->stat_freq = 1;
+}
+
+int nds_create(const nds_config* cfg, nds_engine** out) {
+  if (!out) return fail(nullptr, "nds_create: out is null");
+  *out = nullptr;
+  if (validate(cfg)) return 1;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return fail(nullptr, "nds_create: no CUDA device (%s); this engine has no CPU fallback",
+                err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "nds_create: device %d out of range", cfg->device);
+  int rc;
+  nds_engine* e;
+  if (cfg->precision == NDS_F32) { auto* p = new Engine<float>(); rc = p->init(*cfg); e = p; }
+  else { auto* p = new Engine<double>(); rc = p->init(*cfg); e = p; }
+  if (rc) { g_last_error = e->err; delete e; return rc; }
+  *out = e;
+  return 0;
+}
+
+void nds_destroy(nds_engine* e) { delete e; }
+int nds_set_state(nds_engine* e, const double* x, const double* v) { return e->set_state(x, v); }
+int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0) { return e->set_walker_bias(k, r0); }
+int nds_set_noise(nds_engine* e, const double* n, int64_t first, int64_t ns) { return e->set_noise(n, first, ns); }
+int nds_begin(nds_engine* e) { return e->begin(); }
+int nds_run(nds_engine* e, int64_t n) { return e->run(n); }
+int nds_sync(nds_engine* e) { return e->sync(); }
+int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv, double* thermo) {
+  return e->get_state(x, v, f, fixf, colv, thermo);
+}
+int64_t nds_step(const nds_engine* e) { return e->step; }
+double nds_time(const nds_engine* e) { return e->time; }
+int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, double* F, double* colv, double* J,
+                double* Vb, double* Fb) {
+  return e->eval_at(x, n, V, F, colv, J, Vb, Fb);
+}
+int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* c, double* h, int64_t cap) {
+  return e->get_hills(walker, n, c, h, cap);
+}
+int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* c, const double* h) {
+  return e->set_hills(walker, n, c, h);
+}
+int nds_get_vr(nds_engine* e, double* vr) { return e->get_vr(vr); }
+int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
+  e->exchange = cb; e->exchange_user = user;
+  return 0;
+}
+int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e->get_commit(basin, exit_step); }
+int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
+int nds_frame_width(const nds_engine* e) { return e->frame_width; }
+int64_t nds_frames_pending(const nds_engine* e) { return e->frames_written; }
+int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n) { return e->drain_frames(out, max_frames, n); }
+int nds_fes_grid(nds_engine* e, int64_t walker, double x0, double dx, int64_t nx, double y0, double dy,
+                 int64_t ny, double* grid) {
+  return e->fes_grid(walker, x0, dx, nx, y0, dy, ny, grid);
+}
+int nds_colvar_histogram(nds_engine* e, double x0, double dx, int64_t nx, double y0, double dy, int64_t ny,
+                         int64_t* counts) {
+  return e->histogram(x0, dx, nx, y0, dy, ny, counts);
+}
+int nds_device_pointers(nds_engine* e, void** x, void** v, void** hills, int64_t* stride) {
+  return e->device_pointers(x, v, hills, stride);
+}
+void* nds_stream(nds_engine* e) { return (void*)e->stream; }
+int64_t nds_n_hills(const nds_engine* e, int64_t) { return e->n_hills; }
+int64_t nds_launch_count(const nds_engine* e) { return e->launches; }
+double nds_last_run_ms(nds_engine* e) { return e->last_run_ms(); }
+const char* nds_kernel_name(const nds_engine* e) { return e->kernel_name; }
+
+int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "nds_philox_kat: no CUDA device");
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return fail(nullptr, "nds_philox_kat: cudaMalloc failed");
+  philox_kat_kernel<<<1, 1>>>(u32x4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1], d);
+  cudaError_t err = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return err == cudaSuccess ? 0 : fail(nullptr, "nds_philox_kat: %s", cudaGetErrorString(err));
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// nds_kernels.cuh -- the fused multi-walker step kernel and its small companions.
+//
+// md_block<Spec>: one thread per walker, walker state (x, v, total force) register-resident for the
+// whole launch; each launch advances every live walker by `nsteps` iterations of the reference loop
+//   NDRun.run body (ndrun.py:227-251) -> MD.update (engines/md.py:112-231)
+//                                     -> Committor.update (engines/committor.py:82-116)
+// including potential / colvar / bias evaluation, the Langevin / NVE / rescale update, Philox noise,
+// the committor box test and frame recording.  HBM is touched only at launch entry/exit (SoA state,
+// coalesced) and for the hill table / frames.
+#pragma once
+#include "nds_common.cuh"
+#include "nds_philox.cuh"
+#include "nds_physics.cuh"
+
+namespace nds {
+
+constexpr int NDS_BLOCK = 128;
+
+__host__ __device__ constexpr int normals_per_step(int integ, int nd) {
+  return integ == NDS_INT_LANGEVIN ? nd : (integ == NDS_INT_LANGEVIN2 ? 2 * nd : 0);
+}
+__host__ __device__ constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+// steps per noise group: the smallest G with G*NN a multiple of 4 (one Philox call = 4 normals)
+__host__ __device__ constexpr int noise_group(int nn) { return nn == 0 ? 1 : 4 / gcd_(nn, 4); }
+
+// frame events (io/dump.py:76-102 + the lagged thermo row): a frame is recorded after the
+// step that makes NDRun.step == s when s is a dump step, or when s is the last stat sample strictly
+// before the next dump step (that sample is what thermo.dat prints beside the next dump row).
+__host__ __device__ __forceinline__ bool frame_event(long long s, long long dump_freq, long long stat_freq) {
+  if (dump_freq <= 0) return false;
+  if (s % dump_freq == 0) return true;
+  if (stat_freq > 0 && s % stat_freq == 0) {
+    const long long next_dump = (s / dump_freq + 1) * dump_freq;
+    return next_dump - s <= stat_freq;
+  }
+  return false;
+}
+
+// Everything evaluated at one configuration.
+template <typename R, int ND>
+struct Eval {
+  CvOut<R, ND> cv;
+  R pe, be, vm;
+  R fp[ND], fb[ND];
+};
+
+template <typename R, int ND, bool ENERGY>
+NDS_DEV void eval_all(const Consts<R>& K, int pot, int cv, int tcv, int cd, int bias_mask,
+                      const R (&x)[ND], const WalkerBias<R, ND>& wb, const R* hills, long long n_hills,
+                      long long elem_stride, Eval<R, ND>& e) {
+  cv_eval<R, ND>(cv, K.rot, x, e.cv);
+  // PE bias needs the potential energy even when the caller does not
+  if (ENERGY || (bias_mask & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
+  else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
+  if (bias_mask != 0)
+    bias_eval<R, ND>(K, bias_mask, cv, cd, x, e.cv, wb, hills, n_hills, elem_stride, e.pe, e.fp, e.be,
+                     e.fb, e.vm);
+  else {
+    e.be = (R)0; e.vm = (R)0;
+#pragma unroll
+    for (int d = 0; d < ND; d++) e.fb[d] = (R)0;
+  }
+}
+
+// one frame row of walker w (layout documented at nds_drain_frames in include/ndsb200.h)
+template <typename R, int ND>
+NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w, long long frame,
+                         long long s, double time, int cd, int bias_mask, const R (&x)[ND],
+                         const R (&v)[ND], const Eval<R, ND>& o, bool begin_mode) {
+  if (frame >= A.frame_cap) return;
+  double* row = A.frames + (frame * A.frame_width) * K.dump_walkers + w;
+  const long long st = K.dump_walkers;
+  int r = 0;
+  row[(r++) * st] = (double)s;
+  row[(r++) * st] = time;
+#pragma unroll
+  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)x[d];
+#pragma unroll
+  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)v[d];
+#pragma unroll
+  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)o.fp[d];
+#pragma unroll
+  for (int k = 0; k < ND; k++)
+    if (k < cd) row[(r++) * st] = (double)o.cv.c[k];
+  R v2 = (R)0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) v2 += v[d] * v[d];
+  const R ke = v2 * K.m / (R)2.0;
+  row[(r++) * st] = (double)(ke / (R)ND / K.kB * (R)2.0);
+  row[(r++) * st] = (double)o.pe;
+  row[(r++) * st] = (double)ke;
+  row[(r++) * st] = (double)o.be;
+  row[(r++) * st] = begin_mode ? (double)(ke + o.pe) : (double)(o.pe + ke + o.be);
+  row[(r++) * st] = (bias_mask & BIAS_MTD) ? (double)A.vr[w] : 0.0;
+}
+
+template <class S>
+__global__ void __launch_bounds__(NDS_BLOCK)
+md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
+  using R = typename S::R;
+  constexpr int ND = S::ND;
+  constexpr int INTEG = S::INTEG;  // always compile-time
+  constexpr int NN = normals_per_step(INTEG, ND);
+  constexpr int G = noise_group(NN);
+  constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
+
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long M = A.M;
+  if (w >= M) return;
+
+  const int pot = S::POT >= 0 ? S::POT : K.pot;
+  const int cv = S::CV >= 0 ? S::CV : K.cv;
+  const int tcv = S::TCV >= 0 ? S::TCV : K.tcv;
+  const int cd = S::CV >= 0 ? cv_dim(S::CV, ND) : K.cd;
+  const int bias_mask = S::BIAS >= 0 ? S::BIAS : K.bias_mask;
+  const bool committor = S::METHOD >= 0 ? (S::METHOD == NDS_METHOD_COMMITTOR) : (K.method == NDS_METHOD_COMMITTOR);
+  const bool ext_noise = S::NOISE >= 0 ? (S::NOISE == NDS_NOISE_EXTERNAL) : (K.noise == NDS_NOISE_EXTERNAL);
+  const bool dumping = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0)) && w < K.dump_walkers;
+
+  if (committor && !A.alive[w]) return;
+
+  // ---- load walker state (coalesced SoA)
+  R x[ND], v[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) { x[d] = A.x[d * M + w]; v[d] = A.v[d * M + w]; }
+  WalkerBias<R, ND> wb;
+#pragma unroll
+  for (int k = 0; k < ND; k++) { wb.k[k] = (R)0; wb.r0[k] = (R)0; }
+  if (bias_mask & BIAS_UMB_WALKER) {
+#pragma unroll
+    for (int k = 0; k < ND; k++)
+      if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
+  }
+  const unsigned long long gid = (unsigned long long)(A.walker_offset + w);
+  const long long hstride = K.mtd_shared ? 1 : M;
+  const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
+
+  if (A.need_init_v) {  // Modify.set_velocity(T=initial_temperature), engines/modify.py:44-54
+    R z[4];
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      if ((d & 3) == 0) normals4<R>(K.key0, K.key1 ^ 1u, (unsigned long long)(d >> 2), gid, z);
+      v[d] = K.vel_scale * z[d & 3];
+    }
+  }
+
+  // ---- forces at the current positions: MD.begin (md.py:101-110) / refresh after a deposition
+  //      (gaus.py:138-146).  Identical to the values the previous launch ended with.
+  Eval<R, ND> e;
+  eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+  if (A.refresh_vr && (bias_mask & BIAS_MTD)) A.vr[w] = e.vm;  // Gaussian.VR, gaus.py:292-293
+  R f[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) f[d] = e.fp[d] + e.fb[d];  // md.py:133
+
+  long long s = A.step0;
+  const long long s_end = A.step0 + A.nsteps;
+  double time = A.time0;
+  long long rescale_count = A.rescale_count;
+  long long frame = A.frame_base;
+  bool alive = true;
+  int basin = -1;
+
+  while (s < s_end && alive) {
+    const long long grp = s / G;
+    const int first = (int)(s - grp * G);
+    R zb[G * NN > 0 ? G * NN : 1];
+    if (NN > 0 && !ext_noise) {
+#pragma unroll
+      for (int c = 0; c < CG; c++) {
+        R z4[4];
+        normals4<R>(K.key0, K.key1, (unsigned long long)(grp * CG + c), gid, z4);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (4 * c + j < G * NN) zb[4 * c + j] = z4[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+      if (i >= first && s < s_end && alive) {
+        R xi[ND], eta[ND];
+        if (NN > 0) {
+          if (ext_noise) {  // md.py:120,127-128 with numbers supplied by the caller (parity tests)
+            const double* row = A.noise + ((s - A.noise_first) * NN) * M + w;
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+              xi[d] = (R)row[(long long)d * M];
+              if (INTEG == NDS_INT_LANGEVIN2) eta[d] = (R)row[(long long)(ND + d) * M];
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+              xi[d] = zb[i * NN + d];
+              if (INTEG == NDS_INT_LANGEVIN2) eta[d] = zb[i * NN + ND + d];
+            }
+          }
+        }
+        // ---- first half kick + drift, md.py:164-178
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+          R dx;
+          if constexpr (is_f32<R>::value) {
+            if (INTEG == NDS_INT_LANGEVIN) {
+              v[d] = fmaf(K.hdtm, f[d], v[d]);
+              v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
+              dx = v[d] * K.dt;
+            } else if (INTEG == NDS_INT_LANGEVIN2) {
+              v[d] += K.c1 * f[d] * K.inv_m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
+              dx = K.dt * v[d] + K.c5 * eta[d] * K.dt;
+            } else {
+              v[d] = fmaf(K.hdtm, f[d], v[d]);
+              dx = v[d] * K.dt;
+            }
+          } else {
+            if (INTEG == NDS_INT_LANGEVIN) {
+              v[d] += K.dt / (R)2.0 * f[d] / K.m;
+              v[d] = K.c1 * v[d] + K.c2 * xi[d];
+              dx = v[d] * K.dt;
+            } else if (INTEG == NDS_INT_LANGEVIN2) {
+              v[d] += K.c1 * f[d] / K.m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
+              dx = K.dt * v[d] + K.c5 * eta[d] * K.dt;
+            } else {
+              v[d] += K.dt / (R)2.0 * f[d] / K.m;
+              dx = v[d] * K.dt;
+            }
+          }
+          x[d] = x[d] + dx;
+        }
+        // ---- colvar, potential and biases at the new positions, md.py:179-188
+        eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+#pragma unroll
+        for (int d = 0; d < ND; d++) f[d] = e.fp[d] + e.fb[d];
+        // ---- second half kick, md.py:190-198
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+          if constexpr (is_f32<R>::value) {
+            if (INTEG == NDS_INT_LANGEVIN) {
+              v[d] = fmaf(K.hdtm, f[d], v[d]);
+              v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
+            } else if (INTEG == NDS_INT_LANGEVIN2) {
+              v[d] += K.c1 * f[d] * K.inv_m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
+            } else {
+              v[d] = fmaf(K.hdtm, f[d], v[d]);
+            }
+          } else {
+            if (INTEG == NDS_INT_LANGEVIN) {
+              v[d] += f[d] / (R)2.0 / K.m * K.dt;
+              v[d] = K.c1 * v[d] + K.c2 * xi[d];
+            } else if (INTEG == NDS_INT_LANGEVIN2) {
+              v[d] += K.c1 * f[d] / K.m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
+            } else {
+              v[d] += f[d] / K.m * K.dt / (R)2.0;
+            }
+          }
+        }
+        if (INTEG == NDS_INT_RESCALE) {  // md.py:219-224; `time` is the pre-step time (ndrun.py:230)
+          const long long count = (long long)floor(time / K.rescale_freq) + 1;
+          if (count > rescale_count) {
+            rescale_count = count;
+            R n2 = (R)0;
+#pragma unroll
+            for (int d = 0; d < ND; d++) n2 += v[d] * v[d];
+            const R scale = K.v_target / nds_sqrt(n2);
+#pragma unroll
+            for (int d = 0; d < ND; d++) v[d] *= scale;
+          }
+        }
+        s += 1;            // ndrun.py:232
+        time += K.dt64;    // ndrun.py:240
+        if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
+          basin = commit_test<R, ND>(K, cd, e.cv.c);
+          if (basin >= 0) alive = false;
+        }
+        if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
+          // io/dump.py:76-102: full observables of this walker at NDRun.step == s
+          Eval<R, ND> o;
+          eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+          write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
+        }
+        if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
+      }
+    }
+  }
+
+  // ---- launch exit: observables at the final positions (md.py:210-217,226-229) and state write-back
+  Eval<R, ND> o;
+  eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+  R v2 = (R)0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    A.x[d * M + w] = x[d];
+    A.v[d * M + w] = v[d];
+    A.f[d * M + w] = o.fp[d];
+    A.fixf[d * M + w] = o.fb[d];
+    v2 += v[d] * v[d];
+  }
+#pragma unroll
+  for (int k = 0; k < ND; k++)
+    if (k < cd) A.colv[k * M + w] = o.cv.c[k];
+  const R ke = v2 * K.m / (R)2.0;  // md.py:227
+  A.thermo[0 * M + w] = A.begin_mode ? ke / (R)ND * (R)2.0 / K.kB : ke / (R)ND / K.kB * (R)2.0;  // ndrun.py:195 / md.py:228
+  A.thermo[1 * M + w] = o.pe;
+  A.thermo[2 * M + w] = ke;
+  A.thermo[3 * M + w] = o.be;
+  A.thermo[4 * M + w] = A.begin_mode ? ke + o.pe : o.pe + ke + o.be;  // ndrun.py:196 / md.py:229
+  if (committor) {
+    if (!alive) { A.alive[w] = 0; A.exit_step[w] = s; }
+    A.basin[w] = basin;
+  }
+  // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
+  if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
+}
+
+// ---------------------------------------------------------------------------------- eval_at
+// potential.compute(x), colvar.compute/jacobian(x), sum of fix.compute(x0, col0) at n configurations.
+template <typename R, int ND>
+__global__ void __launch_bounds__(NDS_BLOCK)
+eval_at_kernel(const __grid_constant__ Consts<R> K, long long n, const R* __restrict__ xin,
+               const R* hills, long long n_hills, long long elem_stride, R* V, R* F, R* colv, R* J,
+               R* Vb, R* Fb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R x[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) x[d] = xin[d * n + i];
+  WalkerBias<R, ND> wb;
+#pragma unroll
+  for (int k = 0; k < ND; k++) { wb.k[k] = (R)0; wb.r0[k] = (R)0; }
+  Eval<R, ND> e;
+  const int cd = K.cd;
+  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, K.bias_mask & ~BIAS_UMB_WALKER, x, wb, hills,
+                        n_hills, elem_stride, e);
+  if (V) V[i] = e.pe;
+  if (Vb) Vb[i] = e.be;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    if (F) F[d * n + i] = e.fp[d];
+    if (Fb) Fb[d * n + i] = e.fb[d];
+  }
+  for (int k = 0; k < cd; k++) {
+    if (colv) colv[k * n + i] = e.cv.c[k];
+    if (J) {  // row k of the Jacobian = pull-back of the k-th unit vector
+      R g[ND], row[ND];
+#pragma unroll
+      for (int d = 0; d < ND; d++) g[d] = (d == k) ? (R)1 : (R)0;
+      cv_pullback<R, ND>(K.cv, K.rot, x, e.cv, g, row);
+#pragma unroll
+      for (int d = 0; d < ND; d++) J[(k * ND + d) * n + i] = row[d];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- deposit
+// Gaussian._deposite (bias/gaus.py:148-213), one new hill per live walker at its current colvar with
+// the well-tempered height w_init * exp(-VR / (kB (biasf-1) T)) from the STALE VR; the
+// first deposition uses w_init.  Shared table: walker w of this rank writes record n_hills +
+// walker_offset + w, i.e. straight into its slot of the segment an allgather completes (section 8e).
+template <typename R>
+__global__ void deposit_kernel(const __grid_constant__ Consts<R> K, long long M, long long walker_offset,
+                               const R* __restrict__ colv, const R* __restrict__ vr,
+                               const unsigned char* alive, R* hills, long long n_hills, int first) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= M) return;
+  const bool live = alive ? alive[w] != 0 : true;
+  R h = first ? K.mtd_w : K.mtd_w * nds_exp(-vr[w] / K.mtd_kBdT);
+  if (!live) h = (R)0;
+  const int cd = K.cd, rs = K.hill_stride;
+  if (K.mtd_shared) {
+    R* rec = hills + (n_hills + walker_offset + w) * rs;
+    for (int k = 0; k < cd; k++) rec[k] = colv[k * M + w];
+    rec[cd] = h;
+    for (int k = cd + 1; k < rs; k++) rec[k] = (R)0;
+  } else {
+    for (int k = 0; k < cd; k++) hills[(n_hills * rs + k) * M + w] = colv[k * M + w];
+    hills[(n_hills * rs + cd) * M + w] = h;
+  }
+}
+
+// ------------------------------------------------------------------------- FES grid, histogram
+// Gaussian.projection (bias/gaus.py:365-393, 413-425): sum of hills on a regular grid.
+template <typename R>
+__global__ void fes_grid_kernel(const __grid_constant__ Consts<R> K, const R* __restrict__ hills,
+                                long long n_hills, long long elem_stride, double x0, double dx,
+                                long long nx, double y0, double dy, long long ny, double* grid) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nx * ny) return;
+  const long long i = p % nx, j = p / nx;
+  const double X = x0 + i * dx, Y = y0 + j * dy;
+  const int cd = K.cd, rs = K.hill_stride;
+  const double s0 = (double)1.0 / ((double)K.mtd_invsig2[0]);
+  const double s1 = cd > 1 ? (double)1.0 / ((double)K.mtd_invsig2[1]) : 1.0;
+  double acc = 0.0;
+  for (long long k = 0; k < n_hills; k++) {
+    const R* h = hills + k * rs * elem_stride;
+    const double hx = (double)h[0];
+    double ex = -((X - hx) * (X - hx)) / s0 / 2.0;
+    if (cd > 1) {
+      const double hy = (double)h[elem_stride];
+      ex += -((Y - hy) * (Y - hy)) / s1 / 2.0;
+    }
+    acc += (double)h[cd * elem_stride] * exp(ex);
+  }
+  grid[p] = acc;
+}
+
+// histogram of the current colvar values (io/plot.py:562-572): shared-memory privatised bins when they
+// fit, one global atomic per non-empty bin per block.
+template <typename R>
+__global__ void histogram_kernel(long long M, int cd, const R* __restrict__ colv,
+                                 const unsigned char* alive, double x0, double inv_dx, int nx,
+                                 double y0, double inv_dy, int ny, unsigned long long* counts) {
+  extern __shared__ unsigned int bins[];
+  const int nb = nx * ny;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0u;
+  __syncthreads();
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < M;
+       w += (long long)gridDim.x * blockDim.x) {
+    const double cx = (double)colv[w];
+    const long long ix = (long long)floor((cx - x0) * inv_dx);
+    long long iy = 0;
+    if (cd > 1) iy = (long long)floor(((double)colv[M + w] - y0) * inv_dy);
+    if (ix >= 0 && ix < nx && iy >= 0 && iy < ny) atomicAdd(&bins[iy * nx + ix], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += blockDim.x)
+    if (bins[b]) atomicAdd(&counts[b], (unsigned long long)bins[b]);
+}
+
+template <typename T>
+__global__ void convert_kernel(long long n, const double* __restrict__ in, T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (T)in[i];
+}
+template <typename T>
+__global__ void convert_back_kernel(long long n, const T* __restrict__ in, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+}  // namespace nds

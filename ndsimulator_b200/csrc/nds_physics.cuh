@@ -1,0 +1,420 @@
+// nds_physics.cuh -- device code of the built-in collective variables, potentials and biases.
+//
+// Each function names the reference code it replaces (file:line in mir-group/NDSimulator).  All code is
+// templated on the real type R: the fp64 instantiation keeps the reference's operation order (parity
+// within 1e-10, tests/test_parity_gpu.py); the fp32 instantiation is free to use MUFU intrinsics and
+// algebraically equivalent forms (statistical parity).
+//
+// Every `id` argument (potential / colvar id) is either a compile-time constant folded by inlining
+// (hot-path kernel variants) or a value read from the constant block (generic kernels); the switch
+// statements below serve both.
+#pragma once
+#include "nds_common.cuh"
+
+namespace nds {
+
+#define NDS_DEV __device__ __forceinline__
+
+template <typename R> struct is_f32 { static constexpr bool value = false; };
+template <> struct is_f32<float> { static constexpr bool value = true; };
+
+NDS_DEV float nds_exp(float x) { return __expf(x); }
+NDS_DEV double nds_exp(double x) { return exp(x); }
+NDS_DEV float nds_exp2(float x) { return exp2f(x); }
+NDS_DEV float nds_sqrt(float x) { return sqrtf(x); }
+NDS_DEV double nds_sqrt(double x) { return sqrt(x); }
+NDS_DEV float nds_rcp(float x) { return __frcp_rn(x); }
+NDS_DEV double nds_rcp(double x) { return 1.0 / x; }
+
+// colvardim of a colvar id (colvars/*.py class attribute `colvardim`)
+__host__ __device__ constexpr int cv_dim(int cv, int ndim) {
+  switch (cv) {
+    case NDS_CV_ORIGINAL: return ndim;
+    case NDS_CV_ROTATE2D: case NDS_CV_PROJ5DTO2D: case NDS_CV_PROJ5DTO2DV2: return 2;
+    default: return 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------ colvars
+// Value c[0..cd) plus the few intermediates the Jacobian needs (inverse norms), so that the pull-back
+// f_j = sum_k g_k J_kj can be applied sparsely without materialising J.
+template <typename R, int ND>
+struct CvOut {
+  R c[ND];
+  R q[2];  // norms (Proj*) for the Jacobian
+};
+
+template <typename R, int ND>
+NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
+  switch (cv) {
+    case NDS_CV_ORIGINAL:  // colvars/misc.py:12-13
+#pragma unroll
+      for (int d = 0; d < ND; d++) o.c[d] = x[d];
+      break;
+    default: break;
+  }
+  if constexpr (ND == 2) {
+    switch (cv) {
+      case NDS_CV_EXTRACTX: o.c[0] = x[0]; break;          // two.py:21-22
+      case NDS_CV_EXTRACTY: o.c[0] = x[1]; break;          // two.py:10-11
+      case NDS_CV_XMY: o.c[0] = x[0] - x[1]; break;        // two.py:32-33
+      case NDS_CV_XPY: o.c[0] = x[0] + x[1]; break;        // two.py:43-44
+      case NDS_CV_ROTATE2D: {                              // two.py:52-58
+        const R r = rot;
+        o.c[0] = x[0] * r + x[1] * r;
+        o.c[1] = x[0] * r + x[1] * (-r);
+      } break;
+      case NDS_CV_PROJ2DTO1D:                              // two.py:67-69
+        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1]);
+        o.c[0] = o.q[0];
+        break;
+      default: break;
+    }
+  }
+  if constexpr (ND == 5) {
+    switch (cv) {
+      case NDS_CV_PROJ5DTO1DX0: o.c[0] = x[0]; break;      // five.py:9-11
+      case NDS_CV_PROJ5DTO1DX2: o.c[0] = x[2]; break;      // five.py:22-24
+      case NDS_CV_PROJ5DTO1D:                              // five.py:34-38
+        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]));
+        o.c[0] = o.q[0];
+        break;
+      case NDS_CV_PROJ5DTO2D:                              // five.py:50-57
+        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]));
+        o.q[1] = nds_sqrt(x[2] * x[2] + x[3] * x[3]);
+        o.c[0] = o.q[0];
+        o.c[1] = o.q[1];
+        break;
+      case NDS_CV_PROJ5DTO2DV2: {                          // five.py:77-81
+        const R d = x[1] - x[4];
+        o.q[0] = nds_sqrt(x[0] * x[0] + d * d);
+        o.q[1] = nds_sqrt(x[2] * x[2] + x[3] * x[3]);
+        o.c[0] = o.q[0];
+        o.c[1] = o.q[1];
+      } break;
+      default: break;
+    }
+  }
+}
+
+// f[j] = sum_k g[k] * J[k][j]  with J = colvar.jacobian(x)   (e.g. mueller.py:142, umb.py:31, gaus.py:258)
+template <typename R, int ND>
+NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o, const R (&g)[ND],
+                         R (&f)[ND]) {
+#pragma unroll
+  for (int d = 0; d < ND; d++) f[d] = (R)0;
+  if (cv == NDS_CV_ORIGINAL) {  // identity Jacobian, misc.py:15-16
+#pragma unroll
+    for (int d = 0; d < ND; d++) f[d] = g[d];
+    return;
+  }
+  if constexpr (ND == 2) {
+    switch (cv) {
+      case NDS_CV_EXTRACTX: f[0] = g[0]; break;                        // two.py:19
+      case NDS_CV_EXTRACTY: f[1] = g[0]; break;                        // two.py:8
+      case NDS_CV_XMY: f[0] = g[0]; f[1] = -g[0]; break;               // two.py:30
+      case NDS_CV_XPY: f[0] = g[0]; f[1] = g[0]; break;                // two.py:41
+      case NDS_CV_ROTATE2D: {                                          // two.py:53-54
+        const R r = rot;
+        f[0] = g[0] * r + g[1] * r;
+        f[1] = g[0] * r + g[1] * (-r);
+      } break;
+      case NDS_CV_PROJ2DTO1D:                                          // two.py:71-73
+        if constexpr (is_f32<R>::value) {
+          const R inv = nds_rcp(o.q[0]);
+          f[0] = g[0] * (x[0] * inv); f[1] = g[0] * (x[1] * inv);
+        } else {
+          f[0] = g[0] * (x[0] / o.q[0]); f[1] = g[0] * (x[1] / o.q[0]);
+        }
+        break;
+      default: break;
+    }
+  }
+  if constexpr (ND == 5) {
+    switch (cv) {
+      case NDS_CV_PROJ5DTO1DX0: f[0] = g[0]; break;                    // five.py:7
+      case NDS_CV_PROJ5DTO1DX2: f[2] = g[0]; break;                    // five.py:20
+      case NDS_CV_PROJ5DTO1D:                                          // five.py:40-44 (2e-7)
+        f[0] = g[0] * (x[0] / o.q[0]);
+        f[1] = g[0] * (x[1] / o.q[0]);
+        f[4] = g[0] * ((R)2.0 * (R)1.0e-7 * x[4] / o.q[0]);
+        break;
+      case NDS_CV_PROJ5DTO2D:                                          // five.py:59-71
+        if constexpr (is_f32<R>::value) {
+          const R i0 = nds_rcp(o.q[0]) * g[0], i1 = nds_rcp(o.q[1]) * g[1];
+          f[0] = x[0] * i0; f[1] = x[1] * i0; f[4] = (R)1.0e-7 * x[4] * i0;
+          f[2] = x[2] * i1; f[3] = x[3] * i1;
+        } else {
+          f[0] = g[0] * (x[0] / o.q[0]);
+          f[1] = g[0] * (x[1] / o.q[0]);
+          f[4] = g[0] * ((R)1.0e-7 * x[4] / o.q[0]);
+          f[2] = g[1] * (x[2] / o.q[1]);
+          f[3] = g[1] * (x[3] / o.q[1]);
+        }
+        break;
+      case NDS_CV_PROJ5DTO2DV2: {                                      // five.py:83-98
+        const R d = x[1] - x[4];
+        f[0] = g[0] * (x[0] / o.q[0]);
+        f[1] = g[0] * (d / o.q[0]);
+        f[4] = g[0] * (-d / o.q[0]);
+        f[2] = g[1] * (x[2] / o.q[1]);
+        f[3] = g[1] * (x[3] / o.q[1]);
+      } break;
+      default: break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- potentials
+// Sum of four anisotropic Gaussians in (q0, q1): V = sum A_i exp(a dx^2 + b dx dy + c dy^2) and the
+// gradient force g = -dV/dq.   potentials/mueller.py:30-44, potentials/three_hole.py:36-50.
+template <typename R, bool ENERGY>
+NDS_DEV void four_gauss(const Consts<R>& K, R q0, R q1, R& V, R& g0, R& g1) {
+  if constexpr (is_f32<R>::value) {
+    // fast form: G = k * grad(exponent) with k = log2(e)/2, so that  exponent*log2(e) = dx*Gx + dy*Gy
+    // feeds MUFU.EX2 directly and the force is (A/k) * 2^s * G.  9-11 FP32 ops + 1 MUFU per term.
+    R fx = 0.f, fy = 0.f, e = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const R dx = q0 - K.gx[i], dy = q1 - K.gy[i];
+      const R Gx = fmaf(K.fb[i], dy, K.fa[i] * dx);
+      const R Gy = fmaf(K.fb[i], dx, K.fc[i] * dy);
+      const R s = fmaf(dy, Gy, dx * Gx);
+      const R t = K.fA[i] * nds_exp2(s);
+      fx = fmaf(-t, Gx, fx);
+      fy = fmaf(-t, Gy, fy);
+      if (ENERGY) e += t;
+    }
+    g0 = fx; g1 = fy;
+    if (ENERGY) V = e * (R)0.72134752044448170368;  // k: A = fA * k
+  } else {
+    R v = 0, f0 = 0, f1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const R dx = q0 - K.gx[i], dy = q1 - K.gy[i];
+      const R tmp = K.gA[i] * nds_exp(K.ga[i] * (dx * dx) + K.gb[i] * dx * dy + K.gc[i] * (dy * dy));
+      v += tmp;
+      f0 -= tmp * ((R)2 * K.ga[i] * dx + K.gb[i] * dy);
+      f1 -= tmp * ((R)2 * K.gc[i] * dy + K.gb[i] * dx);
+    }
+    V = v; g0 = f0; g1 = f1;
+  }
+}
+
+// potential.compute(x) -> (V, f).  ENERGY=false lets the compiler drop the energy accumulation in the
+// step loop (the reference evaluates it every step, md.py:180,210; it only feeds observables).
+template <typename R, int ND, bool ENERGY>
+NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R& V, R (&f)[ND]) {
+  V = (R)0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) f[d] = (R)0;
+  if constexpr (ND == 1) {
+    if (pot == NDS_POT_DOUBLEWELL1D) {  // double_well.py:16-25
+      const R d1 = x[0] - K.dw_x1[0], d2 = x[0] - K.dw_x2[0];
+      const R e1 = nds_exp(-(d1 * d1) * K.dw_invsig2), e2 = nds_exp(-(d2 * d2) * K.dw_invsig2);
+      V = (R)-0.5 * (K.dw_K1 * e1 + K.dw_K2 * e2);
+      f[0] = (-K.dw_K1 * e1 * d1 - K.dw_K2 * e2 * d2) * K.dw_invsig2;
+    }
+    // NDS_POT_FLAT1D: zero (flat.py:17-24)
+  }
+  if constexpr (ND == 2) {
+    switch (pot) {
+      case NDS_POT_MUELLER2D: {  // mueller.py:25-45
+        four_gauss<R, ENERGY>(K, x[0], x[1], V, f[0], f[1]);
+      } break;
+      case NDS_POT_DOUBLEWELL: {  // double_well.py:44-53
+        const R a0 = x[0] - K.dw_x1[0], a1 = x[1] - K.dw_x1[1];
+        const R b0 = x[0] - K.dw_x2[0], b1 = x[1] - K.dw_x2[1];
+        const R e1 = nds_exp(-(a0 * a0 + a1 * a1) * K.dw_invsig2);
+        const R e2 = nds_exp(-(b0 * b0 + b1 * b1) * K.dw_invsig2);
+        V = (R)-0.5 * (K.dw_K1 * e1 + K.dw_K2 * e2);
+        f[0] = (-K.dw_K1 * e1 * a0 - K.dw_K2 * e2 * b0) * K.dw_invsig2;
+        f[1] = (-K.dw_K1 * e1 * a1 - K.dw_K2 * e2 * b1) * K.dw_invsig2;
+      } break;
+      case NDS_POT_GAUSSIAN2D: {  // misc.py:7-26: A exp(a (x-20)^2 + c (y-20)^2)
+        const R dx = x[0] - (R)20, dy = x[1] - (R)20;
+        const R tmp = K.gA[0] * nds_exp(K.ga[0] * (dx * dx) + K.gc[0] * (dy * dy));
+        V = tmp;
+        f[0] = -tmp * (R)2 * K.ga[0] * dx;
+        f[1] = -tmp * (R)2 * K.gc[0] * dy;
+      } break;
+      case NDS_POT_GAUSSIAN: {  // misc.py:32-43; the force uses x, not x - centre
+        const R s2 = (R)100;
+        const R V1 = -nds_exp(-((x[0] - (R)0.5) * (x[0] - (R)0.5) + x[1] * x[1]) / s2);
+        const R V2 = -nds_exp(-((x[0] + (R)0.5) * (x[0] + (R)0.5) + x[1] * x[1]) / s2);
+        V = V1 + V2;
+        f[0] = V1 * (R)2 * x[0] / s2 + V2 * (R)2 * x[0] / s2;
+        f[1] = V1 * (R)2 * x[1] / s2 + V2 * (R)2 * x[1] / s2;
+      } break;
+      default: break;  // NDS_POT_FLAT2D: zero (flat.py:5-14)
+    }
+  }
+  if constexpr (ND == 2 || ND == 5) {
+    const bool mueller_cv = (ND == 5) && (pot == NDS_POT_MUELLER5D || pot == NDS_POT_MUELLER5DSHL);
+    const bool threehole = (ND == 2 && pot == NDS_POT_THREEHOLE2D) || (ND == 5 && pot == NDS_POT_THREEHOLE5D);
+    if (mueller_cv || threehole) {
+      // mueller.py:112-142 / three_hole.py:24-57,90-125: evaluate in true_colvar space, chain rule
+      CvOut<R, ND> o;
+      cv_eval<R, ND>(tcv, K.rot, x, o);
+      R g[ND];
+#pragma unroll
+      for (int d = 0; d < ND; d++) g[d] = (R)0;
+      R v = (R)0;
+      four_gauss<R, ENERGY>(K, o.c[0], o.c[1], v, g[0], g[1]);
+      if (threehole) {  // quartic confinement, three_hole.py:51-55
+        const R dx = o.c[0] - K.th_x1, dy = o.c[1] - K.th_y1;
+        const R dx2 = dx * dx, dy2 = dy * dy;
+        if (ENERGY) {
+          v += K.th_D * (dx2 * dx2);
+          if (ND == 2) v += K.th_E * (dy2 * dy2) + K.th_ref;
+          else { v += K.th_E * (dy2 * dy2); v += K.th_ref; }
+        }
+        g[0] -= (R)4.0 * K.th_D * (dx2 * dx);
+        g[1] -= (R)4.0 * K.th_E * (dy2 * dy);
+      }
+      V = v;
+      cv_pullback<R, ND>(tcv, K.rot, x, o, g, f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- biases
+template <typename R, int ND>
+struct WalkerBias {  // umbrella window of this walker (restraint 0) when BIAS_UMB_WALKER
+  R k[ND], r0[ND];
+};
+
+// Hill sum of well-tempered metadynamics, fixed sigma: bias/gaus.py:236-261.
+//   V = sum_i w_i exp(-sum_k (c_k - h_ik)^2 / (2 sigma_k^2)),  g_k = sum_i V_i (c_k - h_ik) / sigma_k^2
+// Hill records are (h_0..h_{cd-1}, w) with stride K.hill_stride; shared table: record i at
+// hills[i*stride]; per-walker tables: field j of record i of walker w at hills[(i*stride + j)*M + w].
+template <typename R, int ND>
+NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, long long n_hills,
+                      long long elem_stride, const R (&c)[ND], R& V, R (&g)[ND]) {
+  R v = (R)0;
+#pragma unroll
+  for (int k = 0; k < ND; k++) g[k] = (R)0;
+  const int rs = K.hill_stride;
+  if (cd == 2 && elem_stride == 1) {
+    // 16/32-byte records (h0, h1, w, pad): one vector load per hill, warp-uniform address (broadcast)
+    if constexpr (is_f32<R>::value) {
+      const float4* __restrict__ h4 = reinterpret_cast<const float4*>(hills);
+#pragma unroll 4
+      for (long long i = 0; i < n_hills; i++) {
+        const float4 h = __ldg(h4 + i);
+        const R d0 = c[0] - h.x, d1 = c[1] - h.y;
+        const R s0 = d0 * K.mtd_invsig2[0], s1 = d1 * K.mtd_invsig2[1];
+        const R ex = (R)0.5 * (d0 * s0 + d1 * s1);
+        const R vr = h.z * nds_exp(-ex);
+        v += vr;
+        g[0] = fmaf(vr, s0, g[0]);
+        g[1] = fmaf(vr, s1, g[1]);
+      }
+    } else {
+      const double2* __restrict__ h2 = reinterpret_cast<const double2*>(hills);
+#pragma unroll 2
+      for (long long i = 0; i < n_hills; i++) {
+        const double2 ha = __ldg(h2 + 2 * i), hb = __ldg(h2 + 2 * i + 1);
+        const R d0 = c[0] - ha.x, d1 = c[1] - ha.y;
+        const R ex = (d0 * d0) / (R)2.0 * K.mtd_invsig2[0] + (d1 * d1) / (R)2.0 * K.mtd_invsig2[1];
+        const R vr = hb.x * nds_exp(-ex);
+        v += vr;
+        g[0] += vr * (d0 * K.mtd_invsig2[0]);
+        g[1] += vr * (d1 * K.mtd_invsig2[1]);
+      }
+    }
+  } else {
+    for (long long i = 0; i < n_hills; i++) {
+      const R* h = hills + i * rs * elem_stride;
+      R ex = (R)0, ds[ND];
+#pragma unroll
+      for (int k = 0; k < ND; k++)
+        if (k < cd) {
+          const R dc = c[k] - __ldg(h + k * elem_stride);
+          ds[k] = dc * K.mtd_invsig2[k];
+          ex += (dc * dc) / (R)2.0 * K.mtd_invsig2[k];
+        }
+      const R vr = __ldg(h + cd * elem_stride) * nds_exp(-ex);
+      v += vr;
+#pragma unroll
+      for (int k = 0; k < ND; k++)
+        if (k < cd) g[k] += vr * ds[k];
+    }
+  }
+  V = v;
+}
+
+struct HillView {
+  const void* base;      // hill table (engine precision)
+  long long n;           // hills visible to this evaluation
+  long long elem_stride; // 1 for the shared table, M for per-walker tables
+};
+
+// Sum of fix.compute(x0, col0) over the bias list (md.py:182-188): energy Vb, force fb[ND] in x space,
+// and the metadynamics part Vm alone (what Gaussian.compute would store in VR on a no-arg call,
+// gaus.py:292-293).  Order of accumulation: harmonic restraints, metadynamics, PE bias.
+template <typename R, int ND>
+NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const R (&x)[ND],
+                       const CvOut<R, ND>& o, const WalkerBias<R, ND>& wb, const R* hills,
+                       long long n_hills, long long elem_stride, R pe, const R (&fpot)[ND], R& Vb,
+                       R (&fb)[ND], R& Vm) {
+  Vb = (R)0;
+  Vm = (R)0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) fb[d] = (R)0;
+  if (bias_mask & BIAS_UMB) {  // bias/umb.py:23-40
+    for (int u = 0; u < K.n_umb; u++) {
+      R g[ND], e = (R)0;
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+        g[k] = (R)0;
+        if (k < cd) {
+          const bool pw = (bias_mask & BIAS_UMB_WALKER) && u == 0;
+          const R kk = pw ? wb.k[k] : K.umb_k[u][k];
+          const R r0 = pw ? wb.r0[k] : K.umb_r0[u][k];
+          const R dR = o.c[k] - r0;
+          g[k] = -kk * dR;
+          e += kk * (dR * dR);
+        }
+      }
+      R f[ND];
+      cv_pullback<R, ND>(cv, K.rot, x, o, g, f);
+#pragma unroll
+      for (int d = 0; d < ND; d++) fb[d] += f[d];
+      Vb += (R)0.5 * e;
+    }
+  }
+  if (bias_mask & BIAS_MTD) {
+    R g[ND], f[ND];
+    hill_sum<R, ND>(K, cd, hills, n_hills, elem_stride, o.c, Vm, g);
+    if (n_hills > 0) {
+      cv_pullback<R, ND>(cv, K.rot, x, o, g, f);
+#pragma unroll
+      for (int d = 0; d < ND; d++) fb[d] += f[d];
+    }
+    Vb += Vm;
+  }
+  if (bias_mask & BIAS_PE) {  // bias/pe.py:30-51
+    if (pe < K.pe_thred) {
+#pragma unroll
+      for (int d = 0; d < ND; d++) fb[d] += -fpot[d];
+      Vb += K.pe_thred - pe;
+    }
+  }
+}
+
+// committor.py:118-142: inclusive boxes in colvar space; the last matching basin wins
+template <typename R, int ND>
+NDS_DEV int commit_test(const Consts<R>& K, int cd, const R (&c)[ND]) {
+  int ib = -1;
+  for (int b = 0; b < K.n_basins; b++) {
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < ND; k++)
+      if (k < cd && (c[k] < K.crit[b][k][0] || c[k] > K.crit[b][k][1])) in = false;
+    if (in) ib = b;
+  }
+  return ib;
+}
+
+}  // namespace nds

@@ -1,0 +1,50 @@
+// nds_variants.h -- registry of compiled md_block variants.
+//
+// A variant is one instantiation of md_block<Spec>; fields equal to DYN (-1) are resolved at run time
+// from the constant block.  The engine picks the matching variant with the most compile-time fields.
+#pragma once
+#include "nds_kernels.cuh"
+
+namespace nds {
+
+struct VariantKey {
+  int prec, nd, pot, cv, tcv, integ, bias, method, noise, dump;
+};
+
+struct Variant {
+  VariantKey key;
+  const char* name;
+  void* launch;  // BlockLaunchFn<R>
+};
+
+template <typename R>
+using BlockLaunchFn = cudaError_t (*)(const Consts<R>&, const BlockArgs<R>&, cudaStream_t);
+
+template <class S>
+cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
+                            cudaStream_t st) {
+  const unsigned grid = (unsigned)((A.M + NDS_BLOCK - 1) / NDS_BLOCK);
+  md_block<S><<<grid, NDS_BLOCK, 0, st>>>(K, A);
+  return cudaGetLastError();
+}
+
+template <typename R> struct prec_of { static constexpr int value = NDS_F64; };
+template <> struct prec_of<float> { static constexpr int value = NDS_F32; };
+
+template <class S>
+Variant make_variant(const char* name) {
+  return Variant{VariantKey{prec_of<typename S::R>::value, S::ND, S::POT, S::CV, S::TCV, S::INTEG,
+                            S::BIAS, S::METHOD, S::NOISE, S::DUMP},
+                 name, (void*)&launch_md_block<S>};
+}
+
+// one table per translation unit
+const Variant* variants_generic_f32_nd1(int* n);
+const Variant* variants_generic_f32_nd2(int* n);
+const Variant* variants_generic_f32_nd5(int* n);
+const Variant* variants_generic_f64_nd1(int* n);
+const Variant* variants_generic_f64_nd2(int* n);
+const Variant* variants_generic_f64_nd5(int* n);
+const Variant* variants_hot(int* n);
+
+}  // namespace nds

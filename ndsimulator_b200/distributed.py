@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
+
+Walkers shard trivially: rank r owns global walkers [r*M, (r+1)*M) and the Philox subsequence is the
+GLOBAL walker id, so results do not depend on the number of ranks.  The only
+exchange on the path is shared-hill metadynamics: every deposition stride each rank writes its M new
+hill records into its slot of the next table segment and the segment is completed by ONE in-place
+allgather (M x hill_stride reals per rank).
+"""
+import os
+
+import numpy as np
+
+
+def shard_config(cfg: dict, n_walkers_per_rank: int = None) -> dict:
+    """Fill device / walker_offset / n_walkers_global from the torchrun environment."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    out = dict(cfg)
+    M = int(n_walkers_per_rank or out.get("n_walkers", 1))
+    out.update(n_walkers=M, walker_offset=rank * M, n_walkers_global=world * M, device=local_rank)
+    return out
+
+
+class _DevSegment:
+    """__cuda_array_interface__ view of raw device memory (lets torch wrap the engine's hill table)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2}
+
+
+def attach_hill_exchange(engine, group=None):
+    """Complete each new hill segment with torch.distributed.all_gather_into_tensor (in place)."""
+    import torch
+    import torch.distributed as dist
+
+    def exchange(ptr, bytes_per_rank, rank_offset_bytes):
+        world = dist.get_world_size(group)
+        seg = torch.as_tensor(_DevSegment(ptr, bytes_per_rank * world), device="cuda")
+        mine = seg[rank_offset_bytes:rank_offset_bytes + bytes_per_rank]
+        dist.all_gather_into_tensor(seg, mine, group=group)
+        torch.cuda.current_stream().synchronize()
+        return 0
+
+    engine.set_exchange(exchange)
+    return engine
+
+
+def gather_commit_counts(basin: np.ndarray, n_basins: int, group=None):
+    """Sum of per-basin commit counts over ranks (the only reduction C3 needs)."""
+    import torch
+    import torch.distributed as dist
+    counts = np.array([(basin == b).sum() for b in range(-1, n_basins)], dtype=np.int64)
+    if dist.is_available() and dist.is_initialized():
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.from_numpy(counts).to(dev)
+        dist.all_reduce(t, group=group)
+        counts = t.cpu().numpy()
+    return counts

@@ -1,0 +1,220 @@
+"""Thin numpy-facing wrapper over the C ABI (``include/ndsb200.h``).  One :class:`Engine` = one
+``nds_engine`` handle = M walkers on one GPU.  All arrays are float64, SoA ``[d][M]``."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import NdsConfig
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class NdsError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, cfg: NdsConfig):
+        self.lib = _abi.load_library()
+        self.cfg = cfg
+        self.M = int(cfg.n_walkers)
+        self.ndim = int(cfg.ndim)
+        self.cd = self.lib.nds_colvar_dim(cfg.colvar, cfg.ndim)
+        self.h = C.c_void_p()
+        if self.lib.nds_create(C.byref(cfg), C.byref(self.h)):
+            raise NdsError(self.lib.nds_last_error(None).decode())
+        self._exchange_cb = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nds_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise NdsError(self.lib.nds_last_error(self.h).decode())
+
+    # ---- state
+    def set_state(self, x, v=None):
+        x = _f64(x, (self.ndim, self.M))
+        v = None if v is None else _f64(v, (self.ndim, self.M))
+        self._check(self.lib.nds_set_state(self.h, _p(x), _p(v)))
+
+    def set_walker_bias(self, k, r0):
+        k = _f64(k, (self.cd, self.M))
+        r0 = _f64(r0, (self.cd, self.M))
+        self._check(self.lib.nds_set_walker_bias(self.h, _p(k), _p(r0)))
+
+    def set_noise(self, noise, first_step=0):
+        noise = _f64(noise)
+        self._check(self.lib.nds_set_noise(self.h, _p(noise), int(first_step), int(noise.shape[0])))
+
+    def begin(self):
+        self._check(self.lib.nds_begin(self.h))
+
+    def run(self, nsteps, sync=True):
+        self._check(self.lib.nds_run(self.h, int(nsteps)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._check(self.lib.nds_sync(self.h))
+
+    def get_state(self, fields=("x", "v", "f", "fixf", "colv", "thermo")):
+        M, nd, cd = self.M, self.ndim, self.cd
+        bufs = dict(x=np.empty((nd, M)), v=np.empty((nd, M)), f=np.empty((nd, M)),
+                    fixf=np.empty((nd, M)), colv=np.empty((cd, M)), thermo=np.empty((5, M)))
+        args = [(_p(bufs[k]) if k in fields else None) for k in ("x", "v", "f", "fixf", "colv", "thermo")]
+        self._check(self.lib.nds_get_state(self.h, *args))
+        out = {k: bufs[k] for k in fields if k != "thermo"}
+        if "thermo" in fields:
+            t = bufs["thermo"]
+            out.update(T=t[0], pe=t[1], ke=t[2], biase=t[3], totale=t[4])
+        return out
+
+    @property
+    def step(self):
+        return int(self.lib.nds_step(self.h))
+
+    @property
+    def time(self):
+        return float(self.lib.nds_time(self.h))
+
+    # ---- deterministic evaluation
+    def eval_at(self, x):
+        x = _f64(x).reshape(self.ndim, -1)
+        n, nd, cd = x.shape[1], self.ndim, self.cd
+        V, Vb = np.empty(n), np.empty(n)
+        F, Fb = np.empty((nd, n)), np.empty((nd, n))
+        colv, J = np.empty((cd, n)), np.empty((cd, nd, n))
+        self._check(self.lib.nds_eval_at(self.h, _p(x), n, _p(V), _p(F), _p(colv), _p(J), _p(Vb), _p(Fb)))
+        return dict(V=V, F=F, colv=colv, J=J, Vb=Vb, Fb=Fb)
+
+    # ---- metadynamics
+    def n_hills(self, walker=0):
+        return int(self.lib.nds_n_hills(self.h, walker))
+
+    def get_hills(self, walker=0):
+        n = self.n_hills(walker)
+        c, w = np.empty((n, self.cd)), np.empty(n)
+        nn = C.c_int64()
+        self._check(self.lib.nds_get_hills(self.h, walker, C.byref(nn), _p(c), _p(w), n))
+        return c, w
+
+    def set_hills(self, centers, heights, walker=-1):
+        c = _f64(centers).reshape(-1, self.cd)
+        w = _f64(heights).reshape(-1)
+        self._check(self.lib.nds_set_hills(self.h, walker, len(w), _p(c), _p(w)))
+
+    def get_vr(self):
+        vr = np.empty(self.M)
+        self._check(self.lib.nds_get_vr(self.h, _p(vr)))
+        return vr
+
+    def set_exchange(self, fn):
+        """fn(dev_segment_ptr:int, bytes_per_rank:int, rank_offset_bytes:int) -> int (0 = ok)."""
+        def tramp(_user, ptr, nbytes, off):
+            try:
+                return int(fn(ptr, nbytes, off) or 0)
+            except Exception as e:  # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._exchange_cb = _abi.EXCHANGE_FN(tramp)
+        self._check(self.lib.nds_set_exchange(self.h, self._exchange_cb, None))
+
+    def fes_grid(self, x0, dx, nx, y0=0.0, dy=1.0, ny=1, walker=0):
+        g = np.empty((ny, nx))
+        self._check(self.lib.nds_fes_grid(self.h, walker, x0, dx, nx, y0, dy, ny, _p(g)))
+        return g
+
+    def colvar_histogram(self, x0, dx, nx, y0=0.0, dy=1.0, ny=1):
+        counts = np.zeros((ny, nx), dtype=np.int64)
+        self._check(self.lib.nds_colvar_histogram(self.h, x0, dx, nx, y0, dy, ny,
+                                                  counts.ctypes.data_as(C.POINTER(C.c_int64))))
+        return counts
+
+    # ---- committor
+    def get_commit(self):
+        basin = np.empty(self.M, dtype=np.int32)
+        exit_step = np.empty(self.M, dtype=np.int64)
+        self._check(self.lib.nds_get_commit(self.h, basin.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            exit_step.ctypes.data_as(C.POINTER(C.c_int64))))
+        return basin, exit_step
+
+    def count_alive(self):
+        return int(self.lib.nds_count_alive(self.h))
+
+    # ---- frames
+    @property
+    def frame_width(self):
+        return int(self.lib.nds_frame_width(self.h))
+
+    def frames_pending(self):
+        return int(self.lib.nds_frames_pending(self.h))
+
+    def drain_frames(self):
+        """-> array ``[n_frames][frame_width][dump_walkers]`` (possibly empty)."""
+        n = self.frames_pending()
+        dw = int(min(self.cfg.dump_walkers, self.M))
+        out = np.empty((n, self.frame_width, dw))
+        got = C.c_int64()
+        self._check(self.lib.nds_drain_frames(self.h, _p(out), n, C.byref(got)))
+        return out[:got.value]
+
+    def frame_fields(self):
+        nd, cd = self.ndim, self.cd
+        names = ["step", "time"] + [f"x{d}" for d in range(nd)] + [f"v{d}" for d in range(nd)] + \
+                [f"f{d}" for d in range(nd)] + [f"c{k}" for k in range(cd)] + \
+                ["T", "pe", "ke", "biase", "totale", "VR"]
+        return names
+
+    # ---- plumbing / introspection
+    def device_pointers(self):
+        x, v, h = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        s = C.c_int64()
+        self._check(self.lib.nds_device_pointers(self.h, C.byref(x), C.byref(v), C.byref(h), C.byref(s)))
+        return dict(x=x.value, v=v.value, hills=h.value, hill_stride=s.value)
+
+    @property
+    def stream(self):
+        return self.lib.nds_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.nds_launch_count(self.h))
+
+    def last_run_ms(self):
+        return float(self.lib.nds_last_run_ms(self.h))
+
+    @property
+    def kernel_name(self):
+        return self.lib.nds_kernel_name(self.h).decode()
+
+
+def philox_kat(ctr, key, device=0):
+    lib = _abi.load_library()
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    out = (C.c_uint32 * 4)()
+    if lib.nds_philox_kat(device, c, k, out):
+        raise NdsError(lib.nds_last_error(None).decode())
+    return list(out)

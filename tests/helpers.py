@@ -35,3 +35,44 @@ def scaled_err(a, b):
     a = np.asarray(a, dtype=float)
     b = np.asarray(b, dtype=float)
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+# ---------------------------------------------------------------------------- Philox4x32-10 (numpy)
+def philox4x32_10(ctr, key):
+    """Reference implementation of Philox4x32-10 (Salmon et al., SC'11; Random123) on Python ints."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(v) & 0xFFFFFFFF for v in ctr]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF,
+             ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return c
+
+
+# Random123 known-answer vectors (kat_vectors: philox4x32 10)
+PHILOX_KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def philox_normals_f64(seed, walker, n_normals, domain=0):
+    """The engine's fp64 normal stream of one walker (ndsimulator_b200/csrc/nds_philox.cuh)."""
+    k0 = seed & 0xFFFFFFFF
+    k1 = ((seed >> 32) & 0xFFFFFFFF) ^ domain
+    out = []
+    call = 0
+    while len(out) < n_normals:
+        r = philox4x32_10((call & 0xFFFFFFFF, call >> 32, walker & 0xFFFFFFFF, walker >> 32), (k0, k1))
+        for a, b in ((r[0], r[1]), (r[2], r[3])):
+            u1 = (a + 1.0) * 2.3283064365386963e-10
+            u2 = b * 2.3283064365386963e-10
+            rad = np.sqrt(-2.0 * np.log(u1))
+            out += [rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)]
+        call += 1
+    return np.array(out[:n_normals])

@@ -1,0 +1,403 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star):
+  * deterministic paths (NVE, zero-friction Langevin, bias / force evaluation at given configurations,
+    and every integrator when the Gaussian numbers are supplied externally) in fp64:
+      - per-step relative error <= 1e-10, checked over 10^4 steps (one-step map along the oracle
+        trajectory, every state advanced by one step on the GPU);
+      - whole 10^4-step trajectories within 1e-9 of the oracle (ulp-level differences of exp / FMA
+        contraction amplified by the dynamics; the oracle itself is within 6e-14 of the NumPy reference);
+  * stochastic paths (Philox noise): statistical agreement with oracle ensembles (KS tests, effective
+    temperature of the reference's integrator quirk A1/A6, committor fractions) -- tests/test_stats_gpu.py.
+"""
+import numpy as np
+import pytest
+
+from ndsimulator_b200 import _abi
+from ndsimulator_b200.engine import Engine
+from oracle import oracle
+from tests.helpers import load_golden, spec_from, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10   # per-step relative error, fp64
+TRAJ_TOL = 1e-9    # 10^4-step trajectory, fp64
+
+
+def make_pair(cfg, M=1, seeds=None, **extra):
+    spec = spec_from(cfg, n_walkers=M, **extra)
+    st = spec.to_struct()
+    eng = Engine(st)
+    orc = oracle.OracleSim(st, seeds=seeds if seeds is not None else list(range(M)))
+    return spec, eng, orc
+
+
+# ------------------------------------------------------------------------------ point evaluations
+@pytest.mark.parametrize("idx", range(23))
+def test_eval_points(idx):
+    rec = load_golden("eval_points.json")[idx]
+    cfg = dict(rec["config"], x0=rec["points"][0], mass=1.0, integrate="nve")
+    spec, eng, orc = make_pair(cfg)
+    pts = np.array(rec["points"]).T
+    r = eng.eval_at(pts)
+    n = pts.shape[1]
+    # against the fixtures generated from the Python reference
+    assert np.allclose(r["V"], rec["V"], rtol=1e-11, atol=1e-300)
+    assert np.allclose(r["F"].T, np.array(rec["F"]), rtol=1e-10, atol=1e-17)
+    assert np.allclose(r["colv"].T, np.array(rec["colv"]), rtol=1e-13, atol=0)
+    J = np.array(rec["J"]).reshape(n, spec.colvardim, spec.ndim)
+    assert np.allclose(np.moveaxis(r["J"], 2, 0), J, rtol=1e-13, atol=0)
+    # and against the oracle on more points
+    rng = np.random.RandomState(idx)
+    lo, hi = pts.min(), pts.max()
+    more = rng.uniform(lo, hi, size=(spec.ndim, 2000))
+    a, b = eng.eval_at(more), orc.eval_at(more)
+    for k in ("V", "F", "colv", "J"):
+        assert scaled_err(a[k], b[k]) < 1e-11, k
+
+
+@pytest.mark.parametrize("idx", range(10))
+def test_bias_points(idx):
+    rec = load_golden("bias_points.json")[idx]
+    cfg = dict(rec["config"], mass=1.0, integrate="nve")
+    if "mtd" in cfg["biases"]:
+        cfg["mtd_capacity"] = 64
+    spec, eng, orc = make_pair(cfg)
+    if "hills_centers" in rec and "mtd" in cfg["biases"]:
+        eng.set_hills(np.array(rec["hills_centers"]), np.array(rec["hills_heights"]))
+        orc.set_hills(np.array(rec["hills_centers"]), np.array(rec["hills_heights"]))
+    pts = np.array(rec["points"]).T
+    r = eng.eval_at(pts)
+    assert np.allclose(r["Vb"], rec["Vb"], rtol=1e-11, atol=1e-300)
+    assert np.allclose(r["Fb"].T, np.array(rec["Fb"]), rtol=1e-10, atol=1e-15)
+    rng = np.random.RandomState(idx)
+    more = rng.uniform(pts.min(), pts.max(), size=(spec.ndim, 1000))
+    a, b = eng.eval_at(more), orc.eval_at(more)
+    assert scaled_err(a["Vb"], b["Vb"]) < 1e-11
+    assert scaled_err(a["Fb"], b["Fb"]) < 1e-11
+
+
+# -------------------------------------------------------------------- one-step map over 10^4 steps
+MD2D = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md", temperature=300,
+            dt=1.0, seed=7)
+
+
+@pytest.mark.parametrize("integrate,gamma", [("nve", 0.0), ("langevin", 0.0)])
+def test_one_step_map_10k(integrate, gamma):
+    """Every state of a 10^4-step oracle trajectory is advanced by ONE step on the GPU (10^4 walkers in
+    one launch) and compared with the oracle's next state: relative error per step <= 1e-10."""
+    n = 10000
+    cfg = dict(MD2D, integrate=integrate, gamma=gamma)
+    spec, _, orc = make_pair(cfg, M=1, seeds=[7])
+    orc.set_state(spec.x0.reshape(-1, 1))
+    orc.begin()
+    v0 = orc.get_state()["v"].copy()
+    x0 = spec.x0.reshape(-1, 1).copy()
+    traj = orc.run(n, traj_every=1)
+    fr = orc.split_frame(traj)
+    xs = np.concatenate([x0.T, fr["x"][:-1, :, 0]], axis=0).T  # states 0..n-1
+    vs = np.concatenate([v0.T, fr["v"][:-1, :, 0]], axis=0).T
+    spec2 = spec_from(cfg, n_walkers=n)
+    eng = Engine(spec2.to_struct())
+    eng.set_state(xs, vs)
+    eng.begin()
+    eng.run(1)
+    st = eng.get_state()
+    assert scaled_err(st["x"], fr["x"][:, :, 0].T) < STEP_TOL
+    assert scaled_err(st["v"], fr["v"][:, :, 0].T) < STEP_TOL
+    assert scaled_err(st["pe"], fr["pe"][:, 0]) < STEP_TOL
+    assert scaled_err(st["f"], fr["f"][:, :, 0].T) < STEP_TOL
+    assert scaled_err(st["totale"], fr["totale"][:, 0]) < STEP_TOL
+
+
+# ------------------------------------------------------------------ golden deterministic trajectories
+TRAJ = load_golden("trajectories.json")
+DETERMINISTIC = ["2d_nve_seed7", "2d_langevin_gamma0_seed7", "2d_rescale_seed3",
+                 "1d_doublewell_nve_seed4", "2d_threehole_nve_seed5"]
+
+
+@pytest.mark.parametrize("name", DETERMINISTIC)
+def test_trajectories(name):
+    """fp64 trajectories against the fixtures of the Python reference (initial velocity injected)."""
+    rec = TRAJ[name]
+    cfg = rec["config"]
+    spec = spec_from(cfg, steps_per_launch=rec["sample_every"])
+    eng = Engine(spec.to_struct())
+    eng.set_state(spec.x0.reshape(-1, 1), np.array(rec["v0"]).reshape(-1, 1))
+    eng.begin()
+    st = eng.get_state()
+    for k in ("pe", "ke", "T", "totale"):
+        assert st[k][0] == pytest.approx(rec["begin"][k], rel=1e-12)
+    got = {k: [] for k in ("x", "v", "f", "colv", "pe", "ke", "totale", "T")}
+    prev = 0
+    for s in rec["steps"]:
+        eng.run(s - prev)
+        prev = s
+        st = eng.get_state()
+        for k in got:
+            got[k].append(st[k][..., 0].copy())
+    for k in got:
+        assert scaled_err(np.array(got[k]).reshape(len(rec["steps"]), -1),
+                          np.array(rec[k]).reshape(len(rec["steps"]), -1)) < TRAJ_TOL, k
+    assert eng.step == rec["steps"][-1]
+    assert eng.time == rec["final_time"]
+
+
+# -------------------------------------------------- every integrator / bias with externally given noise
+def noise_table(seed, nsteps, nn, M):
+    return np.random.RandomState(seed).normal(size=(nsteps, nn, M))
+
+
+EXT_CASES = {
+    "langevin_2d": (dict(MD2D, integrate="langevin", gamma=0.1), 2000, 32),
+    "langevin2_2d": (dict(MD2D, integrate="2nd-langevin", gamma=0.01), 2000, 32),
+    "langevin_1d_dw": (dict(ndim=1, mass=1.0, potential="DoubleWell1d", potential_K1=1.5, x0=30.0,
+                            gamma=0.1, dt=1.0, temperature=300), 2000, 16),
+    "umb_5d": (dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+                    true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0], biases=["umb"],
+                    umb_k=0.1, umb_r0=[18, 18], integrate="2nd-langevin", md_gamma=0.01, dt=1.0,
+                    temperature=300.0), 2000, 16),
+    "umb2_2d_rotate": (dict(MD2D, integrate="langevin", gamma=0.1, colvar_name="Rotate2d",
+                            biases=["umb"], umb_n=2, umb_0_k=0.1, umb_0_r0=[30, 0], umb_1_k=0.05,
+                            umb_1_r0=[28, 2]), 1000, 8),
+    "pe_doublewell": (dict(ndim=2, mass=1.0, potential="DoubleWell", x0=[20.0, 12.0], gamma=0.05,
+                           biases=["pe"], pe_thred=-0.45, dt=1.0, temperature=300), 1500, 8),
+    "threehole_5d": (dict(ndim=5, mass=1.0, potential="ThreeHole5d", colvar_name="Proj5dto2d",
+                          true_colvar_name="Proj5dto2d", x0=[7.0, 1.0, 9.0, 1.0, 3.0], gamma=0.1,
+                          dt=0.5, temperature=3000), 1000, 8),
+    "mueller5dshl_v2": (dict(ndim=5, mass=1.0, potential="Mueller5dshl", colvar_name="Proj5dto2dv2",
+                             true_colvar_name="Proj5dto2dv2", x0=[18.0, 3.0, 18.0, 1.0, 1.0],
+                             gamma=0.1, dt=1.0, temperature=300), 1000, 8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXT_CASES))
+def test_external_noise_trajectory(name):
+    """With the Gaussian numbers supplied by the caller every integrator is deterministic: M walkers,
+    each with its own noise, must follow the oracle within the trajectory tolerance."""
+    cfg, nsteps, M = EXT_CASES[name]
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=250)
+    nn = {"langevin": spec.ndim, "2nd-langevin": 2 * spec.ndim}[spec.integrate]
+    noise = noise_table(11, nsteps, nn, M)
+    rng = np.random.RandomState(5)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.3, size=(spec.ndim, M))
+    v0 = rng.normal(scale=0.01, size=(spec.ndim, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, v0)
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(nsteps)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "f", "fixf", "colv", "pe", "ke", "biase", "totale", "T"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+
+
+def test_mtd_single_walker_external_noise():
+    """examples/2d-mtd.yaml semantics (deposition schedule, stale-VR tempering, force refresh)."""
+    cfg = dict(MD2D, x0=[22.0, 30.0], integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05,
+               mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0, steps=3000)
+    spec, eng, orc = make_pair(cfg, M=1, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=1000)
+    noise = noise_table(3, 3000, 2, 1)
+    for sim in (eng, orc):
+        sim.set_state(spec.x0.reshape(-1, 1), np.array([[0.01], [-0.02]]))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(3000)
+    ce, we = eng.get_hills()
+    co, wo = orc.get_hills()
+    assert len(we) == len(wo) == 30
+    assert we[0] == 0.05
+    assert np.allclose(we, wo, rtol=1e-9)
+    assert np.allclose(ce, co, rtol=1e-9)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "fixf", "biase", "totale"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+    assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
+    # FES estimate on the reference's plot grid (bias/gaus.py:365-393, io/plot.py:517-519)
+    ga = eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40)
+    gb = orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40)
+    assert scaled_err(ga, gb) < 1e-9
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_mtd_multi_walker_external_noise(shared):
+    """New semantics: M walkers deposit together; shared table (multiple-walker metadynamics) or one
+    table per walker (M independent copies of the reference run)."""
+    M = 12
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=50,
+               mtd_biasf=10.0, steps=600, mtd_shared=shared)
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    noise = noise_table(9, 600, 5, M)
+    rng = np.random.RandomState(1)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.5, size=(5, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, rng.normal(scale=0.0, size=(5, M)))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(600)
+    for wk in (0, M - 1):
+        ce, we = eng.get_hills(wk)
+        co, wo = orc.get_hills(wk)
+        assert len(we) == len(wo) == (12 * M if shared else 12)
+        assert np.allclose(we, wo, rtol=1e-9) and np.allclose(ce, co, rtol=1e-9)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "biase"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+
+
+def test_committor_external_noise():
+    """Basin id and exit step must be identical (same inclusive fp64 comparisons, committor.py:127-140)."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], steps=4000)
+    M = 256
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=500)
+    noise = noise_table(21, 4000, 2, M)
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    v0 = np.random.RandomState(2).normal(scale=0.0157, size=(2, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, v0)
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(4000)
+    be, se = eng.get_commit()
+    bo, so = orc.get_commit()
+    assert np.array_equal(be, bo)
+    assert np.array_equal(se, so)
+    assert (be >= 0).sum() > 10  # the case does commit
+    assert eng.count_alive() == int((be < 0).sum())
+    a, b = eng.get_state(), orc.get_state()
+    assert scaled_err(a["x"], b["x"]) < TRAJ_TOL
+
+
+def test_committor_golden_velocities():
+    """The reference's own shots (tests/golden/committor.json): same v0 but Philox noise cannot match
+    MT19937 -- so only gamma-independent facts are checked here: uncommitted walkers report the full
+    step count and basin -1."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], steps=200)
+    spec = spec_from(cfg, n_walkers=8)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), 8, axis=1))
+    eng.begin()
+    eng.run(200)
+    basin, exit_step = eng.get_commit()
+    assert set(np.unique(basin)) <= {-1, 0, 1}
+    assert np.all(exit_step[basin < 0] == 200)
+
+
+def test_umbrella_windows_per_walker():
+    """Per-walker (k, r0): walker w with window (k_w, r0_w) must equal a single-walker run of that window."""
+    base = EXT_CASES["umb_5d"][0]
+    M, nsteps = 6, 500
+    cfg = dict(base, umb_per_walker=True)
+    spec, eng, _ = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL)
+    noise = noise_table(4, nsteps, 10, M)
+    r0 = np.array([[10 + 4 * w for w in range(M)], [30 - 3 * w for w in range(M)]], dtype=float)
+    k = np.array([[0.1 + 0.01 * w for w in range(M)], [0.1] * M])
+    x0 = np.stack([r0[0], np.zeros(M), r0[1], np.zeros(M), np.full(M, 100.0)])
+    eng.set_state(x0, np.zeros((5, M)))
+    eng.set_walker_bias(k, r0)
+    eng.set_noise(noise)
+    eng.begin()
+    eng.run(nsteps)
+    a = eng.get_state()
+    for w in range(M):
+        c1 = dict(base, umb_k=list(k[:, w]), umb_r0=list(r0[:, w]))
+        s1 = spec_from(c1, n_walkers=1, noise_mode=_abi.NDS_NOISE_EXTERNAL).to_struct()
+        o = oracle.OracleSim(s1, seeds=[0])
+        o.set_state(x0[:, w:w + 1], np.zeros((5, 1)))
+        o.set_noise(noise[:, :, w:w + 1])
+        o.begin()
+        o.run(nsteps)
+        b = o.get_state()
+        assert scaled_err(a["x"][:, w], b["x"][:, 0]) < TRAJ_TOL
+        assert scaled_err(a["biase"][w:w + 1], b["biase"]) < TRAJ_TOL
+
+
+def test_frames_match_oracle():
+    """Frames recorded on the device (io/dump.py content) equal the oracle's trajectory rows."""
+    cfg = dict(MD2D, integrate="langevin", gamma=0.1, dump=True, dump_freq=10, stat_freq=1, steps=200,
+               dump_walkers=3)
+    M = 5
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    noise = noise_table(8, 200, 2, M)
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    v0 = np.random.RandomState(3).normal(scale=0.01, size=(2, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, v0)
+        sim.set_noise(noise)
+        sim.begin()
+    eng.run(200)
+    traj = orc.run(200, traj_every=1)
+    fr = orc.split_frame(traj)
+    frames = eng.drain_frames()
+    names = eng.frame_fields()
+    steps = frames[:, names.index("step"), 0].astype(int)
+    # dump steps 0,10,...,200 and the lagged stat samples 9,19,...,199
+    assert list(steps) == sorted([0] + list(range(10, 201, 10)) + list(range(9, 200, 10)))
+    for i, s in enumerate(steps):
+        if s == 0:
+            assert np.allclose(frames[i, names.index("x0"), :], x0[0, :3])
+            continue
+        for d in range(2):
+            assert scaled_err(frames[i, names.index(f"x{d}"), :], fr["x"][s - 1, d, :3]) < TRAJ_TOL
+            assert scaled_err(frames[i, names.index(f"f{d}"), :], fr["f"][s - 1, d, :3]) < TRAJ_TOL
+        assert scaled_err(frames[i, names.index("pe"), :], fr["pe"][s - 1, :3]) < TRAJ_TOL
+        assert scaled_err(frames[i, names.index("T"), :], fr["T"][s - 1, :3]) < TRAJ_TOL
+    assert eng.frames_pending() == 0
+
+
+def test_launch_boundaries_do_not_change_results():
+    """K (steps per launch) is an execution detail: Philox noise is indexed by the global step."""
+    cfg = dict(MD2D, integrate="langevin", gamma=0.1, seed=123)
+    outs = []
+    for K in (1000, 37, 1):
+        spec = spec_from(cfg, n_walkers=64, steps_per_launch=K)
+        eng = Engine(spec.to_struct())
+        eng.set_state(np.repeat(spec.x0.reshape(-1, 1), 64, axis=1))
+        eng.begin()
+        eng.run(300)
+        outs.append(eng.get_state())
+    for o in outs[1:]:
+        assert scaled_err(o["x"], outs[0]["x"]) < 1e-11
+        assert scaled_err(o["v"], outs[0]["v"]) < 1e-11
+
+
+def test_walker_offset_makes_sharding_invisible():
+    """Rank r owning walkers [off, off+M) reproduces the same walkers of a single-rank run."""
+    cfg = dict(MD2D, integrate="2nd-langevin", gamma=0.01, seed=5)
+    spec = spec_from(cfg, n_walkers=96)
+    full = Engine(spec.to_struct())
+    full.set_state(np.repeat(spec.x0.reshape(-1, 1), 96, axis=1))
+    full.begin()
+    full.run(200)
+    a = full.get_state()
+    spec2 = spec_from(cfg, n_walkers=32, walker_offset=64, n_walkers_global=96)
+    part = Engine(spec2.to_struct())
+    part.set_state(np.repeat(spec.x0.reshape(-1, 1), 32, axis=1))
+    part.begin()
+    part.run(200)
+    b = part.get_state()
+    assert np.array_equal(a["x"][:, 64:], b["x"])
+    assert np.array_equal(a["v"][:, 64:], b["v"])
+
+
+def test_fp32_one_step_close_to_fp64():
+    """fp32 kernels (fast MUFU forms) stay within single-precision distance of the fp64 path per step."""
+    rng = np.random.RandomState(0)
+    M = 4096
+    x0 = np.stack([rng.uniform(10, 40, M), rng.uniform(5, 35, M)])
+    v0 = rng.normal(scale=0.0157, size=(2, M))
+    outs = {}
+    for prec in ("f64", "f32"):
+        spec = spec_from(dict(MD2D, integrate="nve"), n_walkers=M, precision=prec)
+        eng = Engine(spec.to_struct())
+        eng.set_state(x0, v0)
+        eng.begin()
+        eng.run(1)
+        outs[prec] = eng.get_state()
+    assert scaled_err(outs["f32"]["x"], outs["f64"]["x"]) < 1e-6
+    assert np.max(np.abs(outs["f32"]["f"] - outs["f64"]["f"])) < 1e-5 * np.max(np.abs(outs["f64"]["f"]))
+    assert np.max(np.abs(outs["f32"]["pe"] - outs["f64"]["pe"])) < 2e-6

@@ -1,0 +1,201 @@
+"""GPU statistical-parity tests for the stochastic paths (Philox noise cannot reproduce MT19937 draws).
+
+The comparison ensembles come from the oracle, which reproduces the reference's own stochastic runs bit
+for bit (tests/test_oracle_golden.py), i.e. "the reference's own runs" of BASELINE.json north_star.
+Acceptance thresholds are stated per test; the KS tests use p > 1e-3 on independent walkers.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from ndsimulator_b200.engine import Engine
+from oracle import oracle
+from tests.helpers import load_golden, spec_from, philox_normals_f64
+
+pytestmark = pytest.mark.gpu
+
+MD2D = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md", temperature=300,
+            dt=1.0, seed=0)
+kB = 8.6173303e-5
+
+
+def test_initial_velocities_are_philox_normals():
+    """v0 = sqrt(kB T / m) * N(0,1) (modify.py:44-54) from the documented Philox stream (domain 1)."""
+    M = 1 << 16
+    spec = spec_from(dict(MD2D, integrate="nve"), n_walkers=M, walker_offset=5, n_walkers_global=M + 5,
+                     seed=1234567890123)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
+    eng.begin()
+    st = eng.get_state()
+    scale = np.sqrt(kB * 300 / (104.23315626367025 * 1.0))
+    z = st["v"] / scale
+    for w in (0, 1, 777, M - 1):  # exact stream check against the Python restatement
+        want = philox_normals_f64(1234567890123, w + 5, 2, domain=1)
+        assert np.allclose(z[:, w], want, rtol=1e-12, atol=1e-14)
+    assert stats.kstest(z.reshape(-1), "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 4 / np.sqrt(z.size)
+    assert abs(z.var() - 1) < 0.02
+    assert abs(np.corrcoef(z[0], z[1])[0, 1]) < 0.02
+    assert st["T"].mean() == pytest.approx(300.0, rel=0.02)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_fp32_normals_moments(precision):
+    """Per-step noise: on a flat potential one Langevin step from v=0 gives v = c2 (1 + c1) xi."""
+    M = 1 << 18
+    cfg = dict(MD2D, potential="Flat2d", gamma=0.1, integrate="langevin")
+    spec = spec_from(cfg, n_walkers=M, precision=precision)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.zeros((2, M)), np.zeros((2, M)))
+    eng.begin()
+    eng.run(1)
+    v = eng.get_state()["v"]
+    c1 = np.exp(-0.05)
+    c2 = np.sqrt((1 - c1 ** 2) * kB * 300 / 104.23315626367025)
+    z = (v / (c2 * (1 + c1))).reshape(-1)
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 4 / np.sqrt(z.size)
+    assert abs(z.var() - 1) < 0.01
+    assert abs(stats.kurtosis(z)) < 0.05
+    assert np.abs(z).max() > 4.0  # tails are populated
+
+
+@pytest.mark.parametrize("integrate,gamma,dt", [("langevin", 0.1, 1.0), ("langevin", 1.0, 1.0),
+                                                ("2nd-langevin", 0.01, 1.0), ("2nd-langevin", 0.1, 2.0)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_effective_temperature_quirks(integrate, gamma, dt, precision):
+    """The reference's integrators do not sample T: free-particle stationary variance is
+    (kBT/m)(1+c1)^2/(1+c1^2) for langevin and (1+a)^2 (c3^2+c4^2)/(1-a^4) for 2nd-langevin.  The engine
+    must reproduce those, not the textbook value."""
+    M = 1 << 16
+    cfg = dict(MD2D, potential="Flat2d", gamma=gamma, dt=dt, integrate=integrate)
+    spec = spec_from(cfg, n_walkers=M, precision=precision)
+    st = spec.to_struct()
+    eng = Engine(st)
+    eng.set_state(np.zeros((2, M)))
+    eng.begin()
+    eng.run(400)
+    T = eng.get_state()["T"].mean()
+    c = oracle.OracleSim(st, seeds=[0]).constants()
+    m = c["m"]
+    if integrate == "langevin":
+        var = (kB * 300 / m) * (1 + c["c1"]) ** 2 / (1 + c["c1"] ** 2)
+    else:
+        a = 1 - c["c2"]
+        var = (1 + a) ** 2 * (c["c3"] ** 2 + c["c4"] ** 2) / (1 - a ** 4)
+    T_eff = m * var / kB
+    assert T == pytest.approx(T_eff, rel=0.02)
+    assert abs(T_eff - 300) > 1 or integrate == "2nd-langevin"
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_cv_histograms_match_oracle_ensemble(precision):
+    """C2 physics (2-D Mueller Langevin, gamma=0.1): two-sample KS on the x and y marginals and on the
+    potential energy of independent walkers after 2000 steps, GPU (Philox) vs oracle (MT19937)."""
+    M, nsteps = 4096, 2000
+    cfg = dict(MD2D, integrate="langevin", gamma=0.1)
+    spec = spec_from(cfg, n_walkers=M, precision=precision)
+    st = spec.to_struct()
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    eng = Engine(st)
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(nsteps)
+    a = eng.get_state()
+    orc = oracle.OracleSim(st, seeds=np.arange(1000, 1000 + M))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(x0)
+    orc.begin()
+    orc.run(nsteps)
+    b = orc.get_state()
+    for name, u, v in (("x", a["x"][0], b["x"][0]), ("y", a["x"][1], b["x"][1]), ("pe", a["pe"], b["pe"]),
+                       ("T", a["T"], b["T"])):
+        p = stats.ks_2samp(u, v).pvalue
+        assert p > 1e-3, (name, p)
+    # <T> agrees within the standard error of the two ensembles (and shows the A1 signature ~ 2T)
+    se = np.sqrt(a["T"].var() / M + b["T"].var() / M)
+    assert abs(a["T"].mean() - b["T"].mean()) < 5 * se
+    assert 500 < a["T"].mean() < 700
+    # on-device histogram equals a host histogram of the same state
+    h = eng.colvar_histogram(0.0, 1.0, 48, 0.0, 1.0, 40)
+    hh, _, _ = np.histogram2d(a["colv"][1], a["colv"][0], bins=[np.arange(0, 41.0), np.arange(0, 49.0)])
+    if precision == "f64":
+        assert np.array_equal(h, hh.astype(np.int64))
+    else:
+        assert np.abs(h - hh).sum() <= 4  # fp32 -> fp64 bin-edge rounding
+
+
+def test_committor_fraction_within_binomial_ci():
+    """C3: p(basin 1 | committed) from 8192 GPU shots vs 2048 oracle shots (and the reference's own 24
+    shots in tests/golden/committor.json): two-proportion z-test at 95 % (z < 1.96 -> use 3 for a
+    deterministic CI-friendly bound), exit-step distribution by KS."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"])
+    Mg, Mo = 8192, 2048
+    spec = spec_from(cfg, n_walkers=Mg, precision="f64")
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), Mg, axis=1))
+    eng.begin()
+    eng.run(cfg["steps"])
+    bg, sg = eng.get_commit()
+    spec_o = spec_from(cfg, n_walkers=Mo)
+    orc = oracle.OracleSim(spec_o.to_struct(), seeds=np.arange(100, 100 + Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(np.repeat(spec.x0.reshape(-1, 1), Mo, axis=1))
+    orc.begin()
+    orc.run(cfg["steps"])
+    bo, so = orc.get_commit()
+
+    def frac(b):
+        c = (b >= 0).sum()
+        return (b == 1).sum() / c, c
+
+    pg, ng = frac(bg)
+    po, no = frac(bo)
+    p = (pg * ng + po * no) / (ng + no)
+    z = abs(pg - po) / np.sqrt(p * (1 - p) * (1 / ng + 1 / no))
+    assert z < 3.0, (pg, po, z)
+    # committed fraction
+    cg, co = (bg >= 0).mean(), (bo >= 0).mean()
+    pc = (cg * Mg + co * Mo) / (Mg + Mo)
+    assert abs(cg - co) / np.sqrt(pc * (1 - pc) * (1 / Mg + 1 / Mo)) < 3.0
+    assert stats.ks_2samp(sg[bg >= 0], so[bo >= 0]).pvalue > 1e-3
+    # the reference's own 24 shots: 6 -> basin 0, 8 -> basin 1 (binomial 95 % CI contains pg)
+    ref = np.array([s["basin"] for s in g["shots"]])
+    k, n = (ref == 1).sum(), (ref >= 0).sum()
+    lo, hi = stats.binomtest(int(k), int(n)).proportion_ci(0.95)
+    assert lo <= pg <= hi
+
+
+def test_mtd_fes_matches_oracle_ensemble():
+    """Free-energy surface estimate (sum of hills on the 48x40 grid, gaus.py:365-393) of a single-walker
+    well-tempered run, averaged over independent runs: GPU vs oracle within 0.1 kT RMS over the
+    visited region after aligning the additive constant."""
+    R, nsteps = 48, 20000
+    cfg = dict(MD2D, x0=[22.0, 30.0], integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05,
+               mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0, steps=nsteps, mtd_shared=False)
+    spec = spec_from(cfg, n_walkers=R, precision="f64")
+    st = spec.to_struct()
+    x0 = np.repeat(spec.x0.reshape(-1, 1), R, axis=1)
+    eng = Engine(st)
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(nsteps)
+    orc = oracle.OracleSim(st, seeds=np.arange(R))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(x0)
+    orc.begin()
+    orc.run(nsteps)
+    ga = np.mean([eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)], axis=0)
+    gb = np.mean([orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)], axis=0)
+    kT = kB * 300
+    mask = gb > 2 * kT  # region the bias has filled
+    assert mask.sum() > 50
+    d = (ga - gb)[mask]
+    d = d - d.mean()
+    # statistical error of the mean over R runs, estimated from the oracle's own run-to-run spread
+    per_run = np.array([orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w)[mask] for w in range(R)])
+    sem = per_run.std(axis=0).mean() / np.sqrt(R)
+    rms = np.sqrt((d ** 2).mean())
+    assert rms < max(0.1 * kT, 3 * np.sqrt(2) * sem), (rms / kT, sem / kT)
