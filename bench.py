@@ -120,7 +120,7 @@ def cpu_baseline(name, threads, target_seconds=12.0):
     from oracle import oracle
     from ndsimulator_b200 import config
     threads = threads or oracle.max_threads()
-    M = 64 * threads
+    M = 256 * threads
     spec = config.parse(workload_cfg(name, M, "f64"))
     x0, extra = initial_state(name, spec, M, 0)
 
@@ -137,7 +137,7 @@ def cpu_baseline(name, threads, target_seconds=12.0):
 
     probe_steps = 200
     dt = run(probe_steps)
-    nsteps = int(max(probe_steps, min(200000, probe_steps * target_seconds / max(dt, 1e-6))))
+    nsteps = int(max(probe_steps, min(2000000, probe_steps * target_seconds / max(dt, 1e-6))))
     dt = run(nsteps)
     return dict(value=M * nsteps / dt, unit="walker-steps/s", cores=threads, kind="port",
                 sample=f"{M} walkers x {nsteps} MD steps of workload {name} (fp64 scalar C oracle, "

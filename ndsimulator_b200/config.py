@@ -334,5 +334,6 @@ def parse(config: dict) -> RunSpec:
             cap = n_dep * per
         spec.mtd_capacity = int(cap)
     if spec.dump:
-        spec.dump_capacity = int(cfg.get("dump_capacity", spec.steps // max(spec.dump_freq, 1) + 2))
+        # dump rows + the lagged stat sample before each of them
+        spec.dump_capacity = int(cfg.get("dump_capacity", 2 * (spec.steps // max(spec.dump_freq, 1)) + 2))
     return spec

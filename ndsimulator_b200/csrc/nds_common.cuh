@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/ndsb200.h"
+#include "nds_philox.cuh"
 
 namespace nds {
 
@@ -62,6 +63,8 @@ struct Consts {
   long long diffusion_time;
   long long dump_freq, stat_freq, dump_walkers;
   unsigned int key0, key1;  // Philox key = seed
+  PhiloxKeys rk_step;       // round keys of the per-step noise stream (domain 0)
+  PhiloxKeys rk_init;       // round keys of the initial-velocity stream (domain 1)
 };
 
 // Per-launch arguments of the fused step kernel.

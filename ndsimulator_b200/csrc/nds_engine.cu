@@ -239,6 +239,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.dump_walkers = dumping ? (c.dump_walkers < c.n_walkers ? c.dump_walkers : c.n_walkers) : 0;
   K.key0 = (unsigned)(c.seed & 0xffffffffull);
   K.key1 = (unsigned)(c.seed >> 32);
+  K.rk_step = philox_round_keys(K.key0, K.key1);
+  K.rk_init = philox_round_keys(K.key0, K.key1 ^ 1u);
 }
 
 // -------------------------------------------------------------------------- variant lookup

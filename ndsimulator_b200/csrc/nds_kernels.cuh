@@ -139,7 +139,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     R z[4];
 #pragma unroll
     for (int d = 0; d < ND; d++) {
-      if ((d & 3) == 0) normals4<R>(K.key0, K.key1 ^ 1u, (unsigned long long)(d >> 2), gid, z);
+      if ((d & 3) == 0) normals4<R>(K.rk_init, (unsigned long long)(d >> 2), gid, z);
       v[d] = K.vel_scale * z[d & 3];
     }
   }
@@ -151,7 +151,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   if (A.refresh_vr && (bias_mask & BIAS_MTD)) A.vr[w] = e.vm;  // Gaussian.VR, gaus.py:292-293
   R f[ND];
 #pragma unroll
-  for (int d = 0; d < ND; d++) f[d] = e.fp[d] + e.fb[d];  // md.py:133
+  for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];  // md.py:133
 
   long long s = A.step0;
   const long long s_end = A.step0 + A.nsteps;
@@ -169,7 +169,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CG; c++) {
         R z4[4];
-        normals4<R>(K.key0, K.key1, (unsigned long long)(grp * CG + c), gid, z4);
+        normals4<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, z4);
 #pragma unroll
         for (int j = 0; j < 4; j++)
           if (4 * c + j < G * NN) zb[4 * c + j] = z4[j];
@@ -229,7 +229,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
         // ---- colvar, potential and biases at the new positions, md.py:179-188
         eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
 #pragma unroll
-        for (int d = 0; d < ND; d++) f[d] = e.fp[d] + e.fb[d];
+        for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];
         // ---- second half kick, md.py:190-198
 #pragma unroll
         for (int d = 0; d < ND; d++) {

@@ -40,21 +40,45 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, ui
   return c;
 }
 
+// Same function with the ten round keys precomputed (they are uniform over the whole run, so the
+// kernels read them from the constant bank instead of bumping them per thread).
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+
+__host__ __device__ inline PhiloxKeys philox_round_keys(uint32_t k0, uint32_t k1) {
+  PhiloxKeys r;
+  for (int i = 0; i < 10; i++) { r.k0[i] = k0 + (uint32_t)i * PHILOX_W0; r.k1[i] = k1 + (uint32_t)i * PHILOX_W1; }
+  return r;
+}
+
 #ifdef __CUDACC__
+__device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+    c = u32x4{hi1 ^ c.y ^ rk.k0[r], lo1, hi0 ^ c.w ^ rk.k1[r], lo0};
+  }
+  return c;
+}
+
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_approx(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Two standard normals from two 32-bit words (Box-Muller).
 // fp32: u1 in (0,1] from 24 bits feeds lg2.approx / sqrt.approx, the angle uses sin/cos.approx
 //       (MUFU pipe); fp64: full-precision log / sqrt / sincospi on 32-bit uniforms.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  // u1 = (a >> 8 + 1) * 2^-24 in (0, 1]; built with integer ops + one FFMA (no I2F on the XU pipe for
-  // the mantissa trick would need |u| in [1,2); the conversion below is a single I2F.
-  const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-08f;   // 2^-24
-  const float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;          // [0, 1)
-  // r = sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1)
-  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
+  // u1 = n * 2^-24 with n = (a >> 8) + 1 in [1, 2^24]  (never 0, never denormal):
+  //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 24)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
+  // angle = 2 pi * (b >> 8) * 2^-24                  -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
+  const float n = (float)((a >> 8) + 1u);
+  // |.|: at n = 2^24 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
+  const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), -1.3862943611198906f, 33.271064666877374f)));
+  const float ang = (float)(b >> 8) * 3.7450702829239655e-07f;  // 2 pi 2^-24
+  z0 = r * cos_approx(ang);
+  z1 = r * sin_approx(ang);
 }
 
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, double& z1) {
@@ -69,10 +93,10 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, d
 
 // Fill z[0..3] with the four normals of Philox call `call` of one walker.
 template <typename R>
-__device__ __forceinline__ void normals4(uint32_t k0, uint32_t k1, unsigned long long call,
+__device__ __forceinline__ void normals4(const PhiloxKeys& rk, unsigned long long call,
                                          unsigned long long walker, R (&z)[4]) {
   const u32x4 r = philox4x32_10(
-      u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, k0, k1);
+      u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);
 }

@@ -18,9 +18,10 @@ namespace nds {
 template <typename R> struct is_f32 { static constexpr bool value = false; };
 template <> struct is_f32<float> { static constexpr bool value = true; };
 
-NDS_DEV float nds_exp(float x) { return __expf(x); }
+NDS_DEV float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+NDS_DEV float nds_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
 NDS_DEV double nds_exp(double x) { return exp(x); }
-NDS_DEV float nds_exp2(float x) { return exp2f(x); }
+NDS_DEV float nds_exp2(float x) { return ex2_approx(x); }
 NDS_DEV float nds_sqrt(float x) { return sqrtf(x); }
 NDS_DEV double nds_sqrt(double x) { return sqrt(x); }
 NDS_DEV float nds_rcp(float x) { return __frcp_rn(x); }
@@ -168,7 +169,9 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
 // ---------------------------------------------------------------------------------- potentials
 // Sum of four anisotropic Gaussians in (q0, q1): V = sum A_i exp(a dx^2 + b dx dy + c dy^2) and the
 // gradient force g = -dV/dq.   potentials/mueller.py:30-44, potentials/three_hole.py:36-50.
-template <typename R, bool ENERGY>
+// BMASK: bit i set when term i has a non-zero cross coefficient b_i (class constants of the reference:
+// Mueller 0b1100, ThreeHole 0); lets the fp32 form drop the b terms at compile time.
+template <typename R, bool ENERGY, int BMASK = 0xF>
 NDS_DEV void four_gauss(const Consts<R>& K, R q0, R q1, R& V, R& g0, R& g1) {
   if constexpr (is_f32<R>::value) {
     // fast form: G = k * grad(exponent) with k = log2(e)/2, so that  exponent*log2(e) = dx*Gx + dy*Gy
@@ -177,13 +180,14 @@ NDS_DEV void four_gauss(const Consts<R>& K, R q0, R q1, R& V, R& g0, R& g1) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const R dx = q0 - K.gx[i], dy = q1 - K.gy[i];
-      const R Gx = fmaf(K.fb[i], dy, K.fa[i] * dx);
-      const R Gy = fmaf(K.fb[i], dx, K.fc[i] * dy);
+      const bool cross = (BMASK >> i) & 1;
+      const R Gx = cross ? fmaf(K.fb[i], dy, K.fa[i] * dx) : K.fa[i] * dx;
+      const R Gy = cross ? fmaf(K.fb[i], dx, K.fc[i] * dy) : K.fc[i] * dy;
       const R s = fmaf(dy, Gy, dx * Gx);
       const R t = K.fA[i] * nds_exp2(s);
-      fx = fmaf(-t, Gx, fx);
-      fy = fmaf(-t, Gy, fy);
-      if (ENERGY) e += t;
+      if (i == 0) { fx = -t * Gx; fy = -t * Gy; }
+      else { fx = fmaf(-t, Gx, fx); fy = fmaf(-t, Gy, fy); }
+      if (ENERGY) e = (i == 0) ? t : e + t;
     }
     g0 = fx; g1 = fy;
     if (ENERGY) V = e * (R)0.72134752044448170368;  // k: A = fA * k
@@ -220,7 +224,7 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
   if constexpr (ND == 2) {
     switch (pot) {
       case NDS_POT_MUELLER2D: {  // mueller.py:25-45
-        four_gauss<R, ENERGY>(K, x[0], x[1], V, f[0], f[1]);
+        four_gauss<R, ENERGY, 0xC>(K, x[0], x[1], V, f[0], f[1]);
       } break;
       case NDS_POT_DOUBLEWELL: {  // double_well.py:44-53
         const R a0 = x[0] - K.dw_x1[0], a1 = x[1] - K.dw_x1[1];
@@ -260,7 +264,8 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
 #pragma unroll
       for (int d = 0; d < ND; d++) g[d] = (R)0;
       R v = (R)0;
-      four_gauss<R, ENERGY>(K, o.c[0], o.c[1], v, g[0], g[1]);
+      if (threehole) four_gauss<R, ENERGY, 0x0>(K, o.c[0], o.c[1], v, g[0], g[1]);
+      else four_gauss<R, ENERGY, 0xC>(K, o.c[0], o.c[1], v, g[0], g[1]);
       if (threehole) {  // quartic confinement, three_hole.py:51-55
         const R dx = o.c[0] - K.th_x1, dy = o.c[1] - K.th_y1;
         const R dx2 = dx * dx, dy2 = dy * dy;

@@ -30,16 +30,29 @@ class _DevSegment:
                                          "version": 2}
 
 
+def exchange_segment(seg, bytes_per_rank, rank_offset_bytes, group=None):
+    """In-place allgather of one hill segment.  ``seg`` is a uint8 tensor of ``world * bytes_per_rank``
+    bytes (device memory under NCCL, host memory under gloo in the CPU tests); this rank's records
+    already sit at ``rank_offset_bytes``.  Afterwards every rank holds every rank's records, in global
+    walker order -- the layout the step kernel reads."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert seg.numel() == world * bytes_per_rank
+    assert rank_offset_bytes == dist.get_rank(group) * bytes_per_rank
+    mine = seg[rank_offset_bytes:rank_offset_bytes + bytes_per_rank].clone()
+    dist.all_gather_into_tensor(seg, mine, group=group)
+    return seg
+
+
 def attach_hill_exchange(engine, group=None):
-    """Complete each new hill segment with torch.distributed.all_gather_into_tensor (in place)."""
+    """Complete each new hill segment with torch.distributed.all_gather_into_tensor (NCCL)."""
     import torch
     import torch.distributed as dist
 
     def exchange(ptr, bytes_per_rank, rank_offset_bytes):
         world = dist.get_world_size(group)
         seg = torch.as_tensor(_DevSegment(ptr, bytes_per_rank * world), device="cuda")
-        mine = seg[rank_offset_bytes:rank_offset_bytes + bytes_per_rank]
-        dist.all_gather_into_tensor(seg, mine, group=group)
+        exchange_segment(seg, bytes_per_rank, rank_offset_bytes, group)
         torch.cuda.current_stream().synchronize()
         return 0
 

@@ -1,0 +1,43 @@
+"""Command line: ``python -m ndsimulator_b200.scripts.run <config.yaml>`` -- the reference's
+``ndsimulator <yaml>`` (ndsimulator/scripts/run.py:20-76) on the B200 engine.  Same YAML keys, same
+defaults (verbose=info, run_name=ndrun, seed=0, root=./); extra keys: n_walkers, precision,
+steps_per_launch, device, dump_walkers, mtd_shared, umb_per_walker."""
+import argparse
+import logging
+import time
+
+import yaml
+
+from ndsimulator_b200.ndrun import NDRun
+
+default_config = dict(verbose="info", run_name="ndrun", seed=0, root="./")  # scripts/run.py:17
+
+
+def parse_command_line(args=None):
+    parser = argparse.ArgumentParser(description="Run a ND simulation on the B200 multi-walker engine")
+    parser.add_argument("config", help="configuration file")
+    parser.add_argument("--set", nargs="*", default=[], metavar="KEY=VALUE",
+                        help="override YAML keys, e.g. --set n_walkers=65536 precision=f32")
+    ns = parser.parse_args(args=args)
+    config = dict(default_config)
+    with open(ns.config) as f:
+        config.update(yaml.safe_load(f))
+    for kv in ns.set:
+        k, v = kv.split("=", 1)
+        config[k] = yaml.safe_load(v)
+    return config
+
+
+def main(args=None):
+    start = time.time()
+    config = parse_command_line(args)
+    simulation = NDRun(**config)
+    simulation.begin()
+    simulation.run()
+    simulation.end()
+    logging.info(f"total time: {time.time() - start}")  # scripts/run.py:63-64
+    return simulation
+
+
+if __name__ == "__main__":
+    main()

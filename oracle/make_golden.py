@@ -297,9 +297,52 @@ def constants():
     dump("constants.json", out)
 
 
+def dump_files():
+    """Text dumps of the reference (io/dump.py) for deterministic runs: NVE and gamma=0 metadynamics."""
+    out = {}
+    cases = {
+        "2d_nve_dump10": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
+                              integrate="nve", temperature=300, dt=1.0, seed=7, steps=40, dump=True,
+                              dump_freq=10, screen=False),
+        "2d_mtd_gamma0_dump100": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 30.0],
+                                      method="md", integrate="langevin", gamma=0.0, temperature=300,
+                                      dt=1.0, seed=3, steps=300, biases=["mtd"], mtd_w=0.05,
+                                      mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0, dump=True,
+                                      dump_freq=100, screen=False),
+        "5d_umb_nve_stat10": dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+                                  true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0],
+                                  biases=["umb"], umb_k=0.1, umb_r0=[18, 18], integrate="nve", dt=1.0,
+                                  temperature=300.0, seed=2, steps=60, dump=True, dump_freq=20,
+                                  stat_freq=10, screen=False),
+        "2d_xmy_nve": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
+                           integrate="nve", colvar_name="XmY", temperature=300, dt=1.0, seed=7, steps=20,
+                           dump=True, dump_freq=10, screen=False),
+    }
+    for name, cfg in cases.items():
+        d = tempfile.mkdtemp()
+        sim = ref_stub.make_run(dict(cfg, root=d, run_name="r"))
+        sim.begin()
+        v0 = tolist(sim.atoms.velocities)
+        sim.run()
+        sim.end()
+        import logging
+        logging.shutdown()
+        files = {}
+        for fn in sorted(os.listdir(os.path.join(d, "r"))):
+            if fn.endswith(".dat"):
+                with open(os.path.join(d, "r", fn)) as f:
+                    files[fn] = f.read()
+        out[name] = dict(config=cfg, v0=v0, files=files)
+    dump("dump_files.json", out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dump_files":
+        dump_files()
+        sys.exit(0)
     eval_points()
     bias_points()
     constants()
     trajectories()
     committor()
+    dump_files()

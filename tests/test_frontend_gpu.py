@@ -1,0 +1,111 @@
+"""GPU: the NDRun-shaped front-end, the reference-format dump files and the CLI."""
+import os
+
+import numpy as np
+import pytest
+
+from ndsimulator_b200 import NDRun
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def tokens(text):
+    return [ln.split() for ln in text.split("\n")]
+
+
+def assert_same_text(got, want, rtol=1e-9, what=""):
+    """Same lines and tokens; numeric tokens agree to rtol, everything else exactly."""
+    g, w = tokens(got), tokens(want)
+    assert len(g) == len(w), (what, len(g), len(w))
+    for i, (a, b) in enumerate(zip(g, w)):
+        assert len(a) == len(b), (what, i, a, b)
+        for x, y in zip(a, b):
+            try:
+                fx, fy = float(x.strip("[]")), float(y.strip("[]"))
+            except ValueError:
+                assert x == y, (what, i, x, y)
+                continue
+            assert fx == pytest.approx(fy, rel=rtol, abs=1e-13), (what, i, x, y)
+            assert x.startswith("[") == y.startswith("["), (what, i, x, y)
+
+
+@pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve"])
+def test_dump_files_match_reference(name, tmp_path):
+    """pos/force/velocity/colvar/thermo/fix*.dat of deterministic runs against the files the Python
+    reference wrote (tests/golden/dump_files.json), including the lagged thermo row (A16)."""
+    rec = load_golden("dump_files.json")[name]
+    cfg = dict(rec["config"], root=str(tmp_path), run_name="r", screen=False, precision="f64")
+    sim = NDRun(**cfg)
+    sim.modify.set_velocity(v=np.array(rec["v0"]))
+    sim.begin()
+    sim.run()
+    sim.end()
+    for fn, want in rec["files"].items():
+        with open(os.path.join(str(tmp_path), "r", fn)) as f:
+            got = f.read()
+        assert_same_text(got, want, what=f"{name}/{fn}")
+    log = open(os.path.join(str(tmp_path), "r", "log")).read()
+    assert f"end condition {cfg['steps']} {cfg['steps']} True" in log
+
+
+def test_ndrun_protocol_and_atoms_view(tmp_path):
+    cfg = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md", integrate="nve",
+               temperature=300, dt=1.0, seed=7, steps=500, dump=False, screen=False, root=str(tmp_path),
+               n_walkers=4)
+    sim = NDRun(**cfg)
+    sim.begin()
+    e0 = sim.atoms.totale
+    assert sim.atoms.positions.tolist() == [22.0, 24.0]
+    sim.run()
+    sim.end()
+    assert sim.step == 500 and sim.time == 500.0
+    assert abs(sim.atoms.totale - e0) < 1e-3          # NVE: bounded energy error (1.9e-4)
+    assert sim.positions.shape == (2, 4)
+    assert not np.allclose(sim.positions[:, 0], sim.positions[:, 1])  # independent initial velocities
+    # set_seed + injected velocities reproduce a run exactly
+    sim2 = NDRun(**cfg)
+    sim2.begin()
+    sim2.run()
+    assert np.array_equal(sim2.positions, sim.positions)
+
+
+def test_committor_frontend(tmp_path):
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], root=str(tmp_path), run_name="c", dump=False, screen=False, n_walkers=512,
+               seed=3, precision="f32")
+    sim = NDRun(**cfg)
+    sim.begin()
+    sim.run()
+    sim.end()
+    assert sim.commit_basin in (-1, 0, 1)
+    assert sim.commit_basins.shape == (512,)
+    committed = sim.commit_basins >= 0
+    assert 0.2 < committed.mean() < 0.7               # reference: 205/480 committed within 10^4 steps
+    assert np.all(sim.exit_steps[~committed] == cfg["steps"])
+    log = open(os.path.join(str(tmp_path), "c", "log")).read()
+    assert "end condition" in log
+
+
+def test_cli_runs_reference_yaml(tmp_path):
+    import yaml
+    from ndsimulator_b200.scripts.run import main
+    cfg = dict(root=str(tmp_path), run_name="cli", ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0],
+               method="md", integration="langevin", gamma=1, temperature=300, dt=1.0, steps=200, dump=True,
+               dump_freq=10, movie=False, oneplot=True, plot=True, plot_boundary=[[0.0, 48.0], [0.0, 40.0]],
+               verbose="debug", screen=False)  # examples/2d-md.yaml keys, including the ignored ones
+    path = os.path.join(str(tmp_path), "run.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    sim = main([path, "--set", "n_walkers=8", "dump_walkers=2"])
+    assert sim.spec.integrate == "langevin"          # `integration:` is not a key
+    assert sim.step == 200
+    rows = open(os.path.join(str(tmp_path), "cli", "pos.dat")).read().strip().split("\n")
+    assert len(rows) == 21
+    assert os.path.exists(os.path.join(str(tmp_path), "cli", "walker_1", "thermo.dat"))
+
+
+def test_user_defined_python_colvar_is_rejected(tmp_path):
+    with pytest.raises(ValueError, match="cannot run on the B200 engine"):
+        NDRun(ndim=2, potential="Mueller2d", x0=[1.0, 2.0], colvar_name="my_colvar.NewColvar",
+              root=str(tmp_path), screen=False)

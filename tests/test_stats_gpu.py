@@ -77,7 +77,7 @@ def test_effective_temperature_quirks(integrate, gamma, dt, precision):
     eng.begin()
     eng.run(400)
     T = eng.get_state()["T"].mean()
-    c = oracle.OracleSim(st, seeds=[0]).constants()
+    c = oracle.OracleSim(spec_from(cfg, n_walkers=1).to_struct(), seeds=[0]).constants()
     m = c["m"]
     if integrate == "langevin":
         var = (kB * 300 / m) * (1 + c["c1"]) ** 2 / (1 + c["c1"] ** 2)
