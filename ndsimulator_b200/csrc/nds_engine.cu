@@ -12,6 +12,8 @@
 
 #include "nds_variants.h"
 
+namespace nds { constexpr int MTD_TILE_HOST = 1024; }  // == MTD_TILE of nds_mtd_kernel.cuh
+
 using namespace nds;
 
 // ---------------------------------------------------------------------------------- errors
@@ -272,6 +274,40 @@ static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dump
   return best;
 }
 
+// shared-hill metadynamics: pick the mtd_block variant with the best SM fill for M walkers
+static const MtdVariant* pick_mtd_variant(const nds_config& c, int bias_mask, int n_sm) {
+  typedef const MtdVariant* (*table_fn)(int*);
+  static const table_fn tables[] = {mtd_variants_f32_nd2, mtd_variants_f32_nd5, mtd_variants_f64_nd2,
+                                    mtd_variants_f64_nd5};
+  const int want[10] = {c.precision, c.ndim, c.potential, c.colvar, c.true_colvar, c.integrator,
+                        bias_mask, c.method, c.noise_mode, 0};
+  const MtdVariant* best = nullptr;
+  long long best_cost = 0;
+  int best_score = -1;
+  for (table_fn t : tables) {
+    int n = 0;
+    const MtdVariant* v = t(&n);
+    for (int i = 0; i < n; i++) {
+      const int have[10] = {v[i].key.prec, v[i].key.nd, v[i].key.pot, v[i].key.cv, v[i].key.tcv,
+                            v[i].key.integ, v[i].key.bias, v[i].key.method, v[i].key.noise, v[i].key.dump};
+      bool ok = true;
+      int score = 0;
+      for (int k = 0; k < 10 && ok; k++) {
+        if (have[k] == DYN) continue;
+        if (have[k] != want[k]) ok = false; else score++;
+      }
+      if (!ok) continue;
+      // time ~ waves x walkers-per-warp (every warp streams the whole table once per walker it owns)
+      const long long ctas = (c.n_walkers + (long long)v[i].W * v[i].NW - 1) / ((long long)v[i].W * v[i].NW);
+      const long long cost = ((ctas + n_sm - 1) / n_sm) * v[i].W;
+      if (!best || cost < best_cost || (cost == best_cost && score > best_score)) {
+        best = &v[i]; best_cost = cost; best_score = score;
+      }
+    }
+  }
+  return best;
+}
+
 static __global__ void philox_kat_kernel(u32x4 c, uint32_t k0, uint32_t k1, uint32_t* out) {
   const u32x4 r = philox4x32_10(c, k0, k1);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
@@ -322,7 +358,10 @@ struct Engine : nds_engine {
   }
 
   int64_t hill_elems() const {
-    return cfg.mtd_capacity * (int64_t)K.hill_stride * (cfg.mtd_shared ? 1 : M);
+    if (!cfg.mtd_shared) return cfg.mtd_capacity * (int64_t)K.hill_stride * M;
+    // shared table: padded with zero-height records to whole TMA tiles (mtd_block reads full tiles)
+    const int64_t cap = (cfg.mtd_capacity + MTD_TILE_HOST - 1) / MTD_TILE_HOST * MTD_TILE_HOST + MTD_TILE_HOST;
+    return cap * (int64_t)K.hill_stride;
   }
 
   int init(const nds_config& c) {
@@ -340,6 +379,12 @@ struct Engine : nds_engine {
     if (!var) return fail(this, "no compiled md_block variant matches this configuration");
     launch_block = (BlockLaunchFn<R>)var->launch;
     kernel_name = var->name;
+    if (c.mtd_enabled && c.mtd_shared && cd == 2 && c.method == NDS_METHOD_MD && !dumping) {
+      cudaDeviceProp prop;
+      CU(cudaGetDeviceProperties(&prop, c.device));
+      const MtdVariant* mv = pick_mtd_variant(c, K.bias_mask, prop.multiProcessorCount);
+      if (mv) { launch_block = (BlockLaunchFn<R>)mv->launch; kernel_name = mv->name; }
+    }
     const size_t sM = (size_t)M;
     CU(cudaMalloc(&d_x, sizeof(R) * nd * sM));
     CU(cudaMalloc(&d_v, sizeof(R) * nd * sM));
@@ -650,6 +695,7 @@ struct Engine : nds_engine {
         for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
         h[(size_t)(i * rs + cd)] = heights[i];
       }
+      CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)hill_elems(), stream));  // padding stays zero
       if (n && upload(h.data(), d_hills, n * rs)) return 1;
     } else {
       // per-walker tables: the given hills are installed for EVERY walker (walker < 0) or one walker

@@ -38,6 +38,18 @@ Variant make_variant(const char* name) {
                  name, (void*)&launch_md_block<S>};
 }
 
+// shared-hill metadynamics kernels (nds_mtd_kernel.cuh): W walkers per warp, NW warps per CTA
+struct MtdVariant {
+  VariantKey key;
+  int W, NW;
+  const char* name;
+  void* launch;
+};
+const MtdVariant* mtd_variants_f32_nd2(int* n);
+const MtdVariant* mtd_variants_f32_nd5(int* n);
+const MtdVariant* mtd_variants_f64_nd2(int* n);
+const MtdVariant* mtd_variants_f64_nd5(int* n);
+
 // one table per translation unit
 const Variant* variants_generic_f32_nd1(int* n);
 const Variant* variants_generic_f32_nd2(int* n);

@@ -401,3 +401,59 @@ def test_fp32_one_step_close_to_fp64():
     assert scaled_err(outs["f32"]["x"], outs["f64"]["x"]) < 1e-6
     assert np.max(np.abs(outs["f32"]["f"] - outs["f64"]["f"])) < 1e-5 * np.max(np.abs(outs["f64"]["f"]))
     assert np.max(np.abs(outs["f32"]["pe"] - outs["f64"]["pe"])) < 2e-6
+
+
+@pytest.mark.parametrize("integrate", ["langevin", "2nd-langevin"])
+def test_mtd_block_many_tiles(integrate):
+    """The TMA-tiled shared-hill kernel (mtd_block): table spanning several 1024-record tiles, walkers
+    not a multiple of the per-CTA count, against the oracle with external noise."""
+    M, nsteps = 45, 500
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate=integrate, gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=10,
+               mtd_biasf=10.0, steps=nsteps, mtd_shared=True)
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=100)
+    assert eng.kernel_name.startswith("mtd_block")
+    nn = 5 if integrate == "langevin" else 10
+    noise = noise_table(13, nsteps, nn, M)
+    rng = np.random.RandomState(2)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.5, size=(5, M))
+    v0 = rng.normal(scale=0.01, size=(5, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, v0)
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(nsteps)
+    ce, we = eng.get_hills()
+    co, wo = orc.get_hills()
+    assert len(we) == len(wo) == 50 * M > 2048
+    assert np.allclose(we, wo, rtol=1e-9) and np.allclose(ce, co, rtol=1e-9)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "f", "fixf", "biase", "pe", "totale"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+    assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
+
+
+def test_mtd_block_fp32_close_to_fp64():
+    """fp32 mtd_block (prescaled exponent, MUFU.EX2) vs the fp64 instantiation on a frozen table."""
+    M = 300
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=1e9,
+               mtd_biasf=10.0, steps=10, mtd_shared=True, mtd_capacity=5000)
+    rng = np.random.RandomState(4)
+    centers = rng.uniform(8, 18, size=(3000, 2))
+    heights = rng.uniform(0.01, 0.05, size=3000)
+    x0 = 12.0 + rng.normal(scale=1.0, size=(5, M))
+    outs = {}
+    for prec in ("f64", "f32"):
+        spec = spec_from(cfg, n_walkers=M, precision=prec)
+        eng = Engine(spec.to_struct())
+        assert eng.kernel_name.startswith("mtd_block")
+        eng.set_state(x0, np.zeros((5, M)))
+        eng.set_hills(centers, heights)
+        eng.begin()
+        outs[prec] = eng.get_state()
+    # begin deposits nothing; the table has the 3000 given hills
+    assert np.max(np.abs(outs["f32"]["biase"] - outs["f64"]["biase"])) < 2e-5 * np.max(outs["f64"]["biase"])
+    assert np.max(np.abs(outs["f32"]["fixf"] - outs["f64"]["fixf"])) < 1e-4 * np.max(np.abs(outs["f64"]["fixf"]))
