@@ -7,12 +7,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "nds_variants.h"
 
-namespace nds { constexpr int MTD_TILE_HOST = 1024; }  // == MTD_TILE of nds_mtd_kernel.cuh
+namespace nds { constexpr int MTD_TILE_HOST = 2048; }  // >= mtd_tile_records<R>() of nds_mtd_kernel.cuh
 
 using namespace nds;
 
@@ -299,7 +300,14 @@ static const MtdVariant* pick_mtd_variant(const nds_config& c, int bias_mask, in
       if (!ok) continue;
       // time ~ waves x walkers-per-warp (every warp streams the whole table once per walker it owns)
       const long long ctas = (c.n_walkers + (long long)v[i].W * v[i].NW - 1) / ((long long)v[i].W * v[i].NW);
-      const long long cost = ((ctas + n_sm - 1) / n_sm) * v[i].W;
+      // CTAs with a warp count that is not a multiple of 4 leave schedulers idle at every tile barrier
+      const long long slot = (v[i].NW % 2 == 0) ? 100 : 115;
+      long long cost = ((ctas + n_sm - 1) / n_sm) * v[i].W * slot;
+      if (const char* force = getenv("NDS_MTD_VARIANT")) {  // experiments: e.g. "W8,NW7"
+        char tag[32];
+        snprintf(tag, sizeof tag, "W%d,NW%d", v[i].W, v[i].NW);
+        if (strcmp(force, tag) == 0) cost = 0;
+      }
       if (!best || cost < best_cost || (cost == best_cost && score > best_score)) {
         best = &v[i]; best_cost = cost; best_score = score;
       }
@@ -364,6 +372,18 @@ struct Engine : nds_engine {
     return cap * (int64_t)K.hill_stride;
   }
 
+  int clear_hills() {
+    const int64_t n = hill_elems();
+    if (cfg.mtd_shared) {
+      const int64_t nrec = n / K.hill_stride;
+      fill_hills_kernel<R><<<(unsigned)((nrec + 255) / 256), 256, 0, stream>>>(nrec, K.hill_stride, cd, d_hills);
+      CU(cudaGetLastError());
+    } else {
+      CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)n, stream));
+    }
+    return 0;
+  }
+
   int init(const nds_config& c) {
     cfg = c;
     M = c.n_walkers;
@@ -407,7 +427,7 @@ struct Engine : nds_engine {
     }
     if (c.mtd_enabled) {
       CU(cudaMalloc(&d_hills, sizeof(R) * (size_t)hill_elems()));
-      CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)hill_elems(), stream));
+      if (clear_hills()) return 1;
     }
     if (c.method == NDS_METHOD_COMMITTOR) {
       CU(cudaMalloc(&d_alive, sM));
@@ -694,8 +714,9 @@ struct Engine : nds_engine {
       for (int64_t i = 0; i < n; i++) {
         for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
         h[(size_t)(i * rs + cd)] = heights[i];
+        for (int k = cd + 1; k < rs; k++) h[(size_t)(i * rs + k)] = std::log2(heights[i]);
       }
-      CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)hill_elems(), stream));  // padding stays zero
+      if (clear_hills()) return 1;  // padding records stay (0, 0, 0, -inf)
       if (n && upload(h.data(), d_hills, n * rs)) return 1;
     } else {
       // per-walker tables: the given hills are installed for EVERY walker (walker < 0) or one walker

@@ -369,7 +369,9 @@ __global__ void deposit_kernel(const __grid_constant__ Consts<R> K, long long M,
     R* rec = hills + (n_hills + walker_offset + w) * rs;
     for (int k = 0; k < cd; k++) rec[k] = colv[k * M + w];
     rec[cd] = h;
-    for (int k = cd + 1; k < rs; k++) rec[k] = (R)0;
+    // colvardim 2: the 4th word carries log2(height) for the MUFU-bound fp32 loop of mtd_block
+    // (-inf for a zero-height record, which then contributes exactly 0)
+    for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
   } else {
     for (int k = 0; k < cd; k++) hills[(n_hills * rs + k) * M + w] = colv[k * M + w];
     hills[(n_hills * rs + cd) * M + w] = h;
@@ -424,6 +426,14 @@ __global__ void histogram_kernel(long long M, int cd, const R* __restrict__ colv
   __syncthreads();
   for (int b = threadIdx.x; b < nb; b += blockDim.x)
     if (bins[b]) atomicAdd(&counts[b], (unsigned long long)bins[b]);
+}
+
+// empty hill records: height 0, log2(height) = -inf
+template <typename R>
+__global__ void fill_hills_kernel(long long n_records, int rs, int cd, R* hills) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_records) return;
+  for (int k = 0; k < rs; k++) hills[i * rs + k] = (k > cd) ? (R)(-INFINITY) : (R)0;
 }
 
 template <typename T>

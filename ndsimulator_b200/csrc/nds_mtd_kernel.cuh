@@ -3,9 +3,11 @@
 // mtd_block<Spec, W, NW>: the walker x hill interaction of bias/gaus.py:236-261 is the whole cost of
 // multiple-walker metadynamics (M walkers x H hills per MD step, H = M_total * depositions), so the
 // mapping is the opposite of md_block:
-//   * one CTA of NW warps per SM; the hill table streams through shared memory in tiles of MTD_TILE
-//     records with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), NBUF tiles in flight;
-//   * LANES ARE HILLS: lane l of every warp owns records l, l+32, ... of the tile (one LDS.128 each);
+//   * one CTA of NW*HS warps per SM; the hill table streams through shared memory in 32 KB tiles
+//     with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), NBUF tiles in flight;
+//   * LANES ARE HILLS: lane l of a warp owns records l, l+32*HS, ... of the tile (one LDS.128 each);
+//     HS warps share the same walkers and split every tile between them (more warps per scheduler
+//     without changing the walker -> CTA map), partial sums meet in shared memory once per step;
 //   * each warp carries W walkers; their colvars sit in registers of every lane (warp-shuffle broadcast),
 //     so one loaded hill is applied to W walkers: 8 FP32 ops + 1 MUFU.EX2 per walker-hill pair;
 //   * per step a warp-shuffle butterfly reduces (V, g0, g1) of the W walkers; lane w < W owns walker w:
@@ -17,8 +19,9 @@
 
 namespace nds {
 
-constexpr int MTD_TILE = 1024;  // hill records per shared-memory tile
-constexpr int MTD_NBUF = 3;     // tiles in flight
+constexpr int MTD_TILE_BYTES = 32768;  // one shared-memory tile: 2048 fp32 records / 1024 fp64 records
+constexpr int MTD_NBUF = 3;            // tiles in flight
+template <typename R> __host__ __device__ constexpr int mtd_tile_records() { return MTD_TILE_BYTES / (4 * (int)sizeof(R)); }
 
 NDS_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,18 +54,21 @@ NDS_DEV void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* b
 }
 
 template <typename R> struct HillRec;
-template <> struct HillRec<float> { float4 v; NDS_DEV float h0() const { return v.x; } NDS_DEV float h1() const { return v.y; } NDS_DEV float w() const { return v.z; } };
+template <> struct HillRec<float> { float4 v; NDS_DEV float h0() const { return v.x; } NDS_DEV float h1() const { return v.y; } NDS_DEV float w() const { return v.z; } NDS_DEV float lw() const { return v.w; } };
 template <> struct HillRec<double> { double4 v; NDS_DEV double h0() const { return v.x; } NDS_DEV double h1() const { return v.y; } NDS_DEV double w() const { return v.z; } };
 
 // One pass over the whole table for the W walkers of this warp.
 //   c0[w], c1[w]: colvars of walker w (identical in every lane).
 //   out: lane w receives (Vm, g0, g1) of walker w in CANONICAL units (gaus.py:252-258, before .dot(J)).
-template <typename R, int W, int NW, bool ENERGY>
+template <typename R, int W, int NW, int HS, bool ENERGY>
 NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long long n_tiles,
-                           unsigned char* smem, uint64_t* full, uint32_t& tile_counter,
+                           unsigned char* smem, uint64_t* full, R* red, uint32_t& tile_counter,
                            const R (&c0)[W], const R (&c1)[W], R& Vm, R& g0, R& g1) {
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t TILE_BYTES = MTD_TILE * 4 * sizeof(R);
+  const int warp = threadIdx.x >> 5;
+  const int wi = warp % NW, half = warp / NW;
+  constexpr uint32_t TILE_BYTES = MTD_TILE_BYTES;
+  constexpr int MTD_TILE = mtd_tile_records<R>();
   R aV[W], a0[W], a1[W];
 #pragma unroll
   for (int w = 0; w < W; w++) { aV[w] = (R)0; a0[w] = (R)0; a1[w] = (R)0; }
@@ -89,15 +95,32 @@ NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long
     mbar_wait(&full[b], (seq / MTD_NBUF) & 1u);
     const HillRec<R>* tile = reinterpret_cast<const HillRec<R>*>(smem + (size_t)b * TILE_BYTES);
 #pragma unroll 2
-    for (int j = lane; j < MTD_TILE; j += 32) {
+    for (int j = half * 32 + lane; j < MTD_TILE; j += 32 * HS) {
       const HillRec<R> h = tile[j];
       if constexpr (is_f32<R>::value) {
-        const R hx = h.h0() * p0, hy = h.h1() * p1, hw = h.w();
+        // Blackwell packed FP32 (FFMA2 / FADD2, sm_100 fma.rn.f32x2): two walkers per instruction,
+        // an odd last walker in scalar form.  The height enters through its log2 (4th word of the
+        // record, written at deposition):  w 2^-(d0^2+d1^2) = 2^-(d0^2 + d1^2 - log2 w),
+        // so a walker-hill pair costs 6 FP32 lane-ops (3 packed issue slots) + 1 MUFU.EX2 and the loop
+        // is bound by the MUFU pipe, not by instruction issue.
+        const R hx = h.h0() * p0, hy = h.h1() * p1, nl = -h.lw();
+        const float2 nhx = make_float2(-hx, -hx), nhy = make_float2(-hy, -hy), nlw = make_float2(nl, nl);
 #pragma unroll
-        for (int w = 0; w < W; w++) {
+        for (int w = 0; w + 1 < W; w += 2) {
+          const float2 d0 = __fadd2_rn(make_float2(s0[w], s0[w + 1]), nhx);
+          const float2 d1 = __fadd2_rn(make_float2(s1[w], s1[w + 1]), nhy);
+          const float2 e = __ffma2_rn(d1, d1, __ffma2_rn(d0, d0, nlw));
+          const float2 tt = make_float2(ex2_approx(-e.x), ex2_approx(-e.y));
+          if (ENERGY) { const float2 av = __fadd2_rn(make_float2(aV[w], aV[w + 1]), tt); aV[w] = av.x; aV[w + 1] = av.y; }
+          const float2 n0 = __ffma2_rn(tt, d0, make_float2(a0[w], a0[w + 1]));
+          const float2 n1 = __ffma2_rn(tt, d1, make_float2(a1[w], a1[w + 1]));
+          a0[w] = n0.x; a0[w + 1] = n0.y; a1[w] = n1.x; a1[w + 1] = n1.y;
+        }
+        if constexpr (W % 2 == 1) {
+          constexpr int w = W - 1;
           const R d0 = s0[w] - hx, d1 = s1[w] - hy;
-          const R e = fmaf(d1, d1, d0 * d0);
-          const R tt = hw * ex2_approx(-e);
+          const R e = fmaf(d1, d1, fmaf(d0, d0, nl));
+          const R tt = ex2_approx(-e);
           if (ENERGY) aV[w] += tt;
           a0[w] = fmaf(tt, d0, a0[w]);
           a1[w] = fmaf(tt, d1, a1[w]);
@@ -133,19 +156,35 @@ NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long
       x += __shfl_xor_sync(0xffffffffu, x, o);
       y += __shfl_xor_sync(0xffffffffu, y, o);
     }
-    if (lane == w) {
-      if constexpr (is_f32<R>::value) {
-        // back to canonical units: (c - h)/sigma^2 = d' / (p sigma^2)
-        Vm = v; g0 = x * (K.mtd_invsig2[0] / p0); g1 = y * (K.mtd_invsig2[1] / p1);
-      } else {
-        Vm = v; g0 = x; g1 = y;
-      }
+    if (lane == w) { Vm = v; g0 = x; g1 = y; }
+  }
+  if constexpr (HS > 1) {
+    // the HS warps that share these walkers add their partial sums in a fixed order, so every copy of a
+    // walker sees bit-identical totals
+    if (lane < W) {
+      R* slot = red + ((half * NW + wi) * W + lane) * 3;
+      slot[0] = Vm; slot[1] = g0; slot[2] = g1;
     }
+    __syncthreads();
+    if (lane < W) {
+      R tv = (R)0, t0 = (R)0, t1 = (R)0;
+#pragma unroll
+      for (int hh = 0; hh < HS; hh++) {
+        const R* slot = red + ((hh * NW + wi) * W + lane) * 3;
+        tv += slot[0]; t0 += slot[1]; t1 += slot[2];
+      }
+      Vm = tv; g0 = t0; g1 = t1;
+    }
+    __syncthreads();
+  }
+  if constexpr (is_f32<R>::value) {
+    // back to canonical units: (c - h)/sigma^2 = d' / (p sigma^2)
+    g0 *= K.mtd_invsig2[0] / p0; g1 *= K.mtd_invsig2[1] / p1;
   }
 }
 
-template <class S, int W, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+template <class S, int W, int NW, int HS>
+__global__ void __launch_bounds__(NW * HS * 32, 1)
 mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
   using R = typename S::R;
   constexpr int ND = S::ND;
@@ -157,10 +196,13 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[MTD_NBUF];
+  __shared__ R red[HS * NW * W * 3];
+  constexpr int MTD_TILE = mtd_tile_records<R>();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long M = A.M;
-  const long long w = ((long long)blockIdx.x * NW + warp) * W + lane;  // walker of this lane
+  // the HS warps {wi, wi + NW, ...} carry the same W walkers (identical copies of their state)
+  const long long w = ((long long)blockIdx.x * NW + (warp % NW)) * W + lane;  // walker of this lane
   const bool owner = lane < W && w < M;
 
   const int pot = S::POT >= 0 ? S::POT : K.pot;
@@ -214,8 +256,8 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
     R Vm, g[ND];
 #pragma unroll
     for (int d = 0; d < ND; d++) g[d] = (R)0;
-    if (energy) mtd_hill_pass<R, W, NW, true>(K, A.hills, n_tiles, smem, full, tile_counter, c0, c1, Vm, g[0], g[1]);
-    else mtd_hill_pass<R, W, NW, false>(K, A.hills, n_tiles, smem, full, tile_counter, c0, c1, Vm, g[0], g[1]);
+    if (energy) mtd_hill_pass<R, W, NW, HS, true>(K, A.hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
+    else mtd_hill_pass<R, W, NW, HS, false>(K, A.hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
     if (energy || (other_bias & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
     else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
     R vm_other;
@@ -237,7 +279,8 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   };
 
   evaluate(true);
-  if (A.refresh_vr && owner) A.vr[w] = e.vm;
+  const bool writer = owner && (warp / NW) == 0;  // one copy of each walker writes back
+  if (A.refresh_vr && writer) A.vr[w] = e.vm;
   R f[ND];
 #pragma unroll
   for (int d = 0; d < ND; d++) f[d] = e.fp[d] + e.fb[d];
@@ -313,7 +356,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
     }
   }
 
-  if (owner) {
+  if (writer) {
     R v2 = (R)0;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
@@ -334,16 +377,16 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   }
 }
 
-template <class S, int W, int NW>
+template <class S, int W, int NW, int HS>
 cudaError_t launch_mtd_block(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
                              cudaStream_t st) {
   using R = typename S::R;
-  const size_t smem = (size_t)MTD_NBUF * MTD_TILE * 4 * sizeof(R);
-  cudaError_t e = cudaFuncSetAttribute(mtd_block<S, W, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)MTD_NBUF * MTD_TILE_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(mtd_block<S, W, NW, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long per_cta = (long long)W * NW;
   const unsigned grid = (unsigned)((A.M + per_cta - 1) / per_cta);
-  mtd_block<S, W, NW><<<grid, NW * 32, smem, st>>>(K, A);
+  mtd_block<S, W, NW, HS><<<grid, NW * HS * 32, smem, st>>>(K, A);
   return cudaGetLastError();
 }
 

@@ -457,3 +457,70 @@ def test_mtd_block_fp32_close_to_fp64():
     # begin deposits nothing; the table has the 3000 given hills
     assert np.max(np.abs(outs["f32"]["biase"] - outs["f64"]["biase"])) < 2e-5 * np.max(outs["f64"]["biase"])
     assert np.max(np.abs(outs["f32"]["fixf"] - outs["f64"]["fixf"])) < 1e-4 * np.max(np.abs(outs["f64"]["fixf"]))
+
+
+def test_two_rank_shared_hills_emulated_on_one_gpu():
+    """N > 1 path of shared-hill metadynamics: two engines ("ranks", walkers [0,M) and [M,2M)) driven by
+    two host threads on one GPU, their exchange callbacks completing each new hill segment from the
+    peer's table (the role of the NCCL allgather), must reproduce one engine with 2M walkers exactly."""
+    import threading
+    import torch
+    from ndsimulator_b200.distributed import _DevSegment
+
+    M, nsteps = 20, 300
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=25,
+               mtd_biasf=10.0, steps=nsteps, mtd_shared=True, seed=77)
+    rng = np.random.RandomState(6)
+    x0 = 12.0 + rng.normal(scale=0.5, size=(5, 2 * M))
+    one = Engine(spec_from(cfg, n_walkers=2 * M).to_struct())
+    one.set_state(x0)
+    one.begin()
+    one.run(nsteps)
+    ref = one.get_state()
+    ref_hills = one.get_hills()
+
+    engines = [Engine(spec_from(cfg, n_walkers=M, walker_offset=r * M, n_walkers_global=2 * M).to_struct())
+               for r in range(2)]
+    barrier = threading.Barrier(2)
+    seg_ptr = [None, None]
+
+    def make_cb(r):
+        def cb(ptr, bytes_per_rank, rank_offset_bytes):
+            seg_ptr[r] = ptr
+            barrier.wait()
+            mine = torch.as_tensor(_DevSegment(seg_ptr[r], 2 * bytes_per_rank), device="cuda")
+            peer = torch.as_tensor(_DevSegment(seg_ptr[1 - r], 2 * bytes_per_rank), device="cuda")
+            po = (1 - r) * bytes_per_rank
+            mine[po:po + bytes_per_rank].copy_(peer[po:po + bytes_per_rank])
+            torch.cuda.synchronize()
+            barrier.wait()
+            return 0
+        return cb
+
+    errors = []
+
+    def drive(r):
+        try:
+            e = engines[r]
+            e.set_exchange(make_cb(r))
+            e.set_state(x0[:, r * M:(r + 1) * M])
+            e.begin()
+            e.run(nsteps)
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+            barrier.abort()
+
+    threads = [threading.Thread(target=drive, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    for r in range(2):
+        st = engines[r].get_state()
+        for k in ("x", "v", "biase"):
+            assert np.array_equal(st[k][..., :], ref[k][..., r * M:(r + 1) * M]), (r, k)
+        c, h = engines[r].get_hills()
+        assert np.array_equal(c, ref_hills[0]) and np.array_equal(h, ref_hills[1])
