@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/ndsb200.h"
+#include "nds_f2.cuh"
 #include "nds_philox.cuh"
 
 namespace nds {

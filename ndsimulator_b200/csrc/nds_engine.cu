@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "nds_variants.h"
@@ -247,7 +248,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
 }
 
 // -------------------------------------------------------------------------- variant lookup
-static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dumping) {
+static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dumping, int prec_override = -1) {
   typedef const Variant* (*table_fn)(int*);
   static const table_fn tables[] = {variants_hot,
                                     variants_generic_f32_nd1, variants_generic_f32_nd2,
@@ -255,8 +256,8 @@ static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dump
                                     variants_generic_f64_nd2, variants_generic_f64_nd5};
   const Variant* best = nullptr;
   int best_score = -1;
-  const int want[10] = {c.precision, c.ndim, c.potential, c.colvar, c.true_colvar, c.integrator,
-                        bias_mask, c.method, c.noise_mode, dumping ? 1 : 0};
+  const int want[10] = {prec_override >= 0 ? prec_override : c.precision, c.ndim, c.potential, c.colvar,
+                        c.true_colvar, c.integrator, bias_mask, c.method, c.noise_mode, dumping ? 1 : 0};
   for (table_fn t : tables) {
     int n = 0;
     const Variant* v = t(&n);
@@ -336,6 +337,10 @@ struct Engine : nds_engine {
   int64_t M = 0;
   int nd = 0;
   BlockLaunchFn<R> launch_block = nullptr;
+  // packed-FP32 variant of the step kernel (fp32 engines only): two walkers per thread
+  Consts<f2> K2;
+  BlockLaunchFn<f2> launch_packed = nullptr;
+  const char* packed_name = nullptr;
   // device state
   R *d_x = nullptr, *d_v = nullptr, *d_f = nullptr, *d_fixf = nullptr, *d_colv = nullptr;
   R *d_thermo = nullptr, *d_vr = nullptr, *d_umb_k = nullptr, *d_umb_r0 = nullptr, *d_hills = nullptr;
@@ -399,6 +404,15 @@ struct Engine : nds_engine {
     if (!var) return fail(this, "no compiled md_block variant matches this configuration");
     launch_block = (BlockLaunchFn<R>)var->launch;
     kernel_name = var->name;
+    if (std::is_same<R, float>::value && M % 2 == 0 && !getenv("NDS_NO_PACKED")) {
+      const Variant* pv = pick_variant(c, K.bias_mask, dumping, PREC_F32_PACKED);
+      if (pv) {
+        fill_consts<f2>(c, K2);
+        launch_packed = (BlockLaunchFn<f2>)pv->launch;
+        packed_name = pv->name;
+        kernel_name = pv->name;
+      }
+    }
     if (c.mtd_enabled && c.mtd_shared && cd == 2 && c.method == NDS_METHOD_MD && !dumping) {
       cudaDeviceProp prop;
       CU(cudaGetDeviceProperties(&prop, c.device));
@@ -606,7 +620,20 @@ struct Engine : nds_engine {
       }
       BlockArgs<R> A = make_args(k);
       A.refresh_vr = need_refresh_vr ? 1 : 0;
-      cudaError_t err = launch_block(K, A, stream);
+      cudaError_t err;
+      if (launch_packed) {
+        // same buffers, read as pairs: SoA float[d][M] == f2[d][M/2]
+        BlockArgs<f2> P;
+        memset(&P, 0, sizeof P);
+        P.M = M / 2; P.walker_offset = A.walker_offset; P.step0 = A.step0; P.nsteps = A.nsteps;
+        P.time0 = A.time0; P.rescale_count = A.rescale_count;
+        P.x = (f2*)A.x; P.v = (f2*)A.v; P.f = (f2*)A.f; P.fixf = (f2*)A.fixf; P.colv = (f2*)A.colv;
+        P.thermo = (f2*)A.thermo; P.vr = (f2*)A.vr;
+        P.umb_k = (const f2*)A.umb_k; P.umb_r0 = (const f2*)A.umb_r0;
+        err = launch_packed(K2, P, stream);
+      } else {
+        err = launch_block(K, A, stream);
+      }
       if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
       launches++;
       need_refresh_vr = false;

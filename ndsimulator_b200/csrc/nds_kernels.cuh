@@ -100,6 +100,10 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   using R = typename S::R;
   constexpr int ND = S::ND;
   constexpr int INTEG = S::INTEG;  // always compile-time
+  constexpr int PACK = pack_of<R>::value;  // walkers per thread (2 for the packed-FP32 real type f2)
+  static_assert(PACK == 1 || (S::METHOD == NDS_METHOD_MD && S::NOISE == NDS_NOISE_PHILOX && S::DUMP == 0 &&
+                              S::BIAS >= 0 && (S::BIAS & (BIAS_PE | BIAS_MTD)) == 0),
+                "packed kernels: md, Philox noise, no frames, no PE / metadynamics bias");
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
   constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
@@ -117,7 +121,9 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   const bool ext_noise = S::NOISE >= 0 ? (S::NOISE == NDS_NOISE_EXTERNAL) : (K.noise == NDS_NOISE_EXTERNAL);
   const bool dumping = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0)) && w < K.dump_walkers;
 
-  if (committor && !A.alive[w]) return;
+  if constexpr (PACK == 1) {
+    if (committor && !A.alive[w]) return;
+  }
 
   // ---- load walker state (coalesced SoA)
   R x[ND], v[ND];
@@ -131,7 +137,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     for (int k = 0; k < ND; k++)
       if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
-  const unsigned long long gid = (unsigned long long)(A.walker_offset + w);
+  const unsigned long long gid = (unsigned long long)(A.walker_offset + w * PACK);
   const long long hstride = K.mtd_shared ? 1 : M;
   const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
 
@@ -180,7 +186,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
       if (i >= first && s < s_end && alive) {
         R xi[ND], eta[ND];
         if (NN > 0) {
-          if (ext_noise) {  // md.py:120,127-128 with numbers supplied by the caller (parity tests)
+          if (PACK == 1 && ext_noise) {  // md.py:120,127-128 with numbers supplied by the caller (parity tests)
             const double* row = A.noise + ((s - A.noise_first) * NN) * M + w;
 #pragma unroll
             for (int d = 0; d < ND; d++) {
@@ -267,17 +273,19 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
         }
         s += 1;            // ndrun.py:232
         time += K.dt64;    // ndrun.py:240
-        if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
-          basin = commit_test<R, ND>(K, cd, e.cv.c);
-          if (basin >= 0) alive = false;
+        if constexpr (PACK == 1) {
+          if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
+            basin = commit_test<R, ND>(K, cd, e.cv.c);
+            if (basin >= 0) alive = false;
+          }
+          if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
+            // io/dump.py:76-102: full observables of this walker at NDRun.step == s
+            Eval<R, ND> o;
+            eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+            write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
+          }
+          if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
         }
-        if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
-          // io/dump.py:76-102: full observables of this walker at NDRun.step == s
-          Eval<R, ND> o;
-          eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
-          write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
-        }
-        if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
       }
     }
   }
@@ -303,12 +311,14 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   A.thermo[2 * M + w] = ke;
   A.thermo[3 * M + w] = o.be;
   A.thermo[4 * M + w] = A.begin_mode ? ke + o.pe : o.pe + ke + o.be;  // ndrun.py:196 / md.py:229
-  if (committor) {
-    if (!alive) { A.alive[w] = 0; A.exit_step[w] = s; }
-    A.basin[w] = basin;
+  if constexpr (PACK == 1) {
+    if (committor) {
+      if (!alive) { A.alive[w] = 0; A.exit_step[w] = s; }
+      A.basin[w] = basin;
+    }
+    // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
+    if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
   }
-  // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
-  if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
 }
 
 // ---------------------------------------------------------------------------------- eval_at

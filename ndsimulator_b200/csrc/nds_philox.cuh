@@ -12,6 +12,7 @@
 //   lanes (0,1) and (2,3) are the two Box-Muller pairs of a call.
 #pragma once
 #include <cstdint>
+#include "nds_f2.cuh"
 
 namespace nds {
 
@@ -91,7 +92,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, d
   z1 = r * s;
 }
 
-// Fill z[0..3] with the four normals of Philox call `call` of one walker.
+// Fill z[0..3] with the four normals of Philox call `call` of one walker (for f2: of the walker pair
+// (walker, walker + 1), one Philox call each).
 template <typename R>
 __device__ __forceinline__ void normals4(const PhiloxKeys& rk, unsigned long long call,
                                          unsigned long long walker, R (&z)[4]) {
@@ -99,6 +101,16 @@ __device__ __forceinline__ void normals4(const PhiloxKeys& rk, unsigned long lon
       u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);
+}
+
+template <>
+__device__ __forceinline__ void normals4<f2>(const PhiloxKeys& rk, unsigned long long call,
+                                             unsigned long long walker, f2 (&z)[4]) {
+  float a[4], b[4];
+  normals4<float>(rk, call, walker, a);
+  normals4<float>(rk, call, walker + 1ull, b);
+#pragma unroll
+  for (int j = 0; j < 4; j++) z[j] = f2(a[j], b[j]);
 }
 #endif
 

@@ -15,8 +15,12 @@ namespace nds {
 
 #define NDS_DEV __device__ __forceinline__
 
+// is_f32: fp32 arithmetic (scalar float or the packed pair f2) -> MUFU / re-associated fast forms
 template <typename R> struct is_f32 { static constexpr bool value = false; };
 template <> struct is_f32<float> { static constexpr bool value = true; };
+template <> struct is_f32<f2> { static constexpr bool value = true; };
+template <typename R> struct is_scalar_f32 { static constexpr bool value = false; };
+template <> struct is_scalar_f32<float> { static constexpr bool value = true; };
 
 NDS_DEV float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 NDS_DEV float nds_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
@@ -26,6 +30,10 @@ NDS_DEV float nds_sqrt(float x) { return sqrtf(x); }
 NDS_DEV double nds_sqrt(double x) { return sqrt(x); }
 NDS_DEV float nds_rcp(float x) { return __frcp_rn(x); }
 NDS_DEV double nds_rcp(double x) { return 1.0 / x; }
+NDS_DEV f2 nds_exp(f2 x) { return f2(nds_exp(x.v.x), nds_exp(x.v.y)); }
+NDS_DEV f2 nds_exp2(f2 x) { return f2(ex2_approx(x.v.x), ex2_approx(x.v.y)); }
+NDS_DEV f2 nds_sqrt(f2 x) { return f2(sqrtf(x.v.x), sqrtf(x.v.y)); }
+NDS_DEV f2 nds_rcp(f2 x) { return f2(__frcp_rn(x.v.x), __frcp_rn(x.v.y)); }
 
 // colvardim of a colvar id (colvars/*.py class attribute `colvardim`)
 __host__ __device__ constexpr int cv_dim(int cv, int ndim) {
@@ -300,9 +308,9 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
 #pragma unroll
   for (int k = 0; k < ND; k++) g[k] = (R)0;
   const int rs = K.hill_stride;
-  if (cd == 2 && elem_stride == 1) {
+  if (pack_of<R>::value == 1 && cd == 2 && elem_stride == 1) {
     // 16/32-byte records (h0, h1, w, pad): one vector load per hill, warp-uniform address (broadcast)
-    if constexpr (is_f32<R>::value) {
+    if constexpr (is_scalar_f32<R>::value) {
       const float4* __restrict__ h4 = reinterpret_cast<const float4*>(hills);
 #pragma unroll 4
       for (long long i = 0; i < n_hills; i++) {
@@ -315,7 +323,7 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
         g[0] = fmaf(vr, s0, g[0]);
         g[1] = fmaf(vr, s1, g[1]);
       }
-    } else {
+    } else if constexpr (pack_of<R>::value == 1) {
       const double2* __restrict__ h2 = reinterpret_cast<const double2*>(hills);
 #pragma unroll 2
       for (long long i = 0; i < n_hills; i++) {
@@ -335,11 +343,11 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
 #pragma unroll
       for (int k = 0; k < ND; k++)
         if (k < cd) {
-          const R dc = c[k] - __ldg(h + k * elem_stride);
+          const R dc = c[k] - h[k * elem_stride];
           ds[k] = dc * K.mtd_invsig2[k];
           ex += (dc * dc) / (R)2.0 * K.mtd_invsig2[k];
         }
-      const R vr = __ldg(h + cd * elem_stride) * nds_exp(-ex);
+      const R vr = h[cd * elem_stride] * nds_exp(-ex);
       v += vr;
 #pragma unroll
       for (int k = 0; k < ND; k++)

@@ -28,8 +28,10 @@ cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<type
   return cudaGetLastError();
 }
 
+constexpr int PREC_F32_PACKED = 2;  // internal: fp32 with two walkers per thread (real type f2)
 template <typename R> struct prec_of { static constexpr int value = NDS_F64; };
 template <> struct prec_of<float> { static constexpr int value = NDS_F32; };
+template <> struct prec_of<f2> { static constexpr int value = PREC_F32_PACKED; };
 
 template <class S>
 Variant make_variant(const char* name) {
