@@ -45,6 +45,7 @@ struct Consts {
   R m, inv_m, dt, kB, kBT;
   R c1, c2, c3, c4, c5, v_target;
   R hdtm;           // dt / (2 m): fused half-kick factor of the fp32 path
+  R l2_a, l2_c1m, l2_c5dt;  // fp32 2nd-order Langevin: 1 - c2, c1 / m, c5 * dt
   R vel_scale;      // sqrt(kB * T_init / m)  (engines/modify.py:45)
   double dt64, rescale_freq;
   // four-Gaussian surfaces (Mueller*: potentials/mueller.py:8-16; ThreeHole*: three_hole.py:10-22)

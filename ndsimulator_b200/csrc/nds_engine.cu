@@ -178,6 +178,9 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
     K.c3 = (R)(std::sqrt(dt) * sigma / 2.0 * (1.0 - frdt / 4.0));
     K.c5 = (R)c5;
     K.c4 = (R)(frdt / 2.0 * c5);
+    K.l2_a = (R)(1.0 - (frdt / 2 - frdt * frdt / 8.0));
+    K.l2_c1m = (R)((dt / 2.0 - dt * frdt / 8.0) / m);
+    K.l2_c5dt = (R)(c5 * dt);
   } else if (c.integrator == NDS_INT_RESCALE) {  // md.py:76-79
     K.v_target = (R)std::sqrt(kBT * c.ndim / m);
   }

@@ -211,8 +211,9 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
               v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
               dx = v[d] * K.dt;
             } else if (INTEG == NDS_INT_LANGEVIN2) {
-              v[d] += K.c1 * f[d] * K.inv_m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
-              dx = K.dt * v[d] + K.c5 * eta[d] * K.dt;
+              // v += c1 f/m - c2 v + c3 xi - c4 eta  ==  a v + (c1/m) f + c3 xi - c4 eta,  a = 1 - c2
+              v[d] = fmaf(K.l2_a, v[d], fmaf(K.l2_c1m, f[d], fmaf(K.c3, xi[d], -(K.c4 * eta[d]))));
+              dx = fmaf(K.l2_c5dt, eta[d], K.dt * v[d]);
             } else {
               v[d] = fmaf(K.hdtm, f[d], v[d]);
               dx = v[d] * K.dt;
@@ -244,7 +245,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
               v[d] = fmaf(K.hdtm, f[d], v[d]);
               v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
             } else if (INTEG == NDS_INT_LANGEVIN2) {
-              v[d] += K.c1 * f[d] * K.inv_m - K.c2 * v[d] + K.c3 * xi[d] - K.c4 * eta[d];
+              v[d] = fmaf(K.l2_a, v[d], fmaf(K.l2_c1m, f[d], fmaf(K.c3, xi[d], -(K.c4 * eta[d]))));
             } else {
               v[d] = fmaf(K.hdtm, f[d], v[d]);
             }

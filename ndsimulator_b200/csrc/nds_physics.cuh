@@ -26,14 +26,19 @@ NDS_DEV float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : 
 NDS_DEV float nds_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
 NDS_DEV double nds_exp(double x) { return exp(x); }
 NDS_DEV float nds_exp2(float x) { return ex2_approx(x); }
-NDS_DEV float nds_sqrt(float x) { return sqrtf(x); }
+NDS_DEV float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+NDS_DEV float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+NDS_DEV float nds_sqrt(float x) { return sqrt_approx(x); }
 NDS_DEV double nds_sqrt(double x) { return sqrt(x); }
-NDS_DEV float nds_rcp(float x) { return __frcp_rn(x); }
+NDS_DEV float nds_rcp(float x) { return rcp_approx(x); }
+NDS_DEV float nds_rsqrt(float x) { return rsqrt_approx(x); }
+NDS_DEV double nds_rsqrt(double x) { return 1.0 / sqrt(x); }
 NDS_DEV double nds_rcp(double x) { return 1.0 / x; }
 NDS_DEV f2 nds_exp(f2 x) { return f2(nds_exp(x.v.x), nds_exp(x.v.y)); }
 NDS_DEV f2 nds_exp2(f2 x) { return f2(ex2_approx(x.v.x), ex2_approx(x.v.y)); }
-NDS_DEV f2 nds_sqrt(f2 x) { return f2(sqrtf(x.v.x), sqrtf(x.v.y)); }
-NDS_DEV f2 nds_rcp(f2 x) { return f2(__frcp_rn(x.v.x), __frcp_rn(x.v.y)); }
+NDS_DEV f2 nds_sqrt(f2 x) { return f2(sqrt_approx(x.v.x), sqrt_approx(x.v.y)); }
+NDS_DEV f2 nds_rcp(f2 x) { return f2(rcp_approx(x.v.x), rcp_approx(x.v.y)); }
+NDS_DEV f2 nds_rsqrt(f2 x) { return f2(rsqrt_approx(x.v.x), rsqrt_approx(x.v.y)); }
 
 // colvardim of a colvar id (colvars/*.py class attribute `colvardim`)
 __host__ __device__ constexpr int cv_dim(int cv, int ndim) {
@@ -50,8 +55,16 @@ __host__ __device__ constexpr int cv_dim(int cv, int ndim) {
 template <typename R, int ND>
 struct CvOut {
   R c[ND];
-  R q[2];  // norms (Proj*) for the Jacobian
+  R q[2];   // norms (Proj*) for the Jacobian
+  R iq[2];  // their reciprocals (fp32 fast path: one MUFU.RSQ gives both the norm and 1/norm)
 };
+
+// norm and reciprocal norm of a squared length
+template <typename R>
+NDS_DEV void norm_pair(R s, R& n, R& inv) {
+  if constexpr (is_f32<R>::value) { inv = nds_rsqrt(s); n = s * inv; }
+  else { n = nds_sqrt(s); inv = (R)0; }
+}
 
 template <typename R, int ND>
 NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
@@ -74,7 +87,7 @@ NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
         o.c[1] = x[0] * r + x[1] * (-r);
       } break;
       case NDS_CV_PROJ2DTO1D:                              // two.py:67-69
-        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1]);
+        norm_pair<R>(x[0] * x[0] + x[1] * x[1], o.q[0], o.iq[0]);
         o.c[0] = o.q[0];
         break;
       default: break;
@@ -85,19 +98,19 @@ NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
       case NDS_CV_PROJ5DTO1DX0: o.c[0] = x[0]; break;      // five.py:9-11
       case NDS_CV_PROJ5DTO1DX2: o.c[0] = x[2]; break;      // five.py:22-24
       case NDS_CV_PROJ5DTO1D:                              // five.py:34-38
-        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]));
+        norm_pair<R>(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]), o.q[0], o.iq[0]);
         o.c[0] = o.q[0];
         break;
       case NDS_CV_PROJ5DTO2D:                              // five.py:50-57
-        o.q[0] = nds_sqrt(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]));
-        o.q[1] = nds_sqrt(x[2] * x[2] + x[3] * x[3]);
+        norm_pair<R>(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]), o.q[0], o.iq[0]);
+        norm_pair<R>(x[2] * x[2] + x[3] * x[3], o.q[1], o.iq[1]);
         o.c[0] = o.q[0];
         o.c[1] = o.q[1];
         break;
       case NDS_CV_PROJ5DTO2DV2: {                          // five.py:77-81
         const R d = x[1] - x[4];
-        o.q[0] = nds_sqrt(x[0] * x[0] + d * d);
-        o.q[1] = nds_sqrt(x[2] * x[2] + x[3] * x[3]);
+        norm_pair<R>(x[0] * x[0] + d * d, o.q[0], o.iq[0]);
+        norm_pair<R>(x[2] * x[2] + x[3] * x[3], o.q[1], o.iq[1]);
         o.c[0] = o.q[0];
         o.c[1] = o.q[1];
       } break;
@@ -130,8 +143,8 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
       } break;
       case NDS_CV_PROJ2DTO1D:                                          // two.py:71-73
         if constexpr (is_f32<R>::value) {
-          const R inv = nds_rcp(o.q[0]);
-          f[0] = g[0] * (x[0] * inv); f[1] = g[0] * (x[1] * inv);
+          const R i0 = g[0] * o.iq[0];
+          f[0] = x[0] * i0; f[1] = x[1] * i0;
         } else {
           f[0] = g[0] * (x[0] / o.q[0]); f[1] = g[0] * (x[1] / o.q[0]);
         }
@@ -144,13 +157,18 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
       case NDS_CV_PROJ5DTO1DX0: f[0] = g[0]; break;                    // five.py:7
       case NDS_CV_PROJ5DTO1DX2: f[2] = g[0]; break;                    // five.py:20
       case NDS_CV_PROJ5DTO1D:                                          // five.py:40-44 (2e-7)
-        f[0] = g[0] * (x[0] / o.q[0]);
-        f[1] = g[0] * (x[1] / o.q[0]);
-        f[4] = g[0] * ((R)2.0 * (R)1.0e-7 * x[4] / o.q[0]);
+        if constexpr (is_f32<R>::value) {
+          const R i0 = o.iq[0] * g[0];
+          f[0] = x[0] * i0; f[1] = x[1] * i0; f[4] = (R)2.0e-7 * x[4] * i0;
+        } else {
+          f[0] = g[0] * (x[0] / o.q[0]);
+          f[1] = g[0] * (x[1] / o.q[0]);
+          f[4] = g[0] * ((R)2.0 * (R)1.0e-7 * x[4] / o.q[0]);
+        }
         break;
       case NDS_CV_PROJ5DTO2D:                                          // five.py:59-71
         if constexpr (is_f32<R>::value) {
-          const R i0 = nds_rcp(o.q[0]) * g[0], i1 = nds_rcp(o.q[1]) * g[1];
+          const R i0 = o.iq[0] * g[0], i1 = o.iq[1] * g[1];
           f[0] = x[0] * i0; f[1] = x[1] * i0; f[4] = (R)1.0e-7 * x[4] * i0;
           f[2] = x[2] * i1; f[3] = x[3] * i1;
         } else {
@@ -163,11 +181,17 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
         break;
       case NDS_CV_PROJ5DTO2DV2: {                                      // five.py:83-98
         const R d = x[1] - x[4];
-        f[0] = g[0] * (x[0] / o.q[0]);
-        f[1] = g[0] * (d / o.q[0]);
-        f[4] = g[0] * (-d / o.q[0]);
-        f[2] = g[1] * (x[2] / o.q[1]);
-        f[3] = g[1] * (x[3] / o.q[1]);
+        if constexpr (is_f32<R>::value) {
+          const R i0 = o.iq[0] * g[0], i1 = o.iq[1] * g[1];
+          f[0] = x[0] * i0; f[1] = d * i0; f[4] = -(d * i0);
+          f[2] = x[2] * i1; f[3] = x[3] * i1;
+        } else {
+          f[0] = g[0] * (x[0] / o.q[0]);
+          f[1] = g[0] * (d / o.q[0]);
+          f[4] = g[0] * (-d / o.q[0]);
+          f[2] = g[1] * (x[2] / o.q[1]);
+          f[3] = g[1] * (x[3] / o.q[1]);
+        }
       } break;
       default: break;
     }
@@ -376,7 +400,9 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
 #pragma unroll
   for (int d = 0; d < ND; d++) fb[d] = (R)0;
   if (bias_mask & BIAS_UMB) {  // bias/umb.py:23-40
-    for (int u = 0; u < K.n_umb; u++) {
+#pragma unroll
+    for (int u = 0; u < NDS_MAX_UMB; u++) {
+      if (u >= K.n_umb) break;
       R g[ND], e = (R)0;
 #pragma unroll
       for (int k = 0; k < ND; k++) {
