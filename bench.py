@@ -25,7 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c4": 289.0}  # SURVEY.md section 8d (algorithmic, fixed)
+FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c3": 128.0, "c4": 289.0}  # SURVEY.md section 8d (algorithmic, fixed)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -34,6 +34,11 @@ def workload_cfg(name, n_walkers, precision):
         return dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
                     integrate="langevin", gamma=0.1, temperature=300, dt=1.0, seed=0, dump=False,
                     n_walkers=n_walkers, precision=precision, steps_per_launch=1000)
+    if name == "c3":  # examples/2d-committor.yaml: shooting from one seed point, 2^20 shots per GPU
+        return dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[21.0, 17.0], method="committor",
+                    n_basins=2, criteria=[[[20, 25], [30, 35]], [[38, 50], [2, 10]]], gamma=0.1,
+                    temperature=300, dt=1.0, seed=0, dump=False, n_walkers=n_walkers, precision=precision,
+                    steps_per_launch=1000, steps=10000)
     if name == "c4":  # examples/5d-umb.yaml, windows x walkers as one batch
         return dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
                     true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0], biases=["umb"],
@@ -188,10 +193,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: per workload)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="C5 hill exchange: peer-memory stores fused into the deposit kernel, or NCCL allgather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -217,7 +224,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     name = args.workload
-    M = args.walkers or {"c2": 1 << 20, "c4": 1 << 17, "c5": 8192}[name]
+    if name == "c3":
+        args.steps = 10 - args.warmup  # the whole job is 10 blocks of 1000 steps (steps: 10000)
+    M = args.walkers or {"c2": 1 << 20, "c3": 1 << 20, "c4": 1 << 17, "c5": 8192}[name]
     cfg = workload_cfg(name, M, args.precision)
     cfg.update(device=local_rank, walker_offset=rank * M, n_walkers_global=world * M)
     md_steps = cfg["steps_per_launch"]
@@ -226,8 +235,11 @@ def main():
     spec = config.parse(cfg)
     eng = Engine(spec.to_struct())
     if name == "c5" and world > 1:
-        from ndsimulator_b200.distributed import attach_hill_exchange
-        attach_hill_exchange(eng)
+        from ndsimulator_b200.distributed import attach_hill_exchange, attach_peer_hill_exchange
+        if args.exchange == "p2p":
+            attach_peer_hill_exchange(eng)
+        else:
+            attach_hill_exchange(eng)
     x0, extra = initial_state(name, spec, M, rank * M)
     eng.set_state(x0)
     if extra:
@@ -270,6 +282,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms = float(t[0]), float(t[1])
     value = world * M * md_steps * args.steps / (dev_ms * 1e-3)
+    c3_info = None
+    if name == "c3":
+        # count the steps that were actually integrated in the timed blocks (stopped walkers do nothing)
+        basin, exit_step = eng.get_commit()
+        lo = args.warmup * md_steps
+        done = np.clip(exit_step, lo, None) - lo
+        tot = torch.tensor([float(done.sum()), float((basin >= 0).sum()), float((basin == 1).sum())],
+                           dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        value = float(tot[0]) / (dev_ms * 1e-3)
+        c3_info = {"shots": world * M, "committed": int(tot[1]), "to_basin_1": int(tot[2]),
+                   "p_basin1_given_committed": float(tot[2] / max(tot[1], 1)),
+                   "lane_utilisation": float(tot[0]) / (world * M * md_steps * args.steps)}
+        args.no_e2e = True
 
     # ---- end to end through the public API with host buffers (pinned), every step
     e2e = None
@@ -329,10 +356,14 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": {"c2": "C2: 2-D Mueller-Brown Langevin gamma=0.1, 2^20 walkers/GPU",
+                                    "c3": "C3: 2d-committor.yaml shooting, 2^20 shots/GPU, <= 10^4 steps each "
+                                          "(a step = the first 1000-step blocks; stopped walkers idle their lane)",
                                     "c4": "C4: 5-D umbrella windows (5d-umb.yaml), 256 windows, 2nd-order Langevin",
                                     "c5": "C5: 5-D multiple-walker metadynamics, shared hill table"}[name],
                        "walkers_per_gpu": M, "md_steps_per_step": md_steps,
-                       "kernel": eng.kernel_name, "l2": "flushed between steps (256 MiB memset)",
+                       "kernel": eng.kernel_name,
+                       **({"hill_exchange": args.exchange if world > 1 else "none"} if name == "c5" else {}),
+                       "l2": "flushed between steps (256 MiB memset)",
                        "timing": "CUDA events on the engine stream per step, summed; max over ranks",
                        "wall_ms_total": wall_ms},
             "gpu_launches": launches,
@@ -355,6 +386,8 @@ def main():
                 "unit": "T hill-evals/s", "frac": he / (mufu_peak * world), "traffic": None,
                 "note": "one MUFU.EX2 per walker-hill pair; peak = SMs x 16 lanes x clocks.max.sm"}
             out["hill_evals_per_s"] = he
+        if c3_info:
+            out["committor"] = c3_info
         if e2e:
             out["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

@@ -219,6 +219,16 @@ typedef int (*nds_exchange_fn)(void* user, void* dev_segment, int64_t bytes_per_
                                int64_t rank_offset_bytes);
 NDS_API int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
 
+/* peer-memory variant of the exchange (NVLink / NVSwitch): after nds_open_peer_tables() the deposition
+ * kernel stores every new hill record directly into the table of EVERY rank (its own included), so no
+ * allgather runs; the exchange callback is then invoked with bytes_per_rank == 0 and only has to act as
+ * a barrier between the ranks.  handle: 64 bytes (cudaIpcMemHandle_t) of this engine's hill table;
+ * handles: [nranks][64] gathered from all ranks of the node, indexed by rank.
+ * nds_set_peer_tables() takes raw device pointers instead (engines living in one process).       */
+NDS_API int nds_hills_ipc_handle(nds_engine* e, void* handle);
+NDS_API int nds_open_peer_tables(nds_engine* e, const void* handles, int nranks, int rank);
+NDS_API int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, int rank);
+
 /* committor outcome (engines/committor.py:103-111; ndrun.py:261-264): basin[M] (-1 = none),
  * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */
 NDS_API int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);

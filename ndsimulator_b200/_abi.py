@@ -105,6 +105,9 @@ _PROTOTYPES = {
     "nds_set_hills": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]),
     "nds_get_vr": (C.c_int, [C.c_void_p, _dp]),
     "nds_set_exchange": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
+    "nds_hills_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nds_open_peer_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nds_set_peer_tables": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
     "nds_frame_width": (C.c_int, [C.c_void_p]),

@@ -44,6 +44,8 @@ struct nds_engine {
   virtual int histogram(double x0, double dx, int64_t nx, double y0, double dy, int64_t ny,
                         int64_t* counts) = 0;
   virtual int device_pointers(void** x, void** v, void** hills, int64_t* stride) = 0;
+  virtual int hills_ipc_handle(void* handle) = 0;
+  virtual int set_peer_tables(void* const* tables, int nranks, int rank, bool opened_by_ipc) = 0;
   virtual double last_run_ms() = 0;
 
   nds_config cfg;
@@ -357,6 +359,10 @@ struct Engine : nds_engine {
   int64_t stage_elems = 0;
   unsigned long long* d_counter = nullptr;
   bool have_v = false, begun = false, need_refresh_vr = true;
+  // peer-memory exchange: device array of every rank's hill table (own included)
+  R** d_peer_tables = nullptr;
+  std::vector<void*> ipc_opened;
+  int n_peers = 0;
   int64_t dep_count = 0, rescale_count = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -368,6 +374,8 @@ struct Engine : nds_engine {
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
                     (void*)d_counter})
       if (p) cudaFree(p);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (d_peer_tables) cudaFree(d_peer_tables);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -567,6 +575,22 @@ struct Engine : nds_engine {
     if (n_hills + add > cfg.mtd_capacity)
       return fail(this, "hill table full: %lld + %lld > mtd_capacity %lld", (long long)n_hills,
                   (long long)add, (long long)cfg.mtd_capacity);
+    if (cfg.mtd_shared && d_peer_tables && cfg.n_walkers_global > M) {
+      // fused deposition + exchange: records go straight into every rank's table over NVLink
+      deposit_p2p_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
+          K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_peer_tables, n_peers, n_hills,
+          dep_count == 0 ? 1 : 0);
+      CU(cudaGetLastError());
+      launches++;
+      CU(cudaStreamSynchronize(stream));
+      if (!exchange) return fail(this, "peer tables need a barrier callback (nds_set_exchange)");
+      const int rc = exchange(exchange_user, nullptr, 0, 0);  // bytes == 0: barrier only
+      if (rc) return fail(this, "barrier callback failed (%d)", rc);
+      n_hills += add;
+      dep_count += 1;
+      need_refresh_vr = true;
+      return 0;
+    }
     deposit_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
         K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, dep_count == 0 ? 1 : 0);
     CU(cudaGetLastError());
@@ -852,6 +876,31 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  int hills_ipc_handle(void* handle) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_hills) return fail(this, "nds_hills_ipc_handle: metadynamics is not enabled");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_hills));
+    memcpy(handle, &h, sizeof h);
+    return 0;
+  }
+
+  int set_peer_tables(void* const* tables, int nranks, int rank, bool opened_by_ipc) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_hills || !cfg.mtd_shared) return fail(this, "peer tables need a shared hill table");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(this, "bad rank / nranks");
+    std::vector<R*> t((size_t)nranks);
+    for (int r = 0; r < nranks; r++) t[(size_t)r] = (r == rank) ? d_hills : (R*)tables[r];
+    if (d_peer_tables) CU(cudaFree(d_peer_tables));
+    CU(cudaMalloc(&d_peer_tables, sizeof(R*) * (size_t)nranks));
+    CU(cudaMemcpy(d_peer_tables, t.data(), sizeof(R*) * (size_t)nranks, cudaMemcpyHostToDevice));
+    n_peers = nranks;
+    if (opened_by_ipc)
+      for (int r = 0; r < nranks; r++)
+        if (r != rank) ipc_opened.push_back(tables[r]);
+    return 0;
+  }
+
   int device_pointers(void** x, void** v, void** hills, int64_t* stride) override {
     if (x) *x = d_x;
     if (v) *v = d_v;
@@ -952,6 +1001,22 @@ int nds_colvar_histogram(nds_engine* e, double x0, double dx, int64_t nx, double
 }
 int nds_device_pointers(nds_engine* e, void** x, void** v, void** hills, int64_t* stride) {
   return e->device_pointers(x, v, hills, stride);
+}
+int nds_hills_ipc_handle(nds_engine* e, void* handle) { return e->hills_ipc_handle(handle); }
+int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, int rank) {
+  return e->set_peer_tables(tables, nranks, rank, false);
+}
+int nds_open_peer_tables(nds_engine* e, const void* handles, int nranks, int rank) {
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) return fail(e, "nds_open_peer_tables: cudaSetDevice failed");
+  std::vector<void*> ptrs((size_t)nranks, nullptr);
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+    cudaError_t err = cudaIpcOpenMemHandle(&ptrs[(size_t)r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) return fail(e, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(err));
+  }
+  return e->set_peer_tables(ptrs.data(), nranks, rank, true);
 }
 void* nds_stream(nds_engine* e) { return (void*)e->stream; }
 int64_t nds_n_hills(const nds_engine* e, int64_t) { return e->n_hills; }

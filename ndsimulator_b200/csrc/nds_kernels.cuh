@@ -389,6 +389,42 @@ __global__ void deposit_kernel(const __grid_constant__ Consts<R> K, long long M,
   }
 }
 
+// Fused deposition + exchange over peer memory (shared table, multi-GPU): the record of every local
+// walker is stored straight into the hill table of EVERY rank through NVLink-mapped peer pointers
+// (tables[r], r = 0..nranks-1, own table included), at the same slot n_hills + global walker id.  One
+// 16-byte (fp32) / 32-byte (fp64) vector store per rank per walker; no allgather, no staging buffer.
+template <typename R>
+__global__ void deposit_p2p_kernel(const __grid_constant__ Consts<R> K, long long M, long long walker_offset,
+                                   const R* __restrict__ colv, const R* __restrict__ vr,
+                                   const unsigned char* alive, R* const* __restrict__ tables, int nranks,
+                                   long long n_hills, int first) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= M) return;
+  const bool live = alive ? alive[w] != 0 : true;
+  R h = first ? K.mtd_w : K.mtd_w * nds_exp(-vr[w] / K.mtd_kBdT);
+  if (!live) h = (R)0;
+  const int cd = K.cd, rs = K.hill_stride;
+  R rec[8];
+  for (int k = 0; k < cd; k++) rec[k] = colv[k * M + w];
+  rec[cd] = h;
+  for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
+  const long long slot = (n_hills + walker_offset + w) * rs;
+  for (int r = 0; r < nranks; r++) {
+    R* dst = tables[r] + slot;
+    if (rs == 4) {
+      if constexpr (sizeof(R) == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(rec[0], rec[1], rec[2], rec[3]);
+      } else {
+        reinterpret_cast<double2*>(dst)[0] = make_double2(rec[0], rec[1]);
+        reinterpret_cast<double2*>(dst)[1] = make_double2(rec[2], rec[3]);
+      }
+    } else {
+      for (int k = 0; k < rs; k++) dst[k] = rec[k];
+    }
+  }
+  __threadfence_system();  // records are visible to the peers before this kernel is reported complete
+}
+
 // ------------------------------------------------------------------------- FES grid, histogram
 // Gaussian.projection (bias/gaus.py:365-393, 413-425): sum of hills on a regular grid.
 template <typename R>

@@ -61,8 +61,8 @@ template <> struct HillRec<double> { double4 v; NDS_DEV double h0() const { retu
 //   c0[w], c1[w]: colvars of walker w (identical in every lane).
 //   out: lane w receives (Vm, g0, g1) of walker w in CANONICAL units (gaus.py:252-258, before .dot(J)).
 template <typename R, int W, int NW, int HS, bool ENERGY>
-NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long long n_tiles,
-                           unsigned char* smem, uint64_t* full, R* red, uint32_t& tile_counter,
+NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long long n_hills,
+                           long long n_tiles, unsigned char* smem, uint64_t* full, R* red, uint32_t& tile_counter,
                            const R (&c0)[W], const R (&c1)[W], R& Vm, R& g0, R& g1) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -94,8 +94,12 @@ NDS_DEV void mtd_hill_pass(const Consts<R>& K, const R* __restrict__ hills, long
     const uint32_t b = seq % MTD_NBUF;
     mbar_wait(&full[b], (seq / MTD_NBUF) & 1u);
     const HillRec<R>* tile = reinterpret_cast<const HillRec<R>*>(smem + (size_t)b * TILE_BYTES);
+    // records at or beyond n_hills are never read: with the peer-memory exchange another rank may
+    // already be storing the NEXT stride's records there while this launch is still running
+    const long long left = n_hills - t * MTD_TILE;
+    const int valid = left < MTD_TILE ? (int)left : MTD_TILE;
 #pragma unroll 2
-    for (int j = half * 32 + lane; j < MTD_TILE; j += 32 * HS) {
+    for (int j = half * 32 + lane; j < valid; j += 32 * HS) {
       const HillRec<R> h = tile[j];
       if constexpr (is_f32<R>::value) {
         // Blackwell packed FP32 (FFMA2 / FADD2, sm_100 fma.rn.f32x2): two walkers per instruction,
@@ -256,8 +260,8 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
     R Vm, g[ND];
 #pragma unroll
     for (int d = 0; d < ND; d++) g[d] = (R)0;
-    if (energy) mtd_hill_pass<R, W, NW, HS, true>(K, A.hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
-    else mtd_hill_pass<R, W, NW, HS, false>(K, A.hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
+    if (energy) mtd_hill_pass<R, W, NW, HS, true>(K, A.hills, A.n_hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
+    else mtd_hill_pass<R, W, NW, HS, false>(K, A.hills, A.n_hills, n_tiles, smem, full, red, tile_counter, c0, c1, Vm, g[0], g[1]);
     if (energy || (other_bias & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
     else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
     R vm_other;

@@ -60,6 +60,28 @@ def attach_hill_exchange(engine, group=None):
     return engine
 
 
+def attach_peer_hill_exchange(engine, group=None):
+    """NVLink peer-memory exchange: every rank maps every other rank's hill table (CUDA IPC) and the
+    deposition kernel stores new records straight into all of them; the only host-side step left per
+    deposition stride is a barrier (a 1-element NCCL all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.hills_ipc_handle(), group=group)
+    engine.open_peer_tables(handles, rank)
+    token = torch.zeros(1, device="cuda")
+
+    def barrier(ptr, bytes_per_rank, rank_offset_bytes):
+        assert bytes_per_rank == 0
+        dist.all_reduce(token, group=group)
+        torch.cuda.current_stream().synchronize()
+        return 0
+
+    engine.set_exchange(barrier)
+    return engine
+
+
 def gather_commit_counts(basin: np.ndarray, n_basins: int, group=None):
     """Sum of per-basin commit counts over ranks (the only reduction C3 needs)."""
     import torch

@@ -141,6 +141,22 @@ class Engine:
         self._exchange_cb = _abi.EXCHANGE_FN(tramp)
         self._check(self.lib.nds_set_exchange(self.h, self._exchange_cb, None))
 
+    def hills_ipc_handle(self) -> bytes:
+        """cudaIpcMemHandle_t (64 bytes) of this engine's hill table."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.nds_hills_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def open_peer_tables(self, handles, rank):
+        """handles: list of 64-byte IPC handles of every rank's table (same node), indexed by rank."""
+        blob = b"".join(handles)
+        self._check(self.lib.nds_open_peer_tables(self.h, blob, len(handles), int(rank)))
+
+    def set_peer_tables(self, pointers, rank):
+        """raw device pointers of every rank's table (engines living in this process)."""
+        arr = (C.c_void_p * len(pointers))(*pointers)
+        self._check(self.lib.nds_set_peer_tables(self.h, arr, len(pointers), int(rank)))
+
     def fes_grid(self, x0, dx, nx, y0=0.0, dy=1.0, ny=1, walker=0):
         g = np.empty((ny, nx))
         self._check(self.lib.nds_fes_grid(self.h, walker, x0, dx, nx, y0, dy, ny, _p(g)))

@@ -547,3 +547,65 @@ def test_packed_fp32_kernel_matches_scalar_fp32(monkeypatch):
     assert scaled_err(outs["packed"]["x"], outs["scalar"]["x"]) < 1e-6
     assert scaled_err(outs["packed"]["v"], outs["scalar"]["v"]) < 1e-4
     assert scaled_err(outs["packed"]["pe"], outs["scalar"]["pe"]) < 1e-4
+
+
+def test_peer_memory_deposit_emulated_on_one_gpu():
+    """Fused deposition + exchange over peer pointers: two engines in one process write their new hill
+    records directly into both tables (nds_set_peer_tables); the callback is only a barrier.  Must equal
+    one engine with 2M walkers bit for bit."""
+    import threading
+
+    M, nsteps = 24, 200
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=20,
+               mtd_biasf=10.0, steps=nsteps, mtd_shared=True, seed=5, precision="f32")
+    rng = np.random.RandomState(8)
+    x0 = 12.0 + rng.normal(scale=0.5, size=(5, 2 * M))
+    one = Engine(spec_from(cfg, n_walkers=2 * M).to_struct())
+    one.set_state(x0)
+    one.begin()
+    one.run(nsteps)
+    ref, ref_hills = one.get_state(), one.get_hills()
+
+    engines = [Engine(spec_from(cfg, n_walkers=M, walker_offset=r * M, n_walkers_global=2 * M).to_struct())
+               for r in range(2)]
+    ptrs = [e.device_pointers()["hills"] for e in engines]
+    barrier = threading.Barrier(2)
+    calls = [0, 0]
+
+    def make_cb(r):
+        def cb(ptr, nbytes, off):
+            assert nbytes == 0 and ptr is None
+            calls[r] += 1
+            barrier.wait()
+            return 0
+        return cb
+
+    errors = []
+
+    def drive(r):
+        try:
+            e = engines[r]
+            e.set_peer_tables(ptrs, r)
+            e.set_exchange(make_cb(r))
+            e.set_state(x0[:, r * M:(r + 1) * M])
+            e.begin()
+            e.run(nsteps)
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+            barrier.abort()
+
+    threads = [threading.Thread(target=drive, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert calls == [10, 10]
+    for r in range(2):
+        st = engines[r].get_state()
+        for k in ("x", "v", "biase"):
+            assert np.array_equal(st[k], ref[k][..., r * M:(r + 1) * M]), (r, k)
+        c, h = engines[r].get_hills()
+        assert np.array_equal(c, ref_hills[0]) and np.array_equal(h, ref_hills[1])
