@@ -108,6 +108,12 @@ def measured_peaks():
 def initial_state(name, spec, M, rank_offset):
     x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
     extra = {}
+    if name == "c5":
+        # SURVEY 8d names x0 = (12,...,12) for every walker; 8192 identical starts would stack 8192 hills
+        # (410 eV) on one point at step 0, so the walkers are spread over the Mueller valley instead
+        rng = np.random.RandomState(1234 + rank_offset)
+        x0 = np.stack([rng.uniform(8, 30, M), rng.uniform(-3, 3, M), rng.uniform(8, 30, M),
+                       rng.uniform(-3, 3, M), np.full(M, 12.0)])
     if name == "c4":
         # 16 x 16 windows: r0 on xi1 in {10..40} x xi2 in {6..36}
         gid = rank_offset + np.arange(M)

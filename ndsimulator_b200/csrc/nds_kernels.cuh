@@ -167,7 +167,10 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   bool alive = true;
   int basin = -1;
 
-  while (s < s_end && alive) {
+  long long exit_s = 0;
+  while (s < s_end) {
+    // the step counter stays warp-uniform: a stopped walker idles its lane until the whole warp is done
+    if (PACK == 1 && committor && !__any_sync(0xffffffffu, alive)) break;
     const long long grp = s / G;
     const int first = (int)(s - grp * G);
     R zb[G * NN > 0 ? G * NN : 1];
@@ -183,7 +186,8 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     }
 #pragma unroll
     for (int i = 0; i < G; i++) {
-      if (i >= first && s < s_end && alive) {
+      if (i >= first && s < s_end) {
+       if (alive) {
         R xi[ND], eta[ND];
         if (NN > 0) {
           if (PACK == 1 && ext_noise) {  // md.py:120,127-128 with numbers supplied by the caller (parity tests)
@@ -272,18 +276,21 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
             for (int d = 0; d < ND; d++) v[d] *= scale;
           }
         }
+       }  // alive
         s += 1;            // ndrun.py:232
         time += K.dt64;    // ndrun.py:240
         if constexpr (PACK == 1) {
-          if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
+          if (committor && alive && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
             basin = commit_test<R, ND>(K, cd, e.cv.c);
-            if (basin >= 0) alive = false;
+            if (basin >= 0) { alive = false; exit_s = s; }
           }
+          if (alive || exit_s == s) {
           if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
             // io/dump.py:76-102: full observables of this walker at NDRun.step == s
             Eval<R, ND> o;
             eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
             write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
+          }
           }
           if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
         }
@@ -314,7 +321,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   A.thermo[4 * M + w] = A.begin_mode ? ke + o.pe : o.pe + ke + o.be;  // ndrun.py:196 / md.py:229
   if constexpr (PACK == 1) {
     if (committor) {
-      if (!alive) { A.alive[w] = 0; A.exit_step[w] = s; }
+      if (!alive) { A.alive[w] = 0; A.exit_step[w] = exit_s; }
       A.basin[w] = basin;
     }
     // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)

@@ -446,12 +446,20 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
 template <typename R, int ND>
 NDS_DEV int commit_test(const Consts<R>& K, int cd, const R (&c)[ND]) {
   int ib = -1;
-  for (int b = 0; b < K.n_basins; b++) {
+  auto in_box = [&](int b) {
     bool in = true;
 #pragma unroll
     for (int k = 0; k < ND; k++)
       if (k < cd && (c[k] < K.crit[b][k][0] || c[k] > K.crit[b][k][1])) in = false;
-    if (in) ib = b;
+    return in;
+  };
+  // the usual case (two basins) is straight-line code on fixed constant-bank slots
+  if (in_box(0)) ib = 0;
+  if (K.n_basins > 1 && in_box(1)) ib = 1;
+  if (K.n_basins > 2) {  // rare: skipped by one uniform branch
+#pragma unroll
+    for (int b = 2; b < NDS_MAX_BASINS; b++)
+      if (b < K.n_basins && in_box(b)) ib = b;
   }
   return ib;
 }

@@ -1,0 +1,190 @@
+"""GPU: the BASELINE.json configurations at FULL size, checked through size-independent properties
+(the oracle cannot run 2^20 walkers x 10^5 steps): time reversibility and energy conservation of the
+Verlet path, invariance under sharding and launch splitting, ensemble statistics against a small oracle
+ensemble, conservation of counts, and identities of the hill table."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from ndsimulator_b200.engine import Engine
+from oracle import oracle
+from tests.helpers import load_golden, spec_from, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+M20 = 1 << 20
+C2 = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md", integrate="langevin",
+          gamma=0.1, temperature=300, dt=1.0, seed=0)
+kB = 8.6173303e-5
+
+
+def test_c2_full_size_statistics_fp32():
+    """2^20 walkers, packed fp32 kernel, 2000 steps: marginals / energy against a 4096-walker oracle
+    ensemble (KS, p > 1e-3), <T> within 4 standard errors, every walker finite, histogram conserves M."""
+    spec = spec_from(C2, n_walkers=M20, precision="f32")
+    eng = Engine(spec.to_struct())
+    assert "f32x2" in eng.kernel_name
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M20, axis=1)
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(2000)
+    a = eng.get_state()
+    assert np.isfinite(a["x"]).all() and np.isfinite(a["v"]).all()
+    Mo = 4096
+    so = spec_from(C2, n_walkers=Mo).to_struct()
+    orc = oracle.OracleSim(so, seeds=np.arange(5000, 5000 + Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(x0[:, :Mo])
+    orc.begin()
+    orc.run(2000)
+    b = orc.get_state()
+    for name, u, v in (("x", a["x"][0], b["x"][0]), ("y", a["x"][1], b["x"][1]), ("pe", a["pe"], b["pe"])):
+        p = stats.ks_2samp(u, v).pvalue
+        assert p > 1e-3, (name, p)
+    se = np.sqrt(a["T"].var() / M20 + b["T"].var() / Mo)
+    assert abs(a["T"].mean() - b["T"].mean()) < 4 * se
+    h = eng.colvar_histogram(-25.0, 1.0, 100, -30.0, 1.0, 100)
+    assert h.sum() == M20
+
+
+def test_verlet_time_reversal_full_size():
+    """NVE at 2^20 walkers, fp64: n steps forward, velocities negated, n steps forward returns to the start."""
+    spec = spec_from(dict(C2, integrate="nve"), n_walkers=M20, precision="f64")
+    eng = Engine(spec.to_struct())
+    rng = np.random.RandomState(0)
+    x0 = np.stack([rng.uniform(18, 28, M20), rng.uniform(18, 34, M20)])
+    v0 = rng.normal(scale=0.0157, size=(2, M20))
+    eng.set_state(x0, v0)
+    eng.begin()
+    e0 = eng.get_state()["totale"].copy()
+    eng.run(300)
+    mid = eng.get_state()
+    assert np.max(np.abs(mid["totale"] - e0)) < 5e-3          # bounded energy error of velocity Verlet
+    eng.set_state(mid["x"], -mid["v"])
+    eng.run(300)
+    end = eng.get_state()
+    assert scaled_err(end["x"], x0) < 1e-9
+    assert scaled_err(-end["v"], v0) < 1e-7
+
+
+def test_sharding_and_launch_split_invariance_full_size():
+    """Two half-size engines with walker offsets, and a different steps_per_launch, reproduce the 2^20-walker
+    engine bit for bit (Philox streams are indexed by global walker id and global step)."""
+    x0 = np.repeat(np.array([[22.0], [24.0]]), M20, axis=1)
+    full = Engine(spec_from(C2, n_walkers=M20, precision="f32").to_struct())
+    full.set_state(x0)
+    full.begin()
+    full.run(200)
+    ref = full.get_state(fields=("x", "v"))
+    half = M20 // 2
+    for r in range(2):
+        part = Engine(spec_from(C2, n_walkers=half, walker_offset=r * half, n_walkers_global=M20,
+                                precision="f32", steps_per_launch=64).to_struct())
+        part.set_state(x0[:, :half])
+        part.begin()
+        part.run(200)
+        st = part.get_state(fields=("x", "v"))
+        assert np.array_equal(st["x"], ref["x"][:, r * half:(r + 1) * half])
+        assert np.array_equal(st["v"], ref["v"][:, r * half:(r + 1) * half])
+
+
+def test_c3_full_size_commit_counts():
+    """2^20 shots of examples/2d-committor.yaml: counts are conserved, exit steps are consistent, and the
+    committed fraction / p(basin 1) agree with a 2048-shot oracle ensemble within 4 sigma (binomial)."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"])
+    spec = spec_from(cfg, n_walkers=M20, precision="f32")
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M20, axis=1))
+    eng.begin()
+    eng.run(cfg["steps"])
+    basin, exit_step = eng.get_commit()
+    assert set(np.unique(basin)) <= {-1, 0, 1}
+    assert (basin == -1).sum() + (basin == 0).sum() + (basin == 1).sum() == M20
+    assert eng.count_alive() == (basin == -1).sum()
+    assert np.all(exit_step[basin < 0] == cfg["steps"]) and np.all(exit_step[basin >= 0] <= cfg["steps"])
+    assert exit_step[basin >= 0].min() >= 1
+    Mo = 2048
+    orc = oracle.OracleSim(spec_from(cfg, n_walkers=Mo).to_struct(), seeds=np.arange(900, 900 + Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(np.repeat(spec.x0.reshape(-1, 1), Mo, axis=1))
+    orc.begin()
+    orc.run(cfg["steps"])
+    bo, _ = orc.get_commit()
+    pc_g, pc_o = (basin >= 0).mean(), (bo >= 0).mean()
+    assert abs(pc_g - pc_o) < 4 * np.sqrt(pc_o * (1 - pc_o) / Mo)
+    p1_g = (basin == 1).sum() / (basin >= 0).sum()
+    p1_o = (bo == 1).sum() / (bo >= 0).sum()
+    assert abs(p1_g - p1_o) < 4 * np.sqrt(p1_o * (1 - p1_o) / (bo >= 0).sum())
+
+
+def test_c4_full_size_windows_stay_in_their_umbrella():
+    """2^17 walkers over 256 umbrella windows (C4): after 2000 steps each window's mean colvar sits near
+    its r0 (k = 0.1 keeps it within a few sigma) and temperatures follow the 2nd-order Langevin quirk A6."""
+    M = 1 << 17
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0], biases=["umb"], umb_k=0.1,
+               umb_r0=[18, 18], umb_per_walker=True, integrate="2nd-langevin", md_gamma=0.01,
+               temperature=300.0, dt=1.0, seed=1)
+    spec = spec_from(cfg, n_walkers=M, precision="f32")
+    eng = Engine(spec.to_struct())
+    win = np.arange(M) % 256
+    r1, r2 = 10.0 + 2.0 * (win % 16), 6.0 + 2.0 * (win // 16)
+    eng.set_state(np.stack([r1, np.zeros(M), r2, np.zeros(M), np.full(M, 100.0)]))
+    eng.set_walker_bias(np.full((2, M), 0.1), np.stack([r1, r2]))
+    eng.begin()
+    eng.run(2000)
+    st = eng.get_state()
+    assert np.isfinite(st["x"]).all()
+    c = st["colv"]
+    for wdw in (0, 17, 100, 255):
+        sel = win == wdw
+        # harmonic restraint k=0.1 at 300 K: sigma = sqrt(kT/k) = 0.51; the Mueller force shifts the mean
+        assert abs(c[0, sel].mean() - r1[sel][0]) < 5.0 and abs(c[1, sel].mean() - r2[sel][0]) < 5.0
+        assert c[0, sel].std() < 1.5
+    assert st["T"].mean() == pytest.approx(300.0, rel=0.05)
+
+
+def test_c5_full_size_hill_table_identities():
+    """8192 walkers sharing one hill table (C5), 3 deposition strides: table size, height bounds, VR
+    definition, and the device FES grid against a host sum of the same hills."""
+    M = 8192
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=100,
+               mtd_biasf=10.0, steps=300, mtd_shared=True, seed=3)
+    spec = spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=100)
+    eng = Engine(spec.to_struct())
+    assert eng.kernel_name.startswith("mtd_block")
+    # walkers spread over the surface (8192 identical starts would stack 8192 hills = 410 eV on one point)
+    rng = np.random.RandomState(0)
+    x0 = np.stack([rng.uniform(8, 30, M), rng.uniform(-3, 3, M), rng.uniform(8, 30, M),
+                   rng.uniform(-3, 3, M), np.full(M, 12.0)])
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(250)
+    c, h = eng.get_hills()
+    assert len(h) == 3 * M                                     # depositions at steps 0, 100, 200
+    assert np.allclose(h[:M], 0.05)                            # first hills: full height
+    assert np.all(h[M:] >= 0) and np.all(h[M:] < 0.05)         # tempered by the bias already present
+    assert (h[M:] > 1e-6).mean() > 0.05  # 8192 walkers x w=0.05 saturate the well-tempered bias at once
+    c_expect = np.stack([np.sqrt(x0[0] ** 2 + x0[1] ** 2 + 1e-7 * x0[4] ** 2), np.sqrt(x0[2] ** 2 + x0[3] ** 2)])
+    assert np.allclose(c[:M], c_expect.T, rtol=1e-6)
+    # well-tempered rule with the stale VR: heights of stride 2 follow VR after stride 1 ... checked through
+    # VR itself: V_bias at each walker's position right after the last deposition (refresh on launch entry)
+    st = eng.get_state()
+    vr = eng.get_vr()
+    assert np.all(vr > 0)
+    # heights of stride 2 are w exp(-VR_1 / kB dT) with VR_1 >= the walker's own first hill (0.05)
+    kBdT = kB * 9 * 300
+    assert h[M:2 * M].max() <= 0.05 * np.exp(-0.05 / kBdT) * (1 + 1e-5)
+    # device FES grid == host sum of the same hills
+    g = eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40)
+    X, Y = np.meshgrid(np.arange(0, 48.0), np.arange(0, 40.0))
+    sub = slice(0, None, 64)
+    host = np.zeros_like(X)
+    for ci, hi in zip(c, h):
+        host += hi * np.exp(-((X - ci[0]) ** 2 + (Y - ci[1]) ** 2) / 8.0)
+    assert scaled_err(g, host) < 1e-5
+    assert np.isfinite(st["x"]).all() and st["biase"].min() > 0
+    assert kBdT > 0 and sub is not None
