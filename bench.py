@@ -39,6 +39,11 @@ def workload_cfg(name, n_walkers, precision):
                     n_basins=2, criteria=[[[20, 25], [30, 35]], [[38, 50], [2, 10]]], gamma=0.1,
                     temperature=300, dt=1.0, seed=0, dump=False, n_walkers=n_walkers, precision=precision,
                     steps_per_launch=1000, steps=10000)
+    if name == "dump":  # C2 physics with EVERY walker dumping a full frame every 10 steps (io/dump.py rows)
+        return dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
+                    integrate="langevin", gamma=0.1, temperature=300, dt=1.0, seed=0, dump=True,
+                    dump_freq=10, stat_freq=10, dump_walkers=n_walkers, dump_capacity=12,
+                    n_walkers=n_walkers, precision=precision, steps_per_launch=100, steps=100)
     if name == "c4":  # examples/5d-umb.yaml, windows x walkers as one batch
         return dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
                     true_colvar_name="Proj5dto2d", x0=[18.0, 0.0, 18.0, 0.0, 100.0], biases=["umb"],
@@ -199,7 +204,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "dump"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: per workload)")
@@ -232,10 +237,12 @@ def main():
     name = args.workload
     if name == "c3":
         args.steps = 10 - args.warmup  # the whole job is 10 blocks of 1000 steps (steps: 10000)
-    M = args.walkers or {"c2": 1 << 20, "c3": 1 << 20, "c4": 1 << 17, "c5": 8192}[name]
+    M = args.walkers or {"c2": 1 << 20, "c3": 1 << 20, "c4": 1 << 17, "c5": 8192, "dump": 1 << 20}[name]
     cfg = workload_cfg(name, M, args.precision)
     cfg.update(device=local_rank, walker_offset=rank * M, n_walkers_global=world * M)
     md_steps = cfg["steps_per_launch"]
+    if name == "dump":
+        args.no_e2e = True
     if name == "c5":
         cfg["steps"] = md_steps * (args.steps + args.warmup + (0 if args.no_e2e else args.steps)) + md_steps
     spec = config.parse(cfg)
@@ -260,8 +267,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def drop_frames():
+        if name == "dump":  # frames stay on the device; the ring is only rewound (no D2H in the timed region)
+            eng.lib.nds_drain_frames(eng.h, None, 0, None)
+
     for _ in range(args.warmup):
         eng.run(md_steps)
+        drop_frames()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -280,6 +292,7 @@ def main():
             hills_evals += M * md_steps * (eng.n_hills() + world * M)  # table after this step's deposit
         eng.run(md_steps, sync=True)
         dev_ms += eng.last_run_ms()
+        drop_frames()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     launches = eng.launch_count - launches0
@@ -365,7 +378,9 @@ def main():
                                     "c3": "C3: 2d-committor.yaml shooting, 2^20 shots/GPU, <= 10^4 steps each "
                                           "(a step = the first 1000-step blocks; stopped walkers idle their lane)",
                                     "c4": "C4: 5-D umbrella windows (5d-umb.yaml), 256 windows, 2nd-order Langevin",
-                                    "c5": "C5: 5-D multiple-walker metadynamics, shared hill table"}[name],
+                                    "c5": "C5: 5-D multiple-walker metadynamics, shared hill table",
+                                    "dump": "C2 physics, every walker records a full frame every 10 steps "
+                                            "(device-side dump rows of io/dump.py)"}[name],
                        "walkers_per_gpu": M, "md_steps_per_step": md_steps,
                        "kernel": eng.kernel_name,
                        **({"hill_exchange": args.exchange if world > 1 else "none"} if name == "c5" else {}),
@@ -375,7 +390,20 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        if name in FLOPS_PER_WALKER_STEP:
+        if name == "dump":
+            width = eng.frame_width
+            frames_per_step = md_steps // 10
+            nbytes = frames_per_step * width * M * 8
+            gbs = nbytes / (dev_ms / args.steps * 1e-3) / 1e9
+            peak = peaks.get("hbm_gbs", 6650.0)
+            out["roofline"] = {
+                "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": None,
+                "note": f"algorithmic dump bytes: {frames_per_step} frames x {width} fp64 fields x {M} walkers per "
+                        f"launch of {md_steps} steps; peak = MEASURED_PEAKS.json hbm_gbs "
+                        f"({'measured' if 'hbm_gbs' in peaks else 'fallback'}); the launch also integrates the steps"}
+            out["dump_gb_per_s"] = gbs
+        elif name in FLOPS_PER_WALKER_STEP:
             ach = per_gpu * FLOPS_PER_WALKER_STEP[name] / 1e12
             out["roofline"] = {
                 "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",

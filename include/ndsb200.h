@@ -237,7 +237,8 @@ NDS_API int64_t nds_count_alive(nds_engine* e);
 /* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
  * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],
  * T, pe, ke, biase, totale, VR, then the lagged thermo sample (A16): time, T, pe, ke, biase, totale.
- * out: [n_frames][nds_frame_width()][dump_walkers].                                             */
+ * out: [n_frames][nds_frame_width()][dump_walkers].  out == NULL discards the pending frames (the
+ * ring is rewound, nothing is copied).                                                          */
 NDS_API int nds_frame_width(const nds_engine* e);
 NDS_API int64_t nds_frames_pending(const nds_engine* e);
 NDS_API int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n_frames);

@@ -824,9 +824,14 @@ struct Engine : nds_engine {
 
   int drain_frames(double* out, int64_t max_frames, int64_t* n_frames) override {
     CU(cudaSetDevice(cfg.device));
+    if (!out) {  // discard: rewind the ring without copying (frames stay on the device)
+      if (n_frames) *n_frames = frames_written;
+      frames_written = 0;
+      return 0;
+    }
     const int64_t n = frames_written < max_frames ? frames_written : max_frames;
     if (n_frames) *n_frames = n;
-    if (n <= 0 || !out) return 0;
+    if (n <= 0) return 0;
     if (n != frames_written) return fail(this, "nds_drain_frames: buffer holds %lld frames, %lld pending", (long long)max_frames, (long long)frames_written);
     const size_t cnt = (size_t)n * frame_width * (size_t)K.dump_walkers;
     CU(cudaMemcpyAsync(out, d_frames, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream));
