@@ -31,6 +31,7 @@ extern "C" {
 #define NDS_MAX_CV 5      /* colvardim <= ndim for every built-in colvar                         */
 #define NDS_MAX_UMB 4     /* harmonic restraints acting on one walker (umb_n, bias/__init__.py:31) */
 #define NDS_MAX_BASINS 8  /* committor basin boxes (engines/committor.py:31-42)                   */
+#define NDS_MAX_PATH_REF 256 /* reference points of a path colvar (colvars/path.py)                */
 
 /* compute precision of the kernels ("precision" key, new) */
 enum { NDS_F32 = 0, NDS_F64 = 1 };
@@ -71,7 +72,10 @@ enum {
   NDS_CV_PROJ5DTO1D = 9,   /* colvars/five.py:31-44 (Jacobian quirk 2e-7) */
   NDS_CV_PROJ5DTO2D = 10,  /* colvars/five.py:47-71 */
   NDS_CV_PROJ5DTO2DV2 = 11,/* colvars/five.py:74-98 */
-  NDS_CV_COUNT = 12
+  NDS_CV_PATH = 12,        /* colvars/path.py:14-102  Branduardi path variable, colvardim 1, any ndim;
+                              reference points set with nds_set_path() */
+  NDS_CV_PATH5DTO2D = 13,  /* colvars/path.py:105-180 path variable in Proj5dto2d space, ndim 5 */
+  NDS_CV_COUNT = 14
 };
 
 /* where the per-step Gaussian numbers come from */
@@ -169,6 +173,12 @@ NDS_API int nds_set_state(nds_engine* e, const double* x, const double* v);
 /* per-walker umbrella windows (new; the reference runs one window per process).
  * k, r0: [colvardim][M].  Requires cfg.umb_per_walker.                                          */
 NDS_API int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0);
+
+/* reference points of a Path / Path5dto2d colvar (colvars/path.py:32-71: `ref`, `ref_ind`, `sigma`,
+ * normally read from `colvar_file_name` with np.loadtxt).  ref: [n_ref][path_dim] row-major,
+ * ref_ind: [n_ref]; path_dim = ndim for Path, 2 for Path5dto2d.  Must be called before nds_begin(). */
+NDS_API int nds_set_path(nds_engine* e, int64_t n_ref, int32_t path_dim, const double* ref,
+                         const double* ref_ind, double sigma);
 
 /* external noise table for parity tests (NDS_NOISE_EXTERNAL): noise[step][j][w], j < normals per
  * step (ndim for langevin: xi; 2*ndim for 2nd-langevin: xi then eta, md.py:120,127-128).

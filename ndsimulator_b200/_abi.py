@@ -49,6 +49,8 @@ COLVARS = {
     "Proj5dto1d": (9, 5, 1),
     "Proj5dto2d": (10, 5, 2),
     "Proj5dto2dv2": (11, 5, 2),
+    "Path": (12, None, 1),
+    "Path5dto2d": (13, 5, 1),
 }
 
 
@@ -93,6 +95,7 @@ _PROTOTYPES = {
     "nds_destroy": (None, [C.c_void_p]),
     "nds_set_state": (C.c_int, [C.c_void_p, _dp, _dp]),
     "nds_set_walker_bias": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "nds_set_path": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _dp, _dp, C.c_double]),
     "nds_set_noise": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int64]),
     "nds_begin": (C.c_int, [C.c_void_p]),
     "nds_run": (C.c_int, [C.c_void_p, C.c_int64]),

@@ -81,6 +81,9 @@ class RunSpec:
     umb_k: List[np.ndarray] = field(default_factory=list)
     umb_r0: List[np.ndarray] = field(default_factory=list)
     umb_per_walker: bool = False
+    path_ref: Optional[np.ndarray] = None     # Path / Path5dto2d colvar (colvars/path.py:32-71)
+    path_ind: Optional[np.ndarray] = None
+    path_sigma: float = 1.0
     mtd_w: float = 0.0
     mtd_sigma: Optional[np.ndarray] = None
     mtd_dep_freq: float = 10
@@ -245,6 +248,23 @@ def parse(config: dict) -> RunSpec:
     spec.true_colvar = _builtin_name(cfg.get("true_colvar_name", "Original"), "colvars",
                                      _abi.COLVARS, "colvar")
     spec.colvardim = colvar_dim(spec.colvar, ndim)
+    if spec.true_colvar in ("Path", "Path5dto2d"):
+        raise NotImplementedError("path variables are supported as colvar_name, not as true_colvar_name")
+    if spec.colvar in ("Path", "Path5dto2d"):  # colvars/path.py:32-60
+        fname = pick(cfg, "file_name", "colvar", None)
+        spec.path_sigma = float(pick(cfg, "sigma", "colvar", 1.0))
+        ref = pick(cfg, "ref", "colvar", None)
+        ind = pick(cfg, "ref_ind", "colvar", None)
+        if fname is not None:
+            data = np.loadtxt(fname)
+            ref, ind = data[:, 1:], data[:, 0]
+        if ref is None or ind is None:
+            raise TypeError("path colvar needs colvar_file_name or colvar_ref + colvar_ref_ind")
+        spec.path_ind = np.asarray(ind, dtype=float).reshape(-1)
+        spec.path_ref = np.asarray(ref, dtype=float).reshape(len(spec.path_ind), -1)
+        want = ndim if spec.colvar == "Path" else 2
+        if spec.path_ref.shape[1] != want:
+            raise ValueError(f"{spec.colvar}: reference points have {spec.path_ref.shape[1]} columns, expected {want}")
     tcd = colvar_dim(spec.true_colvar, ndim)
     if needs_tcv and tcd != 2:
         raise ValueError(f"potential {pot} is evaluated in a 2-D true_colvar space; "

@@ -54,6 +54,9 @@ struct Consts {
   R fa[4], fb[4], fc[4], fA[4];
   R th_D, th_E, th_x1, th_y1, th_ref;
   R rot;            // 1/sqrt(2) as NumPy computes it (colvars/two.py:53)
+  // path colvar (colvars/path.py): reference points [n][path_dim], indices [n] in device memory
+  const R* path_ref; const R* path_ind; int n_path, path_dim;
+  R path_sig2_invh, path_inv_sig2, path_N;
   // DoubleWell(1d): K1, K2, x1[2], x2[2], invsigma2 (double_well.py:9-53)
   R dw_K1, dw_K2, dw_x1[2], dw_x2[2], dw_invsig2;
   // biases

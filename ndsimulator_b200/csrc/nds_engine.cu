@@ -27,6 +27,7 @@ struct nds_engine {
   virtual int set_state(const double* x, const double* v) = 0;
   virtual int set_walker_bias(const double* k, const double* r0) = 0;
   virtual int set_noise(const double* noise, int64_t first, int64_t nsteps) = 0;
+  virtual int set_path(int64_t n_ref, int path_dim, const double* ref, const double* ind, double sigma) = 0;
   virtual int begin() = 0;
   virtual int run(int64_t nsteps) = 0;
   virtual int sync() = 0;
@@ -95,6 +96,8 @@ extern "C" int nds_colvar_dim(int cv, int ndim) {
     case NDS_CV_PROJ5DTO1DX0: case NDS_CV_PROJ5DTO1DX2: case NDS_CV_PROJ5DTO1D:
       return ndim == 5 ? 1 : -1;
     case NDS_CV_PROJ5DTO2D: case NDS_CV_PROJ5DTO2DV2: return ndim == 5 ? 2 : -1;
+    case NDS_CV_PATH: return (ndim == 1 || ndim == 2 || ndim == 5) ? 1 : -1;
+    case NDS_CV_PATH5DTO2D: return ndim == 5 ? 1 : -1;
     default: return -1;
   }
 }
@@ -111,6 +114,8 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "potential %d has ndim=%d, run has ndim=%d", c->potential, kPotNdim[c->potential], c->ndim);
   if (nds_colvar_dim(c->colvar, c->ndim) < 0) return fail(nullptr, "colvar %d is not defined for ndim=%d", c->colvar, c->ndim);
   if (nds_colvar_dim(c->true_colvar, c->ndim) < 0) return fail(nullptr, "true_colvar %d is not defined for ndim=%d", c->true_colvar, c->ndim);
+  if (c->true_colvar == NDS_CV_PATH || c->true_colvar == NDS_CV_PATH5DTO2D)
+    return fail(nullptr, "path colvars are supported as colvar_name, not as true_colvar_name");
   if (kPotNeedsTcv[c->potential] && nds_colvar_dim(c->true_colvar, c->ndim) != 2)
     return fail(nullptr, "potential %d is evaluated in a 2-D true_colvar space", c->potential);
   if (c->integrator < 0 || c->integrator > NDS_INT_RESCALE)  // md.py:59
@@ -353,6 +358,7 @@ struct Engine : nds_engine {
   int* d_basin = nullptr;
   long long* d_exit = nullptr;
   double* d_frames = nullptr;
+  R *d_path_ref = nullptr, *d_path_ind = nullptr;
   double* d_noise = nullptr;
   int64_t noise_first = 0, noise_steps = 0;
   double* d_stage = nullptr;  // fp64 staging for host <-> device conversion
@@ -372,6 +378,7 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
                     (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
+                    (void*)d_path_ref, (void*)d_path_ind,
                     (void*)d_counter})
       if (p) cudaFree(p);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
@@ -540,6 +547,26 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  int set_path(int64_t n_ref, int path_dim, const double* ref, const double* ind, double sigma) override {
+    CU(cudaSetDevice(cfg.device));  // Path.initialize, colvars/path.py:51-71
+    if (cfg.colvar != NDS_CV_PATH && cfg.colvar != NDS_CV_PATH5DTO2D) return fail(this, "nds_set_path: colvar is not a path variable");
+    if (n_ref < 1 || n_ref > NDS_MAX_PATH_REF) return fail(this, "nds_set_path: n_ref must be in [1, %d]", NDS_MAX_PATH_REF);
+    const int want = cfg.colvar == NDS_CV_PATH ? nd : 2;
+    if (path_dim != want) return fail(this, "nds_set_path: path_dim %d, expected %d", path_dim, want);
+    if (!(sigma > 0)) return fail(this, "nds_set_path: sigma must be positive");
+    if (d_path_ref) { CU(cudaFree(d_path_ref)); CU(cudaFree(d_path_ind)); }
+    CU(cudaMalloc(&d_path_ref, sizeof(R) * (size_t)(n_ref * path_dim)));
+    CU(cudaMalloc(&d_path_ind, sizeof(R) * (size_t)n_ref));
+    if (upload(ref, d_path_ref, n_ref * path_dim)) return 1;
+    if (upload(ind, d_path_ind, n_ref)) return 1;
+    K.path_ref = d_path_ref; K.path_ind = d_path_ind; K.n_path = (int)n_ref; K.path_dim = path_dim;
+    K.path_sig2_invh = (R)(1 / (sigma * sigma) / 2.0);
+    K.path_inv_sig2 = (R)(1 / (sigma * sigma));
+    K.path_N = (R)(double)(int)ind[n_ref - 1];
+    begun = false;
+    return 0;
+  }
+
   BlockArgs<R> make_args(int64_t nsteps) {
     BlockArgs<R> A;
     memset(&A, 0, sizeof A);
@@ -557,6 +584,8 @@ struct Engine : nds_engine {
 
   int begin() override {  // NDRun.begin (ndrun.py:182-206) + MD.begin (md.py:101-110)
     CU(cudaSetDevice(cfg.device));
+    if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
+      return fail(this, "path colvar: call nds_set_path() before nds_begin()");
     step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
     BlockArgs<R> A = make_args(0);
     A.refresh_vr = 1;
@@ -710,6 +739,8 @@ struct Engine : nds_engine {
               double* Fb) override {
     CU(cudaSetDevice(cfg.device));
     if (n <= 0) return 0;
+    if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
+      return fail(this, "path colvar: call nds_set_path() before nds_eval_at()");
     const size_t sn = (size_t)n;
     const size_t total = sn * (size_t)(nd + 1 + nd + cd + cd * nd + 1 + nd);
     R* buf = nullptr;
@@ -968,6 +999,9 @@ void nds_destroy(nds_engine* e) { delete e; }
 int nds_set_state(nds_engine* e, const double* x, const double* v) { return e->set_state(x, v); }
 int nds_set_walker_bias(nds_engine* e, const double* k, const double* r0) { return e->set_walker_bias(k, r0); }
 int nds_set_noise(nds_engine* e, const double* n, int64_t first, int64_t ns) { return e->set_noise(n, first, ns); }
+int nds_set_path(nds_engine* e, int64_t n_ref, int32_t path_dim, const double* ref, const double* ind, double sigma) {
+  return e->set_path(n_ref, path_dim, ref, ind, sigma);
+}
 int nds_begin(nds_engine* e) { return e->begin(); }
 int nds_run(nds_engine* e, int64_t n) { return e->run(n); }
 int nds_sync(nds_engine* e) { return e->sync(); }

@@ -48,7 +48,7 @@ template <typename R, int ND, bool ENERGY>
 NDS_DEV void eval_all(const Consts<R>& K, int pot, int cv, int tcv, int cd, int bias_mask,
                       const R (&x)[ND], const WalkerBias<R, ND>& wb, const R* hills, long long n_hills,
                       long long elem_stride, Eval<R, ND>& e) {
-  cv_eval<R, ND>(cv, K.rot, x, e.cv);
+  cv_eval<R, ND>(K, cv, K.rot, x, e.cv);
   // PE bias needs the potential energy even when the caller does not
   if (ENERGY || (bias_mask & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
   else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);

@@ -250,7 +250,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   // full evaluation at x: colvar + potential + other biases on the owner lanes, hill pass by the warp
   Eval<R, ND> e;
   auto evaluate = [&](bool energy) {
-    cv_eval<R, ND>(cv, K.rot, x, e.cv);
+    cv_eval<R, ND>(K, cv, K.rot, x, e.cv);
     R c0[W], c1[W];
 #pragma unroll
     for (int q = 0; q < W; q++) {

@@ -45,7 +45,7 @@ __host__ __device__ constexpr int cv_dim(int cv, int ndim) {
   switch (cv) {
     case NDS_CV_ORIGINAL: return ndim;
     case NDS_CV_ROTATE2D: case NDS_CV_PROJ5DTO2D: case NDS_CV_PROJ5DTO2DV2: return 2;
-    default: return 1;
+    default: return 1;  // including NDS_CV_PATH, NDS_CV_PATH5DTO2D
   }
 }
 
@@ -57,7 +57,57 @@ struct CvOut {
   R c[ND];
   R q[2];   // norms (Proj*) for the Jacobian
   R iq[2];  // their reciprocals (fp32 fast path: one MUFU.RSQ gives both the norm and 1/norm)
+  R jp[ND]; // path colvars: the 1 x ndim Jacobian row (colvars/path.py:90-102,144-180)
 };
+
+// Branduardi path variable s(q) = sum_i ind_i w_i / sum_i w_i / N,  w_i = exp(-|q - r_i|^2 / (2 sigma^2))
+// (shifted by the smallest exponent like path.py:75-77), and ds/dq.  The reference sums
+// w_i w_j ind_i (r_i - r_j) over all pairs (path.py:95-100); the identical
+//   sum_ij = D * sum_i ind_i w_i (r_i - rbar),  rbar = sum_j w_j r_j / D,  D = sum_j w_j
+// needs one more pass instead of n^2 terms and keeps the same (r_i - r_j)-sized differences.
+template <typename R, int PD>
+NDS_DEV void path_eval(const Consts<R>& K, const R (&q)[PD], int pd, R& s, R (&ds)[PD]) {
+  const int n = K.n_path;
+  R dmin = (R)0;
+  for (int i = 0; i < n; i++) {
+    R d2 = (R)0;
+#pragma unroll
+    for (int d = 0; d < PD; d++)
+      if (d < pd) { const R t = q[d] - K.path_ref[i * pd + d]; d2 += t * t * K.path_sig2_invh; }
+    if (i == 0 || d2 < dmin) dmin = d2;
+  }
+  R D = (R)0, B = (R)0, C[PD];
+#pragma unroll
+  for (int d = 0; d < PD; d++) C[d] = (R)0;
+  for (int i = 0; i < n; i++) {
+    R d2 = (R)0;
+#pragma unroll
+    for (int d = 0; d < PD; d++)
+      if (d < pd) { const R t = q[d] - K.path_ref[i * pd + d]; d2 += t * t * K.path_sig2_invh; }
+    const R w = nds_exp(-(d2 - dmin));
+    D += w;
+    B += K.path_ind[i] * w;
+#pragma unroll
+    for (int d = 0; d < PD; d++)
+      if (d < pd) C[d] += w * K.path_ref[i * pd + d];
+  }
+  s = B / D / K.path_N;
+  R acc[PD];
+#pragma unroll
+  for (int d = 0; d < PD; d++) { acc[d] = (R)0; C[d] = C[d] / D; }
+  for (int i = 0; i < n; i++) {
+    R d2 = (R)0;
+#pragma unroll
+    for (int d = 0; d < PD; d++)
+      if (d < pd) { const R t = q[d] - K.path_ref[i * pd + d]; d2 += t * t * K.path_sig2_invh; }
+    const R iw = K.path_ind[i] * nds_exp(-(d2 - dmin));
+#pragma unroll
+    for (int d = 0; d < PD; d++)
+      if (d < pd) acc[d] += iw * (K.path_ref[i * pd + d] - C[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < PD; d++) ds[d] = acc[d] * K.path_inv_sig2 / D / K.path_N;
+}
 
 // norm and reciprocal norm of a squared length
 template <typename R>
@@ -67,11 +117,14 @@ NDS_DEV void norm_pair(R s, R& n, R& inv) {
 }
 
 template <typename R, int ND>
-NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
+NDS_DEV void cv_eval(const Consts<R>& K, int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
   switch (cv) {
     case NDS_CV_ORIGINAL:  // colvars/misc.py:12-13
 #pragma unroll
       for (int d = 0; d < ND; d++) o.c[d] = x[d];
+      break;
+    case NDS_CV_PATH:      // colvars/path.py:73-102 (path_dim == ndim)
+      path_eval<R, ND>(K, x, ND, o.c[0], o.jp);
       break;
     default: break;
   }
@@ -114,6 +167,19 @@ NDS_DEV void cv_eval(int cv, R rot, const R (&x)[ND], CvOut<R, ND>& o) {
         o.c[0] = o.q[0];
         o.c[1] = o.q[1];
       } break;
+      case NDS_CV_PATH5DTO2D: {                            // path.py:121-180: path variable of Proj5dto2d(x)
+        R q[2], dq[2];
+        norm_pair<R>(x[0] * x[0] + x[1] * x[1] + (R)1e-7 * (x[4] * x[4]), o.q[0], o.iq[0]);
+        norm_pair<R>(x[2] * x[2] + x[3] * x[3], o.q[1], o.iq[1]);
+        q[0] = o.q[0]; q[1] = o.q[1];
+        path_eval<R, 2>(K, q, 2, o.c[0], dq);
+        // jab1 (1x2) . jab2 (2x5), path.py:160-169
+        o.jp[0] = dq[0] * (x[0] / o.q[0]);
+        o.jp[1] = dq[0] * (x[1] / o.q[0]);
+        o.jp[2] = dq[1] * (x[2] / o.q[1]);
+        o.jp[3] = dq[1] * (x[3] / o.q[1]);
+        o.jp[4] = dq[0] * ((R)1.0e-7 * x[4] / o.q[0]);
+      } break;
       default: break;
     }
   }
@@ -128,6 +194,11 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
   if (cv == NDS_CV_ORIGINAL) {  // identity Jacobian, misc.py:15-16
 #pragma unroll
     for (int d = 0; d < ND; d++) f[d] = g[d];
+    return;
+  }
+  if (cv == NDS_CV_PATH || cv == NDS_CV_PATH5DTO2D) {  // 1 x ndim Jacobian row stored by cv_eval
+#pragma unroll
+    for (int d = 0; d < ND; d++) f[d] = g[0] * o.jp[d];
     return;
   }
   if constexpr (ND == 2) {
@@ -291,7 +362,7 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
     if (mueller_cv || threehole) {
       // mueller.py:112-142 / three_hole.py:24-57,90-125: evaluate in true_colvar space, chain rule
       CvOut<R, ND> o;
-      cv_eval<R, ND>(tcv, K.rot, x, o);
+      cv_eval<R, ND>(K, tcv, K.rot, x, o);
       R g[ND];
 #pragma unroll
       for (int d = 0; d < ND; d++) g[d] = (R)0;

@@ -63,6 +63,12 @@ class Engine:
         r0 = _f64(r0, (self.cd, self.M))
         self._check(self.lib.nds_set_walker_bias(self.h, _p(k), _p(r0)))
 
+    def set_path(self, ref, ref_ind, sigma=1.0):
+        """Reference points of a Path / Path5dto2d colvar (colvars/path.py:32-71)."""
+        ind = _f64(np.asarray(ref_ind, dtype=float).reshape(-1))
+        ref = _f64(np.asarray(ref, dtype=float).reshape(len(ind), -1))
+        self._check(self.lib.nds_set_path(self.h, len(ind), ref.shape[1], _p(ref), _p(ind), float(sigma)))
+
     def set_noise(self, noise, first_step=0):
         noise = _f64(noise)
         self._check(self.lib.nds_set_noise(self.h, _p(noise), int(first_step), int(noise.shape[0])))

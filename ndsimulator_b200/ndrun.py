@@ -94,6 +94,8 @@ class NDRun:
         self._v0 = None
         self._window = None
         self.engine = Engine(spec.to_struct())
+        if spec.path_ref is not None:
+            self.engine.set_path(spec.path_ref, spec.path_ind, spec.path_sigma)
         self.engine.set_state(self._x0)
         self.atoms = _Atoms(self)
         self.modify = _Modify(self)
@@ -135,6 +137,8 @@ class NDRun:
     def _rebuild(self):
         self.engine.close()
         self.engine = Engine(self.spec.to_struct())
+        if self.spec.path_ref is not None:
+            self.engine.set_path(self.spec.path_ref, self.spec.path_ind, self.spec.path_sigma)
         self.engine.set_state(self._x0, self._v0)
         if self._window is not None:
             self.engine.set_walker_bias(*self._window)

@@ -297,6 +297,55 @@ def constants():
     dump("constants.json", out)
 
 
+def path_colvars():
+    """Path / Path5dto2d (colvars/path.py): values and Jacobians at random points, plus the reference's
+    own known answers (tests/unit/test_colvar_path.py:18,43,65) and a short umbrella trajectory in path
+    space.  The reference-point table of tests/inputs/path_ref is stored inside the fixture."""
+    ref_stub.install()
+    from ndsimulator.colvars import Path, Path5dto2d
+    out = {}
+    data = np.loadtxt(os.path.join(ref_stub.REFERENCE_ROOT, "tests", "inputs", "path_ref"))
+    tables = {
+        "kat_1d": dict(ref=[[1], [3], [5], [7]], ref_ind=[0, 1, 2, 3], sigma=1, point=[6.0],
+                       expect=0.8287934528751985),
+        "kat_2d": dict(ref=[[1, 3.14], [2.05, 4], [3.9, 5], [4.6, 5.9]], ref_ind=[0, 1, 2, 3], sigma=1.0,
+                       point=[2.5, 3.1], expect=0.24646052616257966),
+        "kat_file": dict(ref=data[:, 1:].tolist(), ref_ind=data[:, 0].tolist(), sigma=1.0,
+                         point=[17.40447553, 19.68877675], expect=0.50117643),
+    }
+    rng = np.random.RandomState(5)
+    for name, t in tables.items():
+        cov = Path(ref=np.array(t["ref"], dtype=float), ref_ind=np.array(t["ref_ind"], dtype=float).reshape(-1, 1),
+                   sigma=t["sigma"])
+        cov.initialize()
+        nd = len(t["point"])
+        pts = [np.array(t["point"], dtype=float)] + [np.array(t["point"]) + rng.normal(scale=1.5, size=nd) for _ in range(6)]
+        rec = dict(t, ndim=nd, points=[], value=[], jac=[])
+        for x in pts:
+            rec["points"].append(tolist(x))
+            rec["value"].append(float(cov.compute(x)[0]))
+            rec["jac"].append(tolist(cov.jacobian(x)))
+        out[name] = rec
+    cov5 = Path5dto2d(ref=data[:, 1:], ref_ind=data[:, 0].reshape(-1, 1), sigma=1.5)
+    cov5.initialize()
+    rec = dict(ref=data[:, 1:].tolist(), ref_ind=data[:, 0].tolist(), sigma=1.5, ndim=5, points=[], value=[], jac=[])
+    for _ in range(7):
+        x = np.array([rng.uniform(5, 25), rng.uniform(-5, 5), rng.uniform(10, 30), rng.uniform(-5, 5), rng.uniform(0, 50)])
+        rec["points"].append(tolist(x))
+        rec["value"].append(float(cov5.compute(x)[0]))
+        rec["jac"].append(tolist(cov5.jacobian(x)))
+    out["path5dto2d_file"] = rec
+    # umbrella sampling along the 2-D path variable, NVE (deterministic), through NDRun
+    cfg = base_cfg(ndim=2, potential="Mueller2d", x0=[22.0, 28.0], integrate="nve", seed=11, steps=400,
+                   colvar_name="Path", colvar_ref=data[:, 1:], colvar_ref_ind=data[:, 0].reshape(-1, 1),
+                   colvar_sigma=2.0, biases=["umb"], umb_k=5.0, umb_r0=[0.5])
+    t = run_traj(cfg, 50)
+    t["config"]["colvar_ref"] = data[:, 1:].tolist()
+    t["config"]["colvar_ref_ind"] = data[:, 0].tolist()
+    out["umb_on_path_nve"] = t
+    dump("path_colvar.json", out)
+
+
 def dump_files():
     """Text dumps of the reference (io/dump.py) for deterministic runs: NVE and gamma=0 metadynamics."""
     out = {}
@@ -337,8 +386,8 @@ def dump_files():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "dump_files":
-        dump_files()
+    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars"):
+        globals()[sys.argv[1]]()
         sys.exit(0)
     eval_points()
     bias_points()
@@ -346,3 +395,4 @@ if __name__ == "__main__":
     trajectories()
     committor()
     dump_files()
+    path_colvars()

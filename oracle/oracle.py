@@ -45,6 +45,7 @@ def lib():
         L.oracle_constants.argtypes = [C.c_void_p, _dp]
         L.oracle_set_state.argtypes = [C.c_void_p, _dp, _dp]
         L.oracle_set_walker_bias.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_set_path.argtypes = [C.c_void_p, C.c_int64, C.c_int, _dp, _dp, C.c_double]
         L.oracle_set_noise.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64]
         L.oracle_begin.argtypes = [C.c_void_p]
         L.oracle_frame_width.argtypes = [C.c_void_p]
@@ -122,6 +123,11 @@ class OracleSim:
         k = _f64(np.asarray(k).reshape(self.cd, self.M))
         r0 = _f64(np.asarray(r0).reshape(self.cd, self.M))
         self.L.oracle_set_walker_bias(self.h, _p(k), _p(r0))
+
+    def set_path(self, ref, ref_ind, sigma=1.0):
+        ref = _f64(np.asarray(ref, dtype=float).reshape(len(ref_ind), -1))
+        ind = _f64(np.asarray(ref_ind, dtype=float).reshape(-1))
+        self.L.oracle_set_path(self.h, len(ind), ref.shape[1], _p(ref), _p(ind), float(sigma))
 
     def set_noise(self, noise, first_step=0):
         self._noise = _f64(noise)  # [nsteps][nn][M], kept alive
