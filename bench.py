@@ -314,34 +314,36 @@ def main():
         value = float(tot[0]) / (dev_ms * 1e-3)
         c3_info = {"shots": world * M, "committed": int(tot[1]), "to_basin_1": int(tot[2]),
                    "p_basin1_given_committed": float(tot[2] / max(tot[1], 1)),
-                   "lane_utilisation": float(tot[0]) / (world * M * md_steps * args.steps)}
+                   "integrated_fraction_of_nominal_steps": float(tot[0]) / (world * M * md_steps * args.steps)}
         args.no_e2e = True
 
     # ---- end to end through the public API with host buffers (pinned), every step
     e2e = None
     if not args.no_e2e:
         nd = spec.ndim
-        hx = torch.empty((nd, M), dtype=torch.float64).pin_memory()
-        hv = torch.empty((nd, M), dtype=torch.float64).pin_memory()
-        st = eng.get_state(fields=("x", "v"))
-        hx.numpy()[:] = st["x"]
-        hv.numpy()[:] = st["v"]
-        ox = torch.empty((nd, M), dtype=torch.float64).pin_memory()
-        ov = torch.empty((nd, M), dtype=torch.float64).pin_memory()
+        # two pinned buffer sets, ping-pong: the state read back from step n is the input of step n+1
+        bufs = [dict(x=torch.empty((nd, M), dtype=torch.float64).pin_memory(),
+                     v=torch.empty((nd, M), dtype=torch.float64).pin_memory()) for _ in range(2)]
         oth = torch.empty((5, M), dtype=torch.float64).pin_memory()
+        st = eng.get_state(fields=("x", "v"))
+        bufs[0]["x"].numpy()[:] = st["x"]
+        bufs[0]["v"].numpy()[:] = st["v"]
         import ctypes as C
         dp = C.POINTER(C.c_double)
 
         def ptr(tens):
             return C.cast(tens.data_ptr(), dp)
 
+        flip = [0]
+
         def e2e_step():
+            src, dst = bufs[flip[0]], bufs[1 - flip[0]]
             # positions AND velocities are supplied, so the run continues (no re-draw, no re-begin)
-            eng._check(eng.lib.nds_set_state(eng.h, ptr(hx), ptr(hv)))
+            eng._check(eng.lib.nds_set_state(eng.h, ptr(src["x"]), ptr(src["v"])))            # H2D
             eng._check(eng.lib.nds_run(eng.h, md_steps))
-            eng._check(eng.lib.nds_get_state(eng.h, ptr(ox), ptr(ov), None, None, None, ptr(oth)))
-            hx.copy_(ox)
-            hv.copy_(ov)
+            eng._check(eng.lib.nds_get_state(eng.h, ptr(dst["x"]), ptr(dst["v"]), None, None, None,
+                                             ptr(oth)))                                        # D2H
+            flip[0] = 1 - flip[0]
 
         e2e_n = max(3, min(args.steps, 20))
         for _ in range(2):

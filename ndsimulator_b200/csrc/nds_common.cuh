@@ -75,7 +75,9 @@ struct Consts {
 // Per-launch arguments of the fused step kernel.
 template <typename R>
 struct BlockArgs {
-  long long M;             // local walkers
+  long long M;             // local walkers = stride of the SoA arrays
+  long long n_active;      // slots [0, n_active) are launched (0 = all M); committor compaction shrinks it
+  const long long* ids;    // slot -> local walker index after compaction (null = identity)
   long long walker_offset; // global id of local walker 0
   long long step0;         // NDRun.step before the first step of this launch
   long long nsteps;        // steps to run in this launch

@@ -12,6 +12,8 @@
 #include <type_traits>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "nds_variants.h"
 
 namespace nds { constexpr int MTD_TILE_HOST = 2048; }  // >= mtd_tile_records<R>() of nds_mtd_kernel.cuh
@@ -332,6 +334,26 @@ static __global__ void philox_kat_kernel(u32x4 c, uint32_t k0, uint32_t k1, uint
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+static __global__ void compact_lists_kernel(long long n, long long n_alive, const unsigned char* alive,
+                                     const int* scan, int* holes, int* movers, int* n_holes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int front_alive = n_alive < n ? scan[n_alive] : (int)n_alive;
+  if (i == 0) *n_holes = (int)n_alive - front_alive;
+  if (i >= n) return;
+  if (i < n_alive) { if (!alive[i]) holes[i - scan[i]] = (int)i; }
+  else if (alive[i]) movers[scan[i] - front_alive] = (int)i;
+}
+
+static __global__ void iota_kernel(long long n, long long* ids) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = i;
+}
+static __global__ void alive_flags_kernel(long long n, const unsigned char* alive, int* flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = alive[i] ? 1 : 0;
+}
+
+
 static __global__ void count_alive_kernel(long long M, const unsigned char* alive, unsigned long long* out) {
   unsigned long long local = 0;
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < M; w += (long long)gridDim.x * blockDim.x)
@@ -365,6 +387,13 @@ struct Engine : nds_engine {
   int64_t stage_elems = 0;
   unsigned long long* d_counter = nullptr;
   bool have_v = false, begun = false, need_refresh_vr = true;
+  // committor lane compaction
+  long long* d_ids = nullptr;
+  int *d_flags = nullptr, *d_scan = nullptr, *d_holes = nullptr, *d_movers = nullptr, *d_nholes = nullptr;
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+  int64_t n_active = 0;
+  bool compactable = false, permuted = false;
   // peer-memory exchange: device array of every rank's hill table (own included)
   R** d_peer_tables = nullptr;
   std::vector<void*> ipc_opened;
@@ -378,7 +407,8 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
                     (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
-                    (void*)d_path_ref, (void*)d_path_ind,
+                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_ids, (void*)d_flags, (void*)d_scan,
+                    (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
                     (void*)d_counter})
       if (p) cudaFree(p);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
@@ -469,6 +499,20 @@ struct Engine : nds_engine {
       CU(cudaMemsetAsync(d_basin, 0xff, sizeof(int) * sM, stream));
       CU(cudaMemsetAsync(d_exit, 0, sizeof(long long) * sM, stream));
     }
+    n_active = M;
+    compactable = c.method == NDS_METHOD_COMMITTOR && !dumping && !c.mtd_enabled &&
+                  c.noise_mode == NDS_NOISE_PHILOX && !getenv("NDS_NO_COMPACTION");
+    if (compactable) {
+      CU(cudaMalloc(&d_ids, sizeof(long long) * sM));
+      CU(cudaMalloc(&d_flags, sizeof(int) * sM));
+      CU(cudaMalloc(&d_scan, sizeof(int) * (sM + 1)));
+      CU(cudaMalloc(&d_holes, sizeof(int) * sM));
+      CU(cudaMalloc(&d_movers, sizeof(int) * sM));
+      CU(cudaMalloc(&d_nholes, sizeof(int)));
+      cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_flags, d_scan, (int)M, stream);
+      CU(cudaMalloc(&d_cub, cub_bytes));
+      iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
+    }
     CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     frame_width = 2 + 3 * nd + cd + 6;
     if (dumping) {
@@ -516,6 +560,12 @@ struct Engine : nds_engine {
   int set_state(const double* x, const double* v) override {
     CU(cudaSetDevice(cfg.device));
     if (!x) return fail(this, "nds_set_state: x is null");
+    if (permuted) {  // new state for every walker: slots go back to walker order, all walkers live again
+      iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
+      permuted = false;
+      n_active = M;
+      CU(cudaMemsetAsync(d_alive, 1, (size_t)M, stream));
+    }
     if (upload(x, d_x, (int64_t)nd * M)) return 1;
     if (v) { if (upload(v, d_v, (int64_t)nd * M)) return 1; }
     // positions + velocities given: a running simulation continues from the new state (the next
@@ -575,6 +625,7 @@ struct Engine : nds_engine {
     A.x = d_x; A.v = d_v; A.f = d_f; A.fixf = d_fixf; A.colv = d_colv; A.thermo = d_thermo; A.vr = d_vr;
     A.umb_k = d_umb_k; A.umb_r0 = d_umb_r0;
     A.alive = d_alive; A.basin = d_basin; A.exit_step = d_exit;
+    A.n_active = n_active; A.ids = permuted ? d_ids : nullptr;
     A.hills = d_hills; A.n_hills = n_hills;
     A.noise = d_noise; A.noise_first = noise_first;
     A.frames = d_frames; A.frame_base = frames_written; A.frame_cap = cfg.dump_capacity;
@@ -587,6 +638,13 @@ struct Engine : nds_engine {
     if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
       return fail(this, "path colvar: call nds_set_path() before nds_begin()");
     step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
+    if (cfg.method == NDS_METHOD_COMMITTOR) {
+      if (permuted && unpermute_device()) return 1;
+      CU(cudaMemsetAsync(d_alive, 1, (size_t)M, stream));
+      CU(cudaMemsetAsync(d_basin, 0xff, sizeof(int) * (size_t)M, stream));
+      CU(cudaMemsetAsync(d_exit, 0, sizeof(long long) * (size_t)M, stream));
+      n_active = M;
+    }
     BlockArgs<R> A = make_args(0);
     A.refresh_vr = 1;
     A.need_init_v = have_v ? 0 : 1;
@@ -638,6 +696,68 @@ struct Engine : nds_engine {
     n_hills += add;
     dep_count += 1;
     need_refresh_vr = true;
+    return 0;
+  }
+
+  // pack the live walkers into slots [0, n_alive) (see compact_swap_kernel)
+  int compact() {
+    if (n_active <= 0) return 0;
+    CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+    count_alive_kernel<<<296, 256, 0, stream>>>(n_active, d_alive, d_counter);
+    unsigned long long h_alive = 0;
+    CU(cudaMemcpyAsync(&h_alive, d_counter, sizeof h_alive, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    launches++;
+    const int64_t n_alive = (int64_t)h_alive;
+    if (n_alive == n_active || n_active - n_alive < n_active / 16) return 0;  // not worth a pass yet
+    if (n_alive > 0) {
+      const unsigned g = (unsigned)((n_active + 255) / 256);
+      alive_flags_kernel<<<g, 256, 0, stream>>>(n_active, d_alive, d_flags);
+      size_t bytes = cub_bytes;
+      CU(cub::DeviceScan::ExclusiveSum(d_cub, bytes, d_flags, d_scan, (int)n_active, stream));
+      compact_lists_kernel<<<g, 256, 0, stream>>>(n_active, n_alive, d_alive, d_scan, d_holes, d_movers, d_nholes);
+      const int64_t hb = n_alive < n_active - n_alive ? n_alive : n_active - n_alive;
+      if (hb > 0)
+        compact_swap_kernel<R><<<(unsigned)((hb + 127) / 128), 128, 0, stream>>>(
+            M, nd, cd, d_holes, d_movers, d_nholes, d_x, d_v, d_f, d_fixf, d_colv, d_thermo, d_vr, d_umb_k,
+            d_umb_r0, d_alive, d_basin, d_exit, d_ids);
+      CU(cudaGetLastError());
+      launches += 4;
+      permuted = true;
+    }
+    n_active = n_alive;
+    return 0;
+  }
+
+  // host-side inverse permutation of a downloaded [rows][M] array: out[ids[slot]] = in[slot]
+  template <typename T>
+  int unpermute_host(T* buf, int rows) {
+    if (!permuted) return 0;
+    std::vector<long long> ids((size_t)M);
+    CU(cudaMemcpyAsync(ids.data(), d_ids, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    std::vector<T> tmp((size_t)M);
+    for (int r = 0; r < rows; r++) {
+      T* row = buf + (size_t)r * M;
+      for (int64_t s = 0; s < M; s++) tmp[(size_t)ids[(size_t)s]] = row[s];
+      memcpy(row, tmp.data(), sizeof(T) * (size_t)M);
+    }
+    return 0;
+  }
+
+  // restore slot == walker on the device (before a new begin)
+  int unpermute_device() {
+    std::vector<double> buf;
+    auto fix = [&](R* d, int rows) -> int {
+      if (!d) return 0;
+      buf.resize((size_t)rows * M);
+      if (download(d, buf.data(), (int64_t)rows * M)) return 1;
+      if (unpermute_host<double>(buf.data(), rows)) return 1;
+      return upload(buf.data(), d, (int64_t)rows * M);
+    };
+    if (fix(d_x, nd) || fix(d_v, nd) || fix(d_umb_k, cd) || fix(d_umb_r0, cd)) return 1;
+    iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
+    permuted = false;
     return 0;
   }
 
@@ -703,6 +823,7 @@ struct Engine : nds_engine {
       step += k;
       frames_written += events;
       remaining -= k;
+      if (compactable && compact()) return 1;
     }
     CU(cudaEventRecord(ev1, stream));
     timed = true;
@@ -726,12 +847,12 @@ struct Engine : nds_engine {
 
   int get_state(double* x, double* v, double* f, double* fixf, double* colv, double* thermo) override {
     CU(cudaSetDevice(cfg.device));
-    if (x && download(d_x, x, (int64_t)nd * M)) return 1;
-    if (v && download(d_v, v, (int64_t)nd * M)) return 1;
-    if (f && download(d_f, f, (int64_t)nd * M)) return 1;
-    if (fixf && download(d_fixf, fixf, (int64_t)nd * M)) return 1;
-    if (colv && download(d_colv, colv, (int64_t)cd * M)) return 1;
-    if (thermo && download(d_thermo, thermo, (int64_t)5 * M)) return 1;
+    if (x && (download(d_x, x, (int64_t)nd * M) || unpermute_host(x, nd))) return 1;
+    if (v && (download(d_v, v, (int64_t)nd * M) || unpermute_host(v, nd))) return 1;
+    if (f && (download(d_f, f, (int64_t)nd * M) || unpermute_host(f, nd))) return 1;
+    if (fixf && (download(d_fixf, fixf, (int64_t)nd * M) || unpermute_host(fixf, nd))) return 1;
+    if (colv && (download(d_colv, colv, (int64_t)cd * M) || unpermute_host(colv, cd))) return 1;
+    if (thermo && (download(d_thermo, thermo, (int64_t)5 * M) || unpermute_host(thermo, 5))) return 1;
     return 0;
   }
 
@@ -823,26 +944,33 @@ struct Engine : nds_engine {
 
   int get_vr(double* vr) override {
     CU(cudaSetDevice(cfg.device));
-    return download(d_vr, vr, M);
+    return download(d_vr, vr, M) || unpermute_host(vr, 1);
   }
 
   int get_commit(int32_t* basin, int64_t* exit_step) override {
     CU(cudaSetDevice(cfg.device));
     if (cfg.method != NDS_METHOD_COMMITTOR) return fail(this, "nds_get_commit: method is not committor");
     CU(cudaStreamSynchronize(stream));
-    if (basin) CU(cudaMemcpy(basin, d_basin, sizeof(int) * (size_t)M, cudaMemcpyDeviceToHost));
+    if (basin) {
+      CU(cudaMemcpy(basin, d_basin, sizeof(int) * (size_t)M, cudaMemcpyDeviceToHost));
+      if (unpermute_host<int32_t>(basin, 1)) return 1;
+    }
     if (exit_step) {
       std::vector<unsigned char> alive((size_t)M);
-      CU(cudaMemcpy(exit_step, d_exit, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
+      std::vector<long long> ex((size_t)M);
+      CU(cudaMemcpy(ex.data(), d_exit, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
       CU(cudaMemcpy(alive.data(), d_alive, (size_t)M, cudaMemcpyDeviceToHost));
       for (int64_t w = 0; w < M; w++)
-        if (alive[(size_t)w]) exit_step[w] = step;  // uncommitted: ran all steps (ndrun.py:220)
+        if (alive[(size_t)w]) ex[(size_t)w] = step;  // uncommitted: ran all steps (ndrun.py:220)
+      if (unpermute_host<long long>(ex.data(), 1)) return 1;
+      for (int64_t w = 0; w < M; w++) exit_step[w] = ex[(size_t)w];
     }
     return 0;
   }
 
   int64_t count_alive() override {
     if (cfg.method != NDS_METHOD_COMMITTOR) return M;
+    // after compaction the live walkers are exactly the launched slots that have not stopped since
     cudaSetDevice(cfg.device);
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
     count_alive_kernel<<<296, 256, 0, stream>>>(M, d_alive, d_counter);

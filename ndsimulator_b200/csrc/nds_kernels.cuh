@@ -108,9 +108,10 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   constexpr int G = noise_group(NN);
   constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
 
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
-  if (w >= M) return;
+  if (w >= (A.n_active > 0 ? A.n_active : M)) return;
+  const long long lw = A.ids ? A.ids[w] : w;  // local walker index of this slot (Philox stream, noise row)
 
   const int pot = S::POT >= 0 ? S::POT : K.pot;
   const int cv = S::CV >= 0 ? S::CV : K.cv;
@@ -137,7 +138,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     for (int k = 0; k < ND; k++)
       if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
-  const unsigned long long gid = (unsigned long long)(A.walker_offset + w * PACK);
+  const unsigned long long gid = (unsigned long long)(A.walker_offset + lw * PACK);
   const long long hstride = K.mtd_shared ? 1 : M;
   const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
 
@@ -191,7 +192,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
         R xi[ND], eta[ND];
         if (NN > 0) {
           if (PACK == 1 && ext_noise) {  // md.py:120,127-128 with numbers supplied by the caller (parity tests)
-            const double* row = A.noise + ((s - A.noise_first) * NN) * M + w;
+            const double* row = A.noise + ((s - A.noise_first) * NN) * M + lw;
 #pragma unroll
             for (int d = 0; d < ND; d++) {
               xi[d] = (R)row[(long long)d * M];
@@ -480,6 +481,31 @@ __global__ void histogram_kernel(long long M, int cd, const R* __restrict__ colv
   __syncthreads();
   for (int b = threadIdx.x; b < nb; b += blockDim.x)
     if (bins[b]) atomicAdd(&counts[b], (unsigned long long)bins[b]);
+}
+
+// ---------------------------------------------------------------- committor lane compaction
+// Stopped walkers idle their lane (57 % of the example shots never commit while others exit
+// after a few hundred steps).  Between launches the live walkers are packed into slots [0, n_alive):
+// every dead slot in the front ("hole") swaps with a live slot from the back ("mover"), matched by rank
+// (exclusive scan of the alive flags), so the next launch covers only live walkers.  ids[] keeps
+// slot -> walker so that Philox streams, noise rows and the getters are unaffected.
+template <typename R>
+__global__ void compact_swap_kernel(long long M, int nd, int cd, const int* holes, const int* movers,
+                                    const int* n_holes, R* x, R* v, R* f, R* fixf, R* colv, R* thermo,
+                                    R* vr, R* umb_k, R* umb_r0, unsigned char* alive, int* basin,
+                                    long long* exit_step, long long* ids) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= *n_holes) return;
+  const long long a = holes[r], b = movers[r];
+  auto sw = [&](R* arr, int rows) {
+    for (int q = 0; q < rows; q++) { const R t = arr[q * M + a]; arr[q * M + a] = arr[q * M + b]; arr[q * M + b] = t; }
+  };
+  sw(x, nd); sw(v, nd); sw(f, nd); sw(fixf, nd); sw(colv, cd); sw(thermo, 5); sw(vr, 1);
+  if (umb_k) { sw(umb_k, cd); sw(umb_r0, cd); }
+  { const unsigned char t = alive[a]; alive[a] = alive[b]; alive[b] = t; }
+  { const int t = basin[a]; basin[a] = basin[b]; basin[b] = t; }
+  { const long long t = exit_step[a]; exit_step[a] = exit_step[b]; exit_step[b] = t; }
+  { const long long t = ids[a]; ids[a] = ids[b]; ids[b] = t; }
 }
 
 // empty hill records: height 0, log2(height) = -inf

@@ -23,7 +23,8 @@ using BlockLaunchFn = cudaError_t (*)(const Consts<R>&, const BlockArgs<R>&, cud
 template <class S>
 cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
                             cudaStream_t st) {
-  const unsigned grid = (unsigned)((A.M + NDS_BLOCK - 1) / NDS_BLOCK);
+  const long long n = A.n_active > 0 ? A.n_active : A.M;
+  const unsigned grid = (unsigned)((n + NDS_BLOCK - 1) / NDS_BLOCK);
   md_block<S><<<grid, NDS_BLOCK, 0, st>>>(K, A);
   return cudaGetLastError();
 }

@@ -609,3 +609,27 @@ def test_peer_memory_deposit_emulated_on_one_gpu():
             assert np.array_equal(st[k], ref[k][..., r * M:(r + 1) * M]), (r, k)
         c, h = engines[r].get_hills()
         assert np.array_equal(c, ref_hills[0]) and np.array_equal(h, ref_hills[1])
+
+
+def test_committor_compaction_is_invisible(monkeypatch):
+    """Lane compaction between launches (live walkers packed to the front) must not change any result:
+    same basins, exit steps and final states as with compaction disabled."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], steps=6000, seed=4)
+    M = 20000
+    outs = []
+    for mode in ("compact", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("NDS_NO_COMPACTION", "1")
+        spec = spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=500)
+        eng = Engine(spec.to_struct())
+        eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
+        eng.begin()
+        eng.run(6000)
+        basin, exit_step = eng.get_commit()
+        outs.append((basin, exit_step, eng.get_state(), eng.count_alive()))
+    (b0, e0, s0, a0), (b1, e1, s1, a1) = outs
+    assert (b0 >= 0).sum() > 1000
+    assert np.array_equal(b0, b1) and np.array_equal(e0, e1) and a0 == a1
+    for k in ("x", "v", "colv", "pe", "T"):
+        assert np.array_equal(s0[k], s1[k]), k
