@@ -39,8 +39,11 @@ enum { NDS_F32 = 0, NDS_F64 = 1 };
 /* method: engines/__init__.py:11-31 (md, committor with temperature != 0) */
 enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1 };
 
-/* integrate: engines/md.py:59 */
-enum { NDS_INT_LANGEVIN = 0, NDS_INT_LANGEVIN2 = 1, NDS_INT_NVE = 2, NDS_INT_RESCALE = 3 };
+/* integrate: engines/md.py:59; NDS_INT_MINIMIZE = the fixed-step steepest descent of
+ * engines/minimize.py:41-82 (the inner engine of a committor run at temperature 0,
+ * engines/__init__.py:22-23) */
+enum { NDS_INT_LANGEVIN = 0, NDS_INT_LANGEVIN2 = 1, NDS_INT_NVE = 2, NDS_INT_RESCALE = 3,
+       NDS_INT_MINIMIZE = 4 };
 
 /* potential: class names of ndsimulator/potentials (potentials/_build.py:12-18) */
 enum {
@@ -147,6 +150,11 @@ typedef struct nds_config {
   int64_t dump_walkers;       /* frames are recorded for local walkers [0, dump_walkers) */
   int64_t dump_capacity;      /* frames the device ring can hold between two drains */
   int64_t stat_freq;          /* io/stat.py:10; defines which thermo sample a dump row shows (A16) */
+
+  /* Minimize (engines/minimize.py:8-22) and the T = 0 committor energy criterion (committor.py:41,130) */
+  double emin;                /* committor.py:41, default -1.2: at T = 0 a basin needs pe < emin */
+  double min_gtol;            /* minimize.py:12, default 1e-5 */
+  int64_t min_maxiter;        /* minimize.py:11,26-27, default steps * 10 */
 } nds_config;
 
 typedef struct nds_engine nds_engine;

@@ -14,11 +14,11 @@ NDS_MAX_BASINS = 8
 
 NDS_F32, NDS_F64 = 0, 1
 NDS_METHOD_MD, NDS_METHOD_COMMITTOR = 0, 1
-NDS_INT_LANGEVIN, NDS_INT_LANGEVIN2, NDS_INT_NVE, NDS_INT_RESCALE = 0, 1, 2, 3
+NDS_INT_LANGEVIN, NDS_INT_LANGEVIN2, NDS_INT_NVE, NDS_INT_RESCALE, NDS_INT_MINIMIZE = 0, 1, 2, 3, 4
 NDS_NOISE_PHILOX, NDS_NOISE_EXTERNAL = 0, 1
 
 INTEGRATORS = {"langevin": NDS_INT_LANGEVIN, "2nd-langevin": NDS_INT_LANGEVIN2,
-               "nve": NDS_INT_NVE, "rescale": NDS_INT_RESCALE}
+               "nve": NDS_INT_NVE, "rescale": NDS_INT_RESCALE, "minimize": NDS_INT_MINIMIZE}
 
 # class names of ndsimulator/potentials (reference potentials/__init__.py) -> (id, ndim, require_colvar)
 POTENTIALS = {
@@ -77,6 +77,7 @@ class NdsConfig(C.Structure):
         ("criteria", ((C.c_double * 2) * NDS_MAX_CV) * NDS_MAX_BASINS),
         ("dump_freq", C.c_int64), ("dump_walkers", C.c_int64), ("dump_capacity", C.c_int64),
         ("stat_freq", C.c_int64),
+        ("emin", C.c_double), ("min_gtol", C.c_double), ("min_maxiter", C.c_int64),
     ]
 
 

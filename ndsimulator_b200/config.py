@@ -94,6 +94,9 @@ class RunSpec:
     n_basins: int = 0
     criteria: Optional[np.ndarray] = None
     diffusion_time: int = 0
+    emin: float = -1.2
+    min_gtol: float = 1.0e-5
+    min_maxiter: Optional[int] = None
     dump: bool = True
     dump_freq: int = 1
     stat_freq: int = 1
@@ -162,6 +165,9 @@ class RunSpec:
                 for k in range(self.colvardim):
                     c.criteria[b][k][0] = float(self.criteria[b][k][0])
                     c.criteria[b][k][1] = float(self.criteria[b][k][1])
+        c.emin = float(self.emin)
+        c.min_gtol = float(self.min_gtol)
+        c.min_maxiter = int(self.min_maxiter if self.min_maxiter is not None else self.steps * 10)
         c.dump_freq = int(self.dump_freq) if self.dump else 0
         c.dump_walkers = int(min(self.dump_walkers, self.n_walkers)) if self.dump else 0
         c.dump_capacity = int(self.dump_capacity)
@@ -199,12 +205,10 @@ def parse(config: dict) -> RunSpec:
     if method == "md":
         eng_prefix = ["md", "engine"]
     elif method == "committor":
-        if spec.temperature == 0:
-            raise NotImplementedError(
-                "committor at temperature 0 uses the Minimize engine (engines/minimize.py), which is "
-                "outside the B200 hot path")
         eng_prefix = ["engine_method", "committor", "engine"]
-    elif method in ("mc", "wl-mc", "minimize", "read_dump"):
+    elif method == "minimize":
+        eng_prefix = ["minimize", "engine"]
+    elif method in ("mc", "wl-mc", "read_dump"):
         raise NotImplementedError(
             f"method '{method}' is not part of the B200 multi-walker MD path (SURVEY.md section 8f)")
     else:
@@ -213,6 +217,11 @@ def parse(config: dict) -> RunSpec:
     spec.gamma = pick(cfg, "gamma", eng_prefix, 0.005)
     spec.integrate = pick(cfg, "integrate", eng_prefix, "langevin")
     assert spec.integrate in ["langevin", "2nd-langevin", "rescale", "nve"]  # md.py:59
+    if method == "minimize" or (method == "committor" and spec.temperature == 0):
+        # engines/__init__.py:22-23: the committor's inner engine is Minimize at temperature 0
+        spec.integrate = "minimize"
+        spec.min_gtol = pick(cfg, "gtol", eng_prefix, 1.0e-5)
+        spec.min_maxiter = pick(cfg, "maxiter", eng_prefix, None)
     spec.rescale_freq = pick(cfg, "rescale_freq", eng_prefix, None)
     if spec.integrate == "rescale" and spec.rescale_freq is None:
         raise TypeError("integrate: rescale needs rescale_freq (md.py:220)")
@@ -324,6 +333,7 @@ def parse(config: dict) -> RunSpec:
         spec.n_basins = int(pick(cfg, "n_basins", ["committor", "engine"]))
         spec.criteria = np.array(pick(cfg, "criteria", ["committor", "engine"]), dtype=float)
         spec.diffusion_time = int(pick(cfg, "diffusion_time", ["committor", "engine"], 0))
+        spec.emin = float(pick(cfg, "emin", ["committor", "engine"], -1.2))
         assert len(spec.criteria) == spec.n_basins  # committor.py:57
         for crit in spec.criteria:
             assert len(crit) == cd  # committor.py:73

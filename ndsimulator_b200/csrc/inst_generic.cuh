@@ -11,6 +11,7 @@ const Variant* NDS_FN(int* n) {
       make_variant<Spec<NDS_R, NDS_ND, DYN, DYN, DYN, NDS_INT_LANGEVIN2>>("md_block<" NDS_TAG ",generic,2nd-langevin>"),
       make_variant<Spec<NDS_R, NDS_ND, DYN, DYN, DYN, NDS_INT_NVE>>("md_block<" NDS_TAG ",generic,nve>"),
       make_variant<Spec<NDS_R, NDS_ND, DYN, DYN, DYN, NDS_INT_RESCALE>>("md_block<" NDS_TAG ",generic,rescale>"),
+      make_variant<Spec<NDS_R, NDS_ND, DYN, DYN, DYN, NDS_INT_MINIMIZE>>("md_block<" NDS_TAG ",generic,minimize>"),
   };
   *n = (int)(sizeof(table) / sizeof(table[0]));
   return table;

@@ -66,6 +66,8 @@ struct Consts {
   R pe_thred;
   R crit[NDS_MAX_BASINS][NDS_MAX_CV][2];
   long long diffusion_time;
+  // Minimize (engines/minimize.py) and the T = 0 committor criterion pe < emin (committor.py:128-131)
+  R min_gtol, emin; long long min_maxiter; int zero_temperature;
   long long dump_freq, stat_freq, dump_walkers;
   unsigned int key0, key1;  // Philox key = seed
   PhiloxKeys rk_step;       // round keys of the per-step noise stream (domain 0)

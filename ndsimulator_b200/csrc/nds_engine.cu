@@ -120,7 +120,7 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "path colvars are supported as colvar_name, not as true_colvar_name");
   if (kPotNeedsTcv[c->potential] && nds_colvar_dim(c->true_colvar, c->ndim) != 2)
     return fail(nullptr, "potential %d is evaluated in a 2-D true_colvar space", c->potential);
-  if (c->integrator < 0 || c->integrator > NDS_INT_RESCALE)  // md.py:59
+  if (c->integrator < 0 || c->integrator > NDS_INT_MINIMIZE)  // md.py:59
     return fail(nullptr, "unknown integrator %d", c->integrator);
   if (c->integrator == NDS_INT_RESCALE && !(c->rescale_freq > 0))  // md.py:220 (TypeError on None)
     return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
@@ -140,7 +140,8 @@ static int validate(const nds_config* c) {
   }
   if (c->method == NDS_METHOD_COMMITTOR) {
     if (c->n_basins < 1 || c->n_basins > NDS_MAX_BASINS) return fail(nullptr, "n_basins out of range");
-    if (c->temperature == 0) return fail(nullptr, "committor at temperature 0 (Minimize engine) is out of scope");
+    if (c->temperature == 0 && c->integrator != NDS_INT_MINIMIZE)  // engines/__init__.py:22-23
+      return fail(nullptr, "committor at temperature 0 runs the Minimize engine: set integrator = NDS_INT_MINIMIZE");
   }
   if (c->steps_per_launch <= 0) return fail(nullptr, "steps_per_launch must be positive");
   if (c->dump_freq > 0 && c->dump_walkers > 0 && c->dump_capacity <= 0)
@@ -170,7 +171,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.hill_stride = (K.cd == 2) ? 4 : K.cd + 1;
   const double m = au_mass_() * c.mass;        // data.py:27-28
   const double kBT = kB_ * c.temperature;      // data.py:26
-  const double dt = c.dt, gamma = c.gamma;
+  // Minimize multiplies the configured time step by 10 (engines/minimize.py:18)
+  const double dt = (c.integrator == NDS_INT_MINIMIZE) ? c.dt * 10 : c.dt, gamma = c.gamma;
   K.m = (R)m; K.inv_m = (R)(1.0 / m); K.dt = (R)dt; K.kB = (R)kB_; K.kBT = (R)kBT;
   K.dt64 = dt; K.rescale_freq = c.rescale_freq;
   K.hdtm = (R)(dt / (2.0 * m));
@@ -249,6 +251,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   for (int bb = 0; bb < NDS_MAX_BASINS; bb++)
     for (int k = 0; k < NDS_MAX_CV; k++) { K.crit[bb][k][0] = (R)c.criteria[bb][k][0]; K.crit[bb][k][1] = (R)c.criteria[bb][k][1]; }
   K.diffusion_time = c.diffusion_time;
+  K.min_gtol = (R)c.min_gtol; K.emin = (R)c.emin; K.min_maxiter = c.min_maxiter;
+  K.zero_temperature = (c.temperature == 0) ? 1 : 0;
   const bool dumping = c.dump_freq > 0 && c.dump_walkers > 0;
   K.dump_freq = dumping ? c.dump_freq : 0;
   K.stat_freq = c.stat_freq > 0 ? c.stat_freq : 1;
@@ -418,6 +422,8 @@ struct Engine : nds_engine {
     if (stream) cudaStreamDestroy(stream);
   }
 
+  double step_dt() const { return cfg.integrator == NDS_INT_MINIMIZE ? cfg.dt * 10 : cfg.dt; }
+
   int64_t hill_elems() const {
     if (!cfg.mtd_shared) return cfg.mtd_capacity * (int64_t)K.hill_stride * M;
     // shared table: padded with zero-height records to whole TMA tiles (mtd_block reads full tiles)
@@ -500,7 +506,7 @@ struct Engine : nds_engine {
       CU(cudaMemsetAsync(d_exit, 0, sizeof(long long) * sM, stream));
     }
     n_active = M;
-    compactable = c.method == NDS_METHOD_COMMITTOR && !dumping && !c.mtd_enabled &&
+    compactable = c.method == NDS_METHOD_COMMITTOR && c.integrator != NDS_INT_MINIMIZE && !dumping && !c.mtd_enabled &&
                   c.noise_mode == NDS_NOISE_PHILOX && !getenv("NDS_NO_COMPACTION");
     if (compactable) {
       CU(cudaMalloc(&d_ids, sizeof(long long) * sM));
@@ -782,7 +788,7 @@ struct Engine : nds_engine {
         double t = time;
         int64_t j = 0;
         while (j < k) {
-          t += cfg.dt; j++;
+          t += step_dt(); j++;
           if ((int64_t)std::floor(t / cfg.mtd_dep_freq) + 1 > dep_count) break;
         }
         k = j;
@@ -818,7 +824,7 @@ struct Engine : nds_engine {
           const int64_t count = (int64_t)std::floor(time / cfg.rescale_freq) + 1;  // md.py:220-222
           if (count > rescale_count) rescale_count = count;
         }
-        time += cfg.dt;  // ndrun.py:240
+        time += step_dt();  // ndrun.py:240 (engine.current_dt)
       }
       step += k;
       frames_written += events;

@@ -16,6 +16,7 @@ namespace nds {
 
 constexpr int NDS_BLOCK = 128;
 
+// NDS_INT_NVE, NDS_INT_RESCALE and NDS_INT_MINIMIZE draw no noise
 __host__ __device__ constexpr int normals_per_step(int integ, int nd) {
   return integ == NDS_INT_LANGEVIN ? nd : (integ == NDS_INT_LANGEVIN2 ? 2 * nd : 0);
 }
@@ -154,7 +155,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   // ---- forces at the current positions: MD.begin (md.py:101-110) / refresh after a deposition
   //      (gaus.py:138-146).  Identical to the values the previous launch ended with.
   Eval<R, ND> e;
-  eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+  eval_all<R, ND, INTEG == NDS_INT_MINIMIZE>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
   if (A.refresh_vr && (bias_mask & BIAS_MTD)) A.vr[w] = e.vm;  // Gaussian.VR, gaus.py:292-293
   R f[ND];
 #pragma unroll
@@ -169,6 +170,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   int basin = -1;
 
   long long exit_s = 0;
+  bool min_stop = false;
   while (s < s_end) {
     // the step counter stays warp-uniform: a stopped walker idles its lane until the whole warp is done
     if (PACK == 1 && committor && !__any_sync(0xffffffffu, alive)) break;
@@ -206,6 +208,28 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
             }
           }
         }
+        if constexpr (INTEG == NDS_INT_MINIMIZE) {
+          // Minimize.update, engines/minimize.py:41-82: x += f/m dt^2 with dt = 10 * config dt; a step
+          // that does not lower pe + biase (or starts below gtol) is undone and stops the walker, but
+          // pe / forces / colv stay those of the trial point.
+          const R pe_prev = e.pe + e.be;
+          R n2 = (R)0, xold[ND];
+#pragma unroll
+          for (int d = 0; d < ND; d++) { n2 += f[d] * f[d]; xold[d] = x[d]; x[d] += f[d] / K.m * K.dt * K.dt; }
+          eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+#pragma unroll
+          for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];
+          const R dE = e.pe + e.be - pe_prev;
+          bool stop = false;
+          if (dE >= (R)0) stop = true;
+          if (nds_sqrt(n2) < K.min_gtol) stop = true;
+          if (stop) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) x[d] = xold[d];
+          }
+          if (s > K.min_maxiter) stop = true;  // Minimize.step counts the updates done so far
+          min_stop = stop;
+        } else {
         // ---- first half kick + drift, md.py:164-178
 #pragma unroll
         for (int d = 0; d < ND; d++) {
@@ -265,6 +289,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
             }
           }
         }
+        }  // !MINIMIZE
         if (INTEG == NDS_INT_RESCALE) {  // md.py:219-224; `time` is the pre-step time (ndrun.py:230)
           const long long count = (long long)floor(time / K.rescale_freq) + 1;
           if (count > rescale_count) {
@@ -281,9 +306,13 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
         s += 1;            // ndrun.py:232
         time += K.dt64;    // ndrun.py:240
         if constexpr (PACK == 1) {
-          if (committor && alive && (s - 1) >= K.diffusion_time) {  // committor.py:100-111
-            basin = commit_test<R, ND>(K, cd, e.cv.c);
-            if (basin >= 0) { alive = false; exit_s = s; }
+          if (committor && alive) {
+            bool stopped = (INTEG == NDS_INT_MINIMIZE) && min_stop;  // committor.py:95-97
+            if ((s - 1) >= K.diffusion_time) {  // committor.py:100-111
+              basin = commit_test<R, ND>(K, cd, e.cv.c, e.pe);
+              if (basin >= 0) stopped = true;
+            }
+            if (stopped) { alive = false; exit_s = s; }
           }
           if (alive || exit_s == s) {
           if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
@@ -301,7 +330,8 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 
   // ---- launch exit: observables at the final positions (md.py:210-217,226-229) and state write-back
   Eval<R, ND> o;
-  eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+  if constexpr (INTEG == NDS_INT_MINIMIZE) o = e;  // pe / forces / colv of the last (trial) point, minimize.py:61-67
+  else eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
   R v2 = (R)0;
 #pragma unroll
   for (int d = 0; d < ND; d++) {

@@ -515,7 +515,9 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
 
 // committor.py:118-142: inclusive boxes in colvar space; the last matching basin wins
 template <typename R, int ND>
-NDS_DEV int commit_test(const Consts<R>& K, int cd, const R (&c)[ND]) {
+NDS_DEV int commit_test(const Consts<R>& K, int cd, const R (&c)[ND], R pe) {
+  // at temperature 0 a basin additionally needs pe < emin (committor.py:128-131)
+  if (K.zero_temperature && !(pe < K.emin)) return -1;
   int ib = -1;
   auto in_box = [&](int b) {
     bool in = true;

@@ -217,6 +217,10 @@ class NDRun:
     def run(self, steps=None):  # ndrun.py:214-268
         spec = self.spec
         total = spec.steps if steps is None else steps
+        if spec.method == "minimize":
+            # Minimize.update returns None, so the reference's loop `while step < steps and nostop`
+            # (ndrun.py:220,230) ends after ONE update; kept as is
+            total = min(total, self.step + 1)
         nostop = True
         chunk = max(spec.steps_per_launch, 1)
         if spec.dump:

@@ -279,6 +279,20 @@ def committor():
                                  x=tolist(sim.atoms.positions)))
         print(seed, sim.commit_basin, sim.step)
     dump("committor.json", out)
+    # temperature 0: the inner engine is Minimize (engines/__init__.py:22-23) -- deterministic relaxation
+    t0 = dict(config={k: v for k, v in dict(cm, temperature=0, seed=0, steps=3000).items()
+                      if k not in ("root", "run_name")}, runs=[])
+    rng = np.random.RandomState(3)
+    starts = [[21.0, 17.0], [30.0, 12.0], [24.0, 30.0], [35.0, 8.0], [26.0, 20.0], [22.0, 33.0], [44.0, 5.0]]
+    starts += rng.uniform([12.0, 2.0], [46.0, 36.0], size=(17, 2)).tolist()
+    for x0 in starts:
+        sim = ref_stub.make_run(dict(cm, temperature=0, seed=0, steps=3000, x0=x0))
+        sim.begin()
+        sim.run()
+        t0["runs"].append(dict(x0=tolist(x0), basin=int(sim.commit_basin), step=int(sim.step),
+                               x=tolist(sim.atoms.positions), pe=float(sim.atoms.pe),
+                               colv=tolist(sim.atoms.colv), time=float(sim.time)))
+    dump("committor_T0.json", t0)
 
 
 def constants():
@@ -386,7 +400,7 @@ def dump_files():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor"):
         globals()[sys.argv[1]]()
         sys.exit(0)
     eval_points()

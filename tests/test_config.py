@@ -82,11 +82,13 @@ def test_reference_errors():
 
 
 def test_out_of_scope_is_refused_loudly():
-    for method in ("mc", "wl-mc", "minimize", "read_dump"):
+    for method in ("mc", "wl-mc", "read_dump"):
         with pytest.raises(NotImplementedError):
             config.parse(base(method=method))
-    with pytest.raises(NotImplementedError):
-        config.parse(base(method="committor", temperature=0, n_basins=1, criteria=[[[0, 1], [0, 1]]]))
+    # temperature 0 selects the Minimize inner engine (engines/__init__.py:22-23)
+    s = config.parse(base(method="committor", temperature=0, n_basins=1, criteria=[[[0, 1], [0, 1]]]))
+    assert s.integrate == "minimize" and s.emin == -1.2 and s.to_struct().min_maxiter == 1000
+    assert config.parse(base(method="minimize")).integrate == "minimize"
     with pytest.raises(NotImplementedError):
         config.parse(base(biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=2.0, mtd_adapsig=True))
 

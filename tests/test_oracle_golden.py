@@ -134,3 +134,22 @@ def test_committor_shots():
     assert list(basin) == [s["basin"] for s in shots]
     assert list(exit_step) == [s["step"] for s in shots]
     assert np.allclose(o.get_state()["x"].T, np.array([s["x"] for s in shots]), rtol=1e-9)
+
+
+def test_committor_temperature_zero_minimize():
+    """T = 0 committor: the inner engine is the fixed-step steepest descent of engines/minimize.py;
+    deterministic, so basin, exit step, final position and energy must equal the reference's."""
+    g = load_golden("committor_T0.json")
+    runs = g["runs"]
+    spec = spec_from(g["config"], n_walkers=len(runs))
+    o = oracle.OracleSim(spec.to_struct(), seeds=[0] * len(runs))
+    o.set_state(np.array([r["x0"] for r in runs]).T)
+    o.begin()
+    o.run(g["config"]["steps"])
+    basin, exit_step = o.get_commit()
+    assert list(basin) == [r["basin"] for r in runs]
+    assert list(exit_step) == [r["step"] for r in runs]
+    st = o.get_state()
+    assert np.allclose(st["x"].T, np.array([r["x"] for r in runs]), rtol=1e-12)
+    assert np.allclose(st["pe"], [r["pe"] for r in runs], rtol=1e-12)
+    assert np.allclose(st["colv"].T, np.array([r["colv"] for r in runs]), rtol=1e-12)

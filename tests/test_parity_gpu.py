@@ -633,3 +633,40 @@ def test_committor_compaction_is_invisible(monkeypatch):
     assert np.array_equal(b0, b1) and np.array_equal(e0, e1) and a0 == a1
     for k in ("x", "v", "colv", "pe", "T"):
         assert np.array_equal(s0[k], s1[k]), k
+
+
+def test_committor_temperature_zero_minimize():
+    """T = 0 committor on the GPU (steepest-descent inner engine, pe < emin criterion): basin ids and exit
+    steps identical to the reference's runs, positions / energies within the trajectory tolerance; plus a
+    basin-of-attraction map of 2^16 start points against the oracle."""
+    g = load_golden("committor_T0.json")
+    runs = g["runs"]
+    spec = spec_from(g["config"], n_walkers=len(runs), steps_per_launch=500)
+    eng = Engine(spec.to_struct())
+    assert "minimize" in eng.kernel_name
+    eng.set_state(np.array([r["x0"] for r in runs]).T)
+    eng.begin()
+    eng.run(g["config"]["steps"])
+    basin, exit_step = eng.get_commit()
+    assert list(basin) == [r["basin"] for r in runs]
+    assert list(exit_step) == [r["step"] for r in runs]
+    st = eng.get_state()
+    assert scaled_err(st["x"].T, np.array([r["x"] for r in runs])) < TRAJ_TOL
+    assert scaled_err(st["pe"], np.array([r["pe"] for r in runs])) < TRAJ_TOL
+    assert scaled_err(st["colv"].T, np.array([r["colv"] for r in runs])) < TRAJ_TOL
+    # map: many start points, GPU vs oracle
+    M = 4096
+    rng = np.random.RandomState(0)
+    x0 = np.stack([rng.uniform(12, 46, M), rng.uniform(2, 36, M)])
+    spec = spec_from(dict(g["config"], steps=1500), n_walkers=M)
+    eng, orc = Engine(spec.to_struct()), oracle.OracleSim(spec.to_struct(), seeds=np.zeros(M))
+    orc.set_threads(oracle.max_threads())
+    for sim in (eng, orc):
+        sim.set_state(x0)
+        sim.begin()
+        sim.run(1500)
+    bg, sg = eng.get_commit()
+    bo, so = orc.get_commit()
+    assert (bg >= 0).sum() > 100
+    # ulp-level differences can flip a dE >= 0 stop by a step for walkers sitting at a minimum
+    assert (bg != bo).mean() < 0.002 and (np.abs(sg - so) > 1).mean() < 0.01
