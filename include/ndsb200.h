@@ -36,8 +36,8 @@ extern "C" {
 /* compute precision of the kernels ("precision" key, new) */
 enum { NDS_F32 = 0, NDS_F64 = 1 };
 
-/* method: engines/__init__.py:11-31 (md, committor with temperature != 0) */
-enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1 };
+/* method: engines/__init__.py:11-31: md, committor, mc (Metropolis Monte Carlo, engines/mc.py) */
+enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1, NDS_METHOD_MC = 2 };
 
 /* integrate: engines/md.py:59; NDS_INT_MINIMIZE = the fixed-step steepest descent of
  * engines/minimize.py:41-82 (the inner engine of a committor run at temperature 0,
@@ -155,6 +155,12 @@ typedef struct nds_config {
   double emin;                /* committor.py:41, default -1.2: at T = 0 a basin needs pe < emin */
   double min_gtol;            /* minimize.py:12, default 1e-5 */
   int64_t min_maxiter;        /* minimize.py:11,26-27, default steps * 10 */
+
+  /* Metropolis Monte Carlo, engines/mc.py:7-21 */
+  double mc_bounds[NDS_MAX_DIM];        /* proposal half-widths ("mc_bounds") */
+  double mc_global_bounds[NDS_MAX_DIM]; /* periodic box ("global_bounds") */
+  int32_t mc_propose_all;               /* propose_dim: 0 = "single" (one random coordinate), 1 = "all" */
+  int32_t mc_periodic;                  /* bound_cond == "periodic" (mc.py:57-62) */
 } nds_config;
 
 typedef struct nds_engine nds_engine;
@@ -251,6 +257,13 @@ NDS_API int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, 
  * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */
 NDS_API int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);
 NDS_API int64_t nds_count_alive(nds_engine* e);
+
+/* Metropolis MC (engines/mc.py:42-101): accepted moves per walker [M] (MC.accept_rate); a walker's
+ * NDRun.time is accepted * dt because time only advances on acceptance (ndrun.py:235-238).
+ * With NDS_NOISE_EXTERNAL the table of nds_set_noise holds UNIFORMS in [0,1):
+ *   propose "single": [step][3][M] = (coordinate pick, displacement, acceptance);
+ *   propose "all":    [step][ndim + 1][M] = (displacements..., acceptance).                       */
+NDS_API int nds_get_mc(nds_engine* e, int64_t* accepted);
 
 /* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
  * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],

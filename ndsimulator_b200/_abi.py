@@ -13,7 +13,7 @@ NDS_MAX_UMB = 4
 NDS_MAX_BASINS = 8
 
 NDS_F32, NDS_F64 = 0, 1
-NDS_METHOD_MD, NDS_METHOD_COMMITTOR = 0, 1
+NDS_METHOD_MD, NDS_METHOD_COMMITTOR, NDS_METHOD_MC = 0, 1, 2
 NDS_INT_LANGEVIN, NDS_INT_LANGEVIN2, NDS_INT_NVE, NDS_INT_RESCALE, NDS_INT_MINIMIZE = 0, 1, 2, 3, 4
 NDS_NOISE_PHILOX, NDS_NOISE_EXTERNAL = 0, 1
 
@@ -78,6 +78,8 @@ class NdsConfig(C.Structure):
         ("dump_freq", C.c_int64), ("dump_walkers", C.c_int64), ("dump_capacity", C.c_int64),
         ("stat_freq", C.c_int64),
         ("emin", C.c_double), ("min_gtol", C.c_double), ("min_maxiter", C.c_int64),
+        ("mc_bounds", C.c_double * NDS_MAX_DIM), ("mc_global_bounds", C.c_double * NDS_MAX_DIM),
+        ("mc_propose_all", C.c_int32), ("mc_periodic", C.c_int32),
     ]
 
 
@@ -114,6 +116,7 @@ _PROTOTYPES = {
     "nds_set_peer_tables": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
+    "nds_get_mc": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "nds_frame_width": (C.c_int, [C.c_void_p]),
     "nds_frames_pending": (C.c_int64, [C.c_void_p]),
     "nds_drain_frames": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.POINTER(C.c_int64)]),

@@ -94,6 +94,10 @@ class RunSpec:
     n_basins: int = 0
     criteria: Optional[np.ndarray] = None
     diffusion_time: int = 0
+    mc_bounds: Optional[np.ndarray] = None
+    mc_global_bounds: Optional[np.ndarray] = None
+    mc_propose_dim: str = "single"
+    mc_bound_cond: str = "periodic"
     emin: float = -1.2
     min_gtol: float = 1.0e-5
     min_maxiter: Optional[int] = None
@@ -122,7 +126,14 @@ class RunSpec:
                        "f64": _abi.NDS_F64, "fp64": _abi.NDS_F64, "float64": _abi.NDS_F64}[
             str(self.precision).lower()]
         c.ndim = self.ndim
-        c.method = _abi.NDS_METHOD_COMMITTOR if self.method == "committor" else _abi.NDS_METHOD_MD
+        c.method = {"committor": _abi.NDS_METHOD_COMMITTOR, "mc": _abi.NDS_METHOD_MC}.get(
+            self.method, _abi.NDS_METHOD_MD)
+        if self.method == "mc":
+            for d in range(self.ndim):
+                c.mc_bounds[d] = float(self.mc_bounds[d])
+                c.mc_global_bounds[d] = float(self.mc_global_bounds[d])
+            c.mc_propose_all = int(self.mc_propose_dim == "all")
+            c.mc_periodic = int(self.mc_bound_cond == "periodic")
         c.integrator = _abi.INTEGRATORS[self.integrate]
         c.potential = _abi.POTENTIALS[self.potential][0]
         c.colvar = _abi.COLVARS[self.colvar][0]
@@ -208,7 +219,9 @@ def parse(config: dict) -> RunSpec:
         eng_prefix = ["engine_method", "committor", "engine"]
     elif method == "minimize":
         eng_prefix = ["minimize", "engine"]
-    elif method in ("mc", "wl-mc", "read_dump"):
+    elif method == "mc":
+        eng_prefix = ["mc", "engine"]
+    elif method in ("wl-mc", "read_dump"):
         raise NotImplementedError(
             f"method '{method}' is not part of the B200 multi-walker MD path (SURVEY.md section 8f)")
     else:
@@ -225,6 +238,20 @@ def parse(config: dict) -> RunSpec:
     spec.rescale_freq = pick(cfg, "rescale_freq", eng_prefix, None)
     if spec.integrate == "rescale" and spec.rescale_freq is None:
         raise TypeError("integrate: rescale needs rescale_freq (md.py:220)")
+
+    if method == "mc":  # engines/mc.py:7-32
+        spec.mc_bounds = np.array(pick(cfg, "bounds", eng_prefix, [1.0, 1.0]), dtype=float).reshape(-1)
+        spec.mc_global_bounds = np.array(pick(cfg, "global_bounds", eng_prefix, [20.0, 20.0]), dtype=float).reshape(-1)
+        spec.mc_propose_dim = pick(cfg, "propose_dim", eng_prefix, "single")
+        spec.mc_bound_cond = pick(cfg, "bound_cond", eng_prefix, "periodic")
+        if len(spec.mc_bounds) != ndim:
+            raise NameError("wrong input shape of mc_bounds")  # mc.py:31-32
+        if spec.mc_bound_cond == "periodic" and len(spec.mc_global_bounds) != ndim:
+            raise ValueError("global_bounds must have ndim entries (mc.py:60 broadcasts x %= global_bounds)")
+        if spec.mc_propose_dim not in ("single", "all"):
+            raise ValueError("propose_dim must be 'single' or 'all' (mc.py:51-55)")
+        if len(spec.mc_global_bounds) != ndim:
+            spec.mc_global_bounds = np.ones(ndim)
 
     # ---- potential (potentials/_build.py:4-21)
     pot = _builtin_name(cfg.get("potential", "Gaussian"), "potentials", _abi.POTENTIALS, "potential")
@@ -327,6 +354,11 @@ def parse(config: dict) -> RunSpec:
             spec.pe_thred = pick(cfg, "thred", "pe", 0.0)
         else:
             raise UnboundLocalError(f"unknown bias {b}")  # bias/__init__.py:40 would fail on `instance`
+
+    if method == "mc":
+        if "mtd" in biases:
+            raise NotImplementedError("metadynamics under Metropolis MC (per-walker clocks) is not supported")
+        cfg["dump"] = False  # the reference dumps only on accepted moves (ndrun.py:234-251): not recorded
 
     # ---- committor (engines/committor.py:31-75)
     if method == "committor":

@@ -72,6 +72,9 @@ struct Consts {
   unsigned int key0, key1;  // Philox key = seed
   PhiloxKeys rk_step;       // round keys of the per-step noise stream (domain 0)
   PhiloxKeys rk_init;       // round keys of the initial-velocity stream (domain 1)
+  PhiloxKeys rk_mc;         // round keys of the Monte Carlo stream (domain 2)
+  // Metropolis MC (engines/mc.py)
+  R mc_bounds[NDS_MAX_DIM], mc_gb[NDS_MAX_DIM]; int mc_all, mc_periodic;
 };
 
 // Per-launch arguments of the fused step kernel.

@@ -15,6 +15,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "nds_variants.h"
+#include "nds_mc_kernel.cuh"
 
 namespace nds { constexpr int MTD_TILE_HOST = 2048; }  // >= mtd_tile_records<R>() of nds_mtd_kernel.cuh
 
@@ -40,6 +41,7 @@ struct nds_engine {
   virtual int set_hills(int64_t walker, int64_t n, const double* centers, const double* heights) = 0;
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
+  virtual int get_mc(int64_t* accepted) = 0;
   virtual int64_t count_alive() = 0;
   virtual int drain_frames(double* out, int64_t max_frames, int64_t* n_frames) = 0;
   virtual int fes_grid(int64_t walker, double x0, double dx, int64_t nx, double y0, double dy,
@@ -124,7 +126,13 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "unknown integrator %d", c->integrator);
   if (c->integrator == NDS_INT_RESCALE && !(c->rescale_freq > 0))  // md.py:220 (TypeError on None)
     return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
-  if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR) return fail(nullptr, "unknown method %d", c->method);
+  if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR && c->method != NDS_METHOD_MC)
+    return fail(nullptr, "unknown method %d", c->method);
+  if (c->method == NDS_METHOD_MC) {
+    if (c->mtd_enabled) return fail(nullptr, "metadynamics under Metropolis MC is not supported");
+    for (int d = 0; d < c->ndim; d++)
+      if (c->mc_periodic && !(c->mc_global_bounds[d] != 0)) return fail(nullptr, "mc_global_bounds[%d] must be non-zero", d);
+  }
   if (c->n_walkers <= 0) return fail(nullptr, "n_walkers must be positive");
   if (c->n_walkers_global < c->walker_offset + c->n_walkers) return fail(nullptr, "n_walkers_global too small");
   if (!(c->mass > 0) || !(c->dt > 0)) return fail(nullptr, "mass and dt must be positive");
@@ -261,6 +269,9 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.key1 = (unsigned)(c.seed >> 32);
   K.rk_step = philox_round_keys(K.key0, K.key1);
   K.rk_init = philox_round_keys(K.key0, K.key1 ^ 1u);
+  K.rk_mc = philox_round_keys(K.key0, K.key1 ^ 2u);
+  for (int d = 0; d < NDS_MAX_DIM; d++) { K.mc_bounds[d] = (R)c.mc_bounds[d]; K.mc_gb[d] = (R)c.mc_global_bounds[d]; }
+  K.mc_all = c.mc_propose_all; K.mc_periodic = c.mc_periodic;
 }
 
 // -------------------------------------------------------------------------- variant lookup
@@ -385,6 +396,7 @@ struct Engine : nds_engine {
   long long* d_exit = nullptr;
   double* d_frames = nullptr;
   R *d_path_ref = nullptr, *d_path_ind = nullptr;
+  long long* d_mc_accepted = nullptr;
   double* d_noise = nullptr;
   int64_t noise_first = 0, noise_steps = 0;
   double* d_stage = nullptr;  // fp64 staging for host <-> device conversion
@@ -411,7 +423,7 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
                     (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
-                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_ids, (void*)d_flags, (void*)d_scan,
+                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_ids, (void*)d_flags, (void*)d_scan,
                     (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
                     (void*)d_counter})
       if (p) cudaFree(p);
@@ -519,6 +531,11 @@ struct Engine : nds_engine {
       CU(cudaMalloc(&d_cub, cub_bytes));
       iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
     }
+    if (c.method == NDS_METHOD_MC) {
+      CU(cudaMalloc(&d_mc_accepted, sizeof(long long) * sM));
+      CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * sM, stream));
+      kernel_name = sizeof(R) == 4 ? "mc_block<f32>" : "mc_block<f64>";
+    }
     CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     frame_width = 2 + 3 * nd + cd + 6;
     if (dumping) {
@@ -591,7 +608,7 @@ struct Engine : nds_engine {
   int set_noise(const double* noise, int64_t first, int64_t nsteps) override {
     CU(cudaSetDevice(cfg.device));
     if (cfg.noise_mode != NDS_NOISE_EXTERNAL) return fail(this, "nds_set_noise: noise_mode is not NDS_NOISE_EXTERNAL");
-    const int nn = normals_per_step(cfg.integrator, nd);
+    const int nn = cfg.method == NDS_METHOD_MC ? (cfg.mc_propose_all ? nd + 1 : 3) : normals_per_step(cfg.integrator, nd);
     if (d_noise) { CU(cudaFree(d_noise)); d_noise = nullptr; }
     const size_t n = (size_t)nsteps * nn * (size_t)M;
     if (n) {
@@ -644,6 +661,7 @@ struct Engine : nds_engine {
     if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
       return fail(this, "path colvar: call nds_set_path() before nds_begin()");
     step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
+    if (d_mc_accepted) CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * (size_t)M, stream));
     if (cfg.method == NDS_METHOD_COMMITTOR) {
       if (permuted && unpermute_device()) return 1;
       CU(cudaMemsetAsync(d_alive, 1, (size_t)M, stream));
@@ -767,9 +785,40 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  // Metropolis MC: NDRun.run with engine = MC (ndrun.py:230-241, engines/mc.py:42-101)
+  int run_mc(int64_t nsteps) {
+    const int nu = cfg.mc_propose_all ? nd + 1 : 3;
+    if (cfg.noise_mode == NDS_NOISE_EXTERNAL && (!d_noise || step < noise_first || step + nsteps > noise_first + noise_steps))
+      return fail(this, "external uniform table does not cover moves [%lld, %lld)", (long long)step, (long long)(step + nsteps));
+    (void)nu;
+    CU(cudaEventRecord(ev0, stream));
+    int64_t remaining = nsteps;
+    while (remaining > 0) {
+      const int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
+      BlockArgs<R> A = make_args(k);
+      cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, stream);
+      if (err != cudaSuccess) return fail(this, "mc_block launch failed: %s", cudaGetErrorString(err));
+      launches++;
+      step += k;
+      remaining -= k;
+    }
+    CU(cudaEventRecord(ev1, stream));
+    timed = true;
+    return 0;
+  }
+
+  int get_mc(int64_t* accepted) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_MC) return fail(this, "nds_get_mc: method is not mc");
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpy(accepted, d_mc_accepted, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+
   int run(int64_t nsteps) override {  // the NDRun.run loop (ndrun.py:214-251)
     CU(cudaSetDevice(cfg.device));
     if (!begun) return fail(this, "nds_run before nds_begin");
+    if (cfg.method == NDS_METHOD_MC) return run_mc(nsteps);
     if (cfg.noise_mode == NDS_NOISE_EXTERNAL && normals_per_step(cfg.integrator, nd) > 0) {
       if (!d_noise || step < noise_first || step + nsteps > noise_first + noise_steps)
         return fail(this, "external noise table does not cover steps [%lld, %lld)", (long long)step,
@@ -1161,6 +1210,7 @@ int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
 }
 int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e->get_commit(basin, exit_step); }
 int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
+int nds_get_mc(nds_engine* e, int64_t* accepted) { return e->get_mc(accepted); }
 int nds_frame_width(const nds_engine* e) { return e->frame_width; }
 int64_t nds_frames_pending(const nds_engine* e) { return e->frames_written; }
 int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n) { return e->drain_frames(out, max_frames, n); }

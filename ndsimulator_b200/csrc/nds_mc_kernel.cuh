@@ -1,0 +1,116 @@
+// nds_mc_kernel.cuh -- batched Metropolis Monte Carlo (reference engines/mc.py:42-101, "next" row 4 of
+// SURVEY.md section 8f): one thread per walker, K trial moves per launch, energies only.
+//
+// Per move: propose (one random coordinate or all of them, uniform in +-mc_bounds), wrap into the
+// periodic box like numpy's %, evaluate potential + bias energy at the trial point, accept with
+// min(1, exp(-dE/kBT)).  Uniforms come from Philox4x32-10 (domain 2: key1 ^ 2, counter = move index,
+// global walker id) or from a caller-supplied table (parity tests).  The reference draws its proposals
+// from the unseeded global numpy RNG, so only statistical parity exists for this engine.
+#pragma once
+#include "nds_kernels.cuh"
+
+namespace nds {
+
+NDS_DEV double u01(uint32_t w, double) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
+NDS_DEV float u01(uint32_t w, float) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+
+template <typename R, int ND>
+__global__ void __launch_bounds__(NDS_BLOCK)
+mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<R> A, long long* accepted) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long M = A.M;
+  if (w >= M) return;
+  const int cd = K.cd, bias_mask = K.bias_mask;
+  const bool ext = K.noise == NDS_NOISE_EXTERNAL;
+  const int nu = K.mc_all ? ND + 1 : 3;
+  const unsigned long long gid = (unsigned long long)(A.walker_offset + w);
+
+  R x[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) x[d] = A.x[d * M + w];
+  WalkerBias<R, ND> wb;
+#pragma unroll
+  for (int k = 0; k < ND; k++) { wb.k[k] = (R)0; wb.r0[k] = (R)0; }
+  if (bias_mask & BIAS_UMB_WALKER) {
+#pragma unroll
+    for (int k = 0; k < ND; k++)
+      if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
+  }
+  // MC.begin (mc.py:34-40): energies at the current point
+  Eval<R, ND> cur;
+  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, A.hills, A.n_hills, 1, cur);
+  long long acc = accepted[w];
+  const long long acc0 = acc;
+
+  for (long long s = A.step0; s < A.step0 + A.nsteps; s++) {
+    R u[ND + 1];
+    if (ext) {
+      const double* row = A.noise + ((s - A.noise_first) * nu) * M + w;
+      for (int j = 0; j < nu; j++) u[j] = (R)row[(long long)j * M];
+    } else {
+      const u32x4 r0 = philox4x32_10(u32x4{(uint32_t)(2 * s), (uint32_t)((2 * s) >> 32), (uint32_t)gid, (uint32_t)(gid >> 32)}, K.rk_mc);
+      u[0] = u01(r0.x, (R)0); u[1] = u01(r0.y, (R)0); u[2] = u01(r0.z, (R)0);
+      if (ND + 1 > 3) {
+        if (K.mc_all) {
+          const u32x4 r1 = philox4x32_10(u32x4{(uint32_t)(2 * s + 1), (uint32_t)((2 * s + 1) >> 32), (uint32_t)gid, (uint32_t)(gid >> 32)}, K.rk_mc);
+          const uint32_t words[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < ND + 1; j++) u[j] = u01(words[j], (R)0);
+        }
+      }
+    }
+    // propose, mc.py:47-62
+    R xn[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) xn[d] = x[d];
+    int k = 0;
+    if (!K.mc_all) {
+      int dim = (int)floor((double)u[k++] * ND);
+      if (dim >= ND) dim = ND - 1;
+      const R du = (R)2.0 * u[k++] - (R)1.0;
+#pragma unroll
+      for (int d = 0; d < ND; d++)
+        if (d == dim) xn[d] += du * K.mc_bounds[d];
+    } else {
+#pragma unroll
+      for (int d = 0; d < ND; d++) xn[d] += ((R)2.0 * u[k++] - (R)1.0) * K.mc_bounds[d];
+    }
+    if (K.mc_periodic) {  // numpy %: the result takes the sign of the divisor
+#pragma unroll
+      for (int d = 0; d < ND; d++) {
+        R r = fmod(xn[d], K.mc_gb[d]);
+        if (r != (R)0 && ((r < (R)0) != (K.mc_gb[d] < (R)0))) r += K.mc_gb[d];
+        xn[d] = r;
+      }
+    }
+    Eval<R, ND> tr;
+    eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, A.hills, A.n_hills, 1, tr);
+    const R pe = cur.pe + cur.be, pe_new = tr.pe + tr.be;  // mc.py:64-76
+    const R pb = (pe_new > pe) ? nds_exp(-(pe_new - pe) / K.kBT) : (R)1.0;
+    if (u[k] <= pb) {  // mc.py:83-96
+#pragma unroll
+      for (int d = 0; d < ND; d++) x[d] = xn[d];
+      cur = tr;
+      acc += 1;
+    }
+  }
+
+#pragma unroll
+  for (int d = 0; d < ND; d++) A.x[d * M + w] = x[d];
+#pragma unroll
+  for (int q = 0; q < ND; q++)
+    if (q < cd) A.colv[q * M + w] = cur.cv.c[q];
+  A.thermo[1 * M + w] = cur.pe;
+  A.thermo[3 * M + w] = cur.be;
+  if (acc > 0) {  // mc.py:93-94 on the first accepted move: ke = 0, totale = pe
+    A.thermo[2 * M + w] = (R)0;
+    A.thermo[4 * M + w] = cur.pe;
+  }
+  if (acc != acc0) accepted[w] = acc;
+}
+
+template <typename R>
+cudaError_t launch_mc_block(int nd, const Consts<R>& K, const BlockArgs<R>& A, long long* accepted,
+                            cudaStream_t st);
+
+}  // namespace nds

@@ -182,6 +182,12 @@ class Engine:
                                             exit_step.ctypes.data_as(C.POINTER(C.c_int64))))
         return basin, exit_step
 
+    def get_mc(self):
+        """accepted moves per walker (MC.accept_rate, engines/mc.py:85)."""
+        acc = np.empty(self.M, dtype=np.int64)
+        self._check(self.lib.nds_get_mc(self.h, acc.ctypes.data_as(C.POINTER(C.c_int64))))
+        return acc
+
     def count_alive(self):
         return int(self.lib.nds_count_alive(self.h))
 

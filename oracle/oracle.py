@@ -59,6 +59,7 @@ def lib():
         L.oracle_get_state.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]
         L.oracle_get_commit.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.oracle_get_vr.argtypes = [C.c_void_p, _dp]
+        L.oracle_get_mc.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.oracle_n_hills.argtypes = [C.c_void_p, C.c_int64]
         L.oracle_n_hills.restype = C.c_int64
         L.oracle_get_hills.argtypes = [C.c_void_p, C.c_int64, _dp, _dp]
@@ -179,6 +180,11 @@ class OracleSim:
         self.L.oracle_get_commit(self.h, basin.ctypes.data_as(C.POINTER(C.c_int32)),
                                  exit_step.ctypes.data_as(C.POINTER(C.c_int64)))
         return basin, exit_step
+
+    def get_mc(self):
+        acc = np.zeros(self.M, dtype=np.int64)
+        self.L.oracle_get_mc(self.h, acc.ctypes.data_as(C.POINTER(C.c_int64)))
+        return acc
 
     def get_vr(self):
         vr = np.zeros(self.M)

@@ -82,9 +82,10 @@ def test_reference_errors():
 
 
 def test_out_of_scope_is_refused_loudly():
-    for method in ("mc", "wl-mc", "read_dump"):
+    for method in ("wl-mc", "read_dump"):
         with pytest.raises(NotImplementedError):
             config.parse(base(method=method))
+    assert config.parse(base(method="mc", mc_bounds=[1, 1])).method == "mc"
     # temperature 0 selects the Minimize inner engine (engines/__init__.py:22-23)
     s = config.parse(base(method="committor", temperature=0, n_basins=1, criteria=[[[0, 1], [0, 1]]]))
     assert s.integrate == "minimize" and s.emin == -1.2 and s.to_struct().min_maxiter == 1000

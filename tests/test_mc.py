@@ -1,0 +1,119 @@
+"""Metropolis Monte Carlo (reference engines/mc.py, "next" row of SURVEY.md section 8f).
+
+The reference proposes moves with the unseeded GLOBAL numpy RNG, so its runs are not
+reproducible: parity is (i) deterministic against the oracle when the uniforms are supplied by the caller,
+(ii) statistical (Boltzmann distribution, acceptance ratio) otherwise."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from ndsimulator_b200 import _abi, config
+from oracle import oracle
+from tests.helpers import spec_from, scaled_err
+
+kB = 8.6173303e-5
+DW = dict(ndim=1, potential="DoubleWell1d", x0=30.0, method="mc", mc_bounds=[2.0], mc_global_bounds=[40.0],
+          mass=1.0, temperature=3000, seed=0)
+M2 = dict(ndim=2, potential="Mueller2d", x0=[22.0, 24.0], method="mc", mc_bounds=[1.5, 1.5],
+          mc_global_bounds=[48.0, 40.0], mass=1.0, temperature=600, seed=0)
+
+
+def test_config_mc():
+    s = config.parse(dict(M2, propose_dim="all", bound_cond="no_bound"))
+    st = s.to_struct()
+    assert st.method == _abi.NDS_METHOD_MC and st.mc_propose_all == 1 and st.mc_periodic == 0
+    assert not s.dump
+    with pytest.raises(NameError):
+        config.parse(dict(M2, mc_bounds=[1.0]))  # mc.py:31-32
+    with pytest.raises(NotImplementedError):
+        config.parse(dict(M2, biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0))
+
+
+def test_oracle_mc_samples_boltzmann():
+    M, n = 3000, 3000
+    spec = spec_from(DW, n_walkers=M)
+    o = oracle.OracleSim(spec.to_struct(), seeds=np.arange(M))
+    o.set_threads(oracle.max_threads())
+    o.set_state(np.full((1, M), 30.0))
+    o.begin()
+    o.run(n)
+    x = o.get_state()["x"][0]
+    g = np.linspace(0, 40, 4001)[:-1]
+    V = -0.5 * (np.exp(-(g - 10) ** 2 / 100) + np.exp(-(g - 30) ** 2 / 100))
+    p = np.exp(-V / (kB * 3000))
+    cdf = np.cumsum(p) / p.sum()
+    assert stats.kstest(x, lambda t: np.interp(t, g + 0.005, cdf)).pvalue > 1e-3
+    assert np.all((x >= 0) & (x < 40))  # periodic wrap like numpy %
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["single_2d", "all_2d_umb", "single_5d"])
+def test_gpu_mc_external_uniforms_match_oracle(case):
+    """With caller-supplied uniforms every accept / reject decision is deterministic: positions, energies
+    and acceptance counts of M walkers must equal the oracle's."""
+    from ndsimulator_b200.engine import Engine
+    M, n = 64, 600
+    if case == "single_2d":
+        cfg, nu = dict(M2), 3
+    elif case == "all_2d_umb":
+        cfg, nu = dict(M2, propose_dim="all", biases=["umb"], umb_k=0.05, umb_r0=[25, 20]), 3
+    else:
+        cfg, nu = dict(ndim=5, potential="Mueller5d", colvar_name="Proj5dto2d", true_colvar_name="Proj5dto2d",
+                       x0=[12.0] * 5, method="mc", mc_bounds=[2.0] * 5, mc_global_bounds=[40.0] * 5, mass=1.0,
+                       temperature=300, seed=0), 3
+    spec = spec_from(cfg, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=250)
+    st = spec.to_struct()
+    eng, orc = Engine(st), oracle.OracleSim(st, seeds=np.arange(M))
+    assert eng.kernel_name.startswith("mc_block")
+    u = np.random.RandomState(7).uniform(size=(n, nu, M))
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    for sim in (eng, orc):
+        sim.set_state(x0)
+        sim.set_noise(u)
+        sim.begin()
+        sim.run(n)
+    a, b = eng.get_state(), orc.get_state()
+    assert np.array_equal(eng.get_mc(), orc.get_mc())
+    assert 0.2 < eng.get_mc().mean() / n < 1.0
+    for k in ("x", "colv", "pe", "biase"):
+        assert scaled_err(a[k], b[k]) < 1e-10, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_gpu_mc_boltzmann_statistics(precision):
+    """Philox-driven MC: stationary distribution = Boltzmann (KS against the exact 1-D density), and the
+    acceptance ratio agrees with an oracle ensemble within 5 standard errors."""
+    from ndsimulator_b200.engine import Engine
+    M, n = 1 << 15, 3000
+    spec = spec_from(DW, n_walkers=M, precision=precision)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.full((1, M), 30.0))
+    eng.begin()
+    eng.run(n)
+    x = eng.get_state()["x"][0]
+    g = np.linspace(0, 40, 4001)[:-1]
+    V = -0.5 * (np.exp(-(g - 10) ** 2 / 100) + np.exp(-(g - 30) ** 2 / 100))
+    p = np.exp(-V / (kB * 3000))
+    cdf = np.cumsum(p) / p.sum()
+    assert stats.kstest(x, lambda t: np.interp(t, g + 0.005, cdf)).pvalue > 1e-3
+    Mo = 1024
+    orc = oracle.OracleSim(spec_from(DW, n_walkers=Mo).to_struct(), seeds=np.arange(Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(np.full((1, Mo), 30.0))
+    orc.begin()
+    orc.run(n)
+    ra, rb = eng.get_mc() / n, orc.get_mc() / n
+    assert abs(ra.mean() - rb.mean()) < 5 * np.sqrt(ra.var() / M + rb.var() / Mo)
+
+
+@pytest.mark.gpu
+def test_ndrun_mc_frontend(tmp_path):
+    from ndsimulator_b200 import NDRun
+    sim = NDRun(**dict(M2, steps=500, n_walkers=256, root=str(tmp_path), run_name="mc", screen=False))
+    sim.begin()
+    sim.run()
+    sim.end()
+    assert sim.accepted.shape == (256,) and 0 < sim.accept_rate <= 500
+    assert sim.time == sim.accept_rate * 0.5  # dt default 0.5, advanced on accepted moves only
+    assert "!! MC acceptance ratio" not in open(str(tmp_path / "mc" / "log")).read()  # screen: false
