@@ -25,7 +25,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c3": 128.0, "c4": 289.0}  # SURVEY.md section 8d (algorithmic, fixed)
+FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c3": 128.0, "c4": 289.0}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` captures (profiles/r01_*_raw.csv) at the default walker counts
+NCU_DRAM_BYTES_PER_LAUNCH = {"c2": 22.05e6, "c4": 7.37e6, "c5": 1.59e6}  # SURVEY.md section 8d (algorithmic, fixed)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -409,7 +412,8 @@ def main():
             ach = per_gpu * FLOPS_PER_WALKER_STEP[name] / 1e12
             out["roofline"] = {
                 "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak_tflops, "traffic": None,
+                "frac": ach / fp32_peak_tflops,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name) if (args.walkers == 0 and args.precision == "f32") else None,
                 "note": f"algorithmic {FLOPS_PER_WALKER_STEP[name]:.0f} flop/walker-step (SURVEY 8d) x "
                         f"walker-steps/s per GPU; peak = {sm_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
                         "(nvidia-smi clocks.max.sm); MEASURED_PEAKS.json holds no FP32 figure. HBM traffic is "
@@ -419,7 +423,8 @@ def main():
             mufu_peak = sm_count * 16 * sm_max_mhz * 1e6
             out["roofline"] = {
                 "bound": "mufu_ex2", "achieved": he / 1e12, "peak": mufu_peak / 1e12 * world,
-                "unit": "T hill-evals/s", "frac": he / (mufu_peak * world), "traffic": None,
+                "unit": "T hill-evals/s", "frac": he / (mufu_peak * world),
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name) if args.walkers == 0 else None,
                 "note": "one MUFU.EX2 per walker-hill pair; peak = SMs x 16 lanes x clocks.max.sm"}
             out["hill_evals_per_s"] = he
         if c3_info:

@@ -30,6 +30,11 @@ const Variant* variants_hot(int* n) {
           "md_block<f32,nd5,Mueller5d,Proj5dto2d,2nd-langevin,umb>"),
       // (a packed f2 instantiation of C4 was measured 7 % SLOWER than the scalar one: 117 registers,
       //  half the occupancy, and the step is dominated by Philox + Box-Muller, which do not pack)
+      // the remaining shipped examples: examples/2d-umb.yaml and examples/1d-md.yaml
+      make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN2, BIAS_UMB, MD, PHX, OFF>>(
+          "md_block<f32,nd2,Mueller2d,Original,2nd-langevin,umb>"),
+      make_variant<Spec<float, 1, NDS_POT_DOUBLEWELL1D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, OFF>>(
+          "md_block<f32,nd1,DoubleWell1d,Original,langevin,nobias>"),
       // C5 / 2d-mtd: metadynamics
       make_variant<Spec<float, 5, NDS_POT_MUELLER5D, P52, P52, NDS_INT_LANGEVIN, BIAS_MTD, MD, PHX, OFF>>(
           "md_block<f32,nd5,Mueller5d,Proj5dto2d,langevin,mtd>"),
