@@ -20,6 +20,9 @@ const Variant* variants_hot(int* n) {
       // C2 with Blackwell packed FP32 (FFMA2): two walkers per thread, same physics templates
       make_variant<Spec<f2, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, OFF>>(
           "md_block<f32x2,nd2,Mueller2d,Original,langevin,nobias>"),
+      // C2 physics with device-side frames (dump rows of io/dump.py) for the dump-bandwidth measurement
+      make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, 1>>(
+          "md_block<f32,nd2,Mueller2d,Original,langevin,nobias,frames>"),
       // C3: committor shooting on the same surface
       make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, CM, PHX, OFF>>(
           "md_block<f32,nd2,Mueller2d,Original,langevin,committor>"),
