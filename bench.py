@@ -324,28 +324,32 @@ def main():
     e2e = None
     if not args.no_e2e:
         nd = spec.ndim
-        # two pinned buffer sets, ping-pong: the state read back from step n is the input of step n+1
-        bufs = [dict(x=torch.empty((nd, M), dtype=torch.float64).pin_memory(),
-                     v=torch.empty((nd, M), dtype=torch.float64).pin_memory()) for _ in range(2)]
-        oth = torch.empty((5, M), dtype=torch.float64).pin_memory()
+        # two pinned buffer sets, ping-pong: the state read back from step n is the input of step n+1.
+        # Host buffers are in the engine's precision (nds_set_state_f32 / nds_get_state_f32 for fp32).
+        import ctypes as C
+        f32 = args.precision == "f32"
+        tdt, cty, esz = (torch.float32, C.c_float, 4) if f32 else (torch.float64, C.c_double, 8)
+        bufs = [dict(x=torch.empty((nd, M), dtype=tdt).pin_memory(),
+                     v=torch.empty((nd, M), dtype=tdt).pin_memory()) for _ in range(2)]
+        oth = torch.empty((5, M), dtype=tdt).pin_memory()
         st = eng.get_state(fields=("x", "v"))
         bufs[0]["x"].numpy()[:] = st["x"]
         bufs[0]["v"].numpy()[:] = st["v"]
-        import ctypes as C
-        dp = C.POINTER(C.c_double)
+        cp = C.POINTER(cty)
+        set_fn = eng.lib.nds_set_state_f32 if f32 else eng.lib.nds_set_state
+        get_fn = eng.lib.nds_get_state_f32 if f32 else eng.lib.nds_get_state
 
         def ptr(tens):
-            return C.cast(tens.data_ptr(), dp)
+            return C.cast(tens.data_ptr(), cp)
 
         flip = [0]
 
         def e2e_step():
             src, dst = bufs[flip[0]], bufs[1 - flip[0]]
             # positions AND velocities are supplied, so the run continues (no re-draw, no re-begin)
-            eng._check(eng.lib.nds_set_state(eng.h, ptr(src["x"]), ptr(src["v"])))            # H2D
+            eng._check(set_fn(eng.h, ptr(src["x"]), ptr(src["v"])))                           # H2D
             eng._check(eng.lib.nds_run(eng.h, md_steps))
-            eng._check(eng.lib.nds_get_state(eng.h, ptr(dst["x"]), ptr(dst["v"]), None, None, None,
-                                             ptr(oth)))                                        # D2H
+            eng._check(get_fn(eng.h, ptr(dst["x"]), ptr(dst["v"]), None, None, None, ptr(oth)))  # D2H
             flip[0] = 1 - flip[0]
 
         e2e_n = max(3, min(args.steps, 20))
@@ -362,7 +366,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
         e2e = {"value": world * M * md_steps * e2e_n / e2e_s, "unit": "walker-steps/s",
-               "h2d_bytes_per_step": 2 * nd * M * 8, "d2h_bytes_per_step": (2 * nd + 5) * M * 8,
+               "h2d_bytes_per_step": 2 * nd * M * esz, "d2h_bytes_per_step": (2 * nd + 5) * M * esz,
                "steps": e2e_n}
 
     clocks = sampler.stop() if sampler else None

@@ -215,6 +215,11 @@ NDS_API int nds_sync(nds_engine* e);
  * thermo: [5][M] = T, pe, ke, biase, totale (data.py:77-81, md.py:226-229).                     */
 NDS_API int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv,
                   double* thermo);
+/* single-precision host buffers (same layouts): for fp32 engines the copies go straight between the
+ * caller's buffers and the SoA state, half the PCIe bytes of the fp64 calls and no conversion pass. */
+NDS_API int nds_set_state_f32(nds_engine* e, const float* x, const float* v);
+NDS_API int nds_get_state_f32(nds_engine* e, float* x, float* v, float* f, float* fixf, float* colv,
+                              float* thermo);
 NDS_API int64_t nds_step(const nds_engine* e);   /* NDRun.step  */
 NDS_API double nds_time(const nds_engine* e);    /* NDRun.time (accumulated in fp64 like ndrun.py:240) */
 

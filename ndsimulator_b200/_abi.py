@@ -104,6 +104,8 @@ _PROTOTYPES = {
     "nds_run": (C.c_int, [C.c_void_p, C.c_int64]),
     "nds_sync": (C.c_int, [C.c_void_p]),
     "nds_get_state": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "nds_set_state_f32": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "nds_get_state_f32": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_float)] * 6),
     "nds_step": (C.c_int64, [C.c_void_p]),
     "nds_time": (C.c_double, [C.c_void_p]),
     "nds_eval_at": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),

@@ -35,6 +35,8 @@ struct nds_engine {
   virtual int run(int64_t nsteps) = 0;
   virtual int sync() = 0;
   virtual int get_state(double* x, double* v, double* f, double* fixf, double* colv, double* thermo) = 0;
+  virtual int set_state_f32(const float* x, const float* v) = 0;
+  virtual int get_state_f32(float* x, float* v, float* f, float* fixf, float* colv, float* thermo) = 0;
   virtual int eval_at(const double* x, int64_t n, double* V, double* F, double* colv, double* J,
                       double* Vb, double* Fb) = 0;
   virtual int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) = 0;
@@ -595,6 +597,61 @@ struct Engine : nds_engine {
     // launch re-evaluates forces at entry); positions only: velocities are re-drawn by nds_begin()
     if (!v) { have_v = false; begun = false; }
     else have_v = true;
+    return 0;
+  }
+
+  // fp32 host buffers: direct copies for fp32 engines, through the staging buffer otherwise
+  int upload_f32(const float* h, R* d, int64_t n) {
+    if (sizeof(R) == sizeof(float)) {
+      CU(cudaMemcpyAsync(d, h, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    } else {
+      if (ensure_stage(n)) return 1;
+      float* st = reinterpret_cast<float*>(d_stage);
+      CU(cudaMemcpyAsync(st, h, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, stream));
+      cast_kernel<float, R><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, st, d);
+      CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int download_f32(const R* d, float* h, int64_t n) {
+    if (sizeof(R) == sizeof(float)) {
+      CU(cudaMemcpyAsync(h, d, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    } else {
+      if (ensure_stage(n)) return 1;
+      float* st = reinterpret_cast<float*>(d_stage);
+      cast_kernel<R, float><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, d, st);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(h, st, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  int set_state_f32(const float* x, const float* v) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!x) return fail(this, "nds_set_state_f32: x is null");
+    if (permuted) {
+      iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
+      permuted = false;
+      n_active = M;
+      CU(cudaMemsetAsync(d_alive, 1, (size_t)M, stream));
+    }
+    if (upload_f32(x, d_x, (int64_t)nd * M)) return 1;
+    if (v) { if (upload_f32(v, d_v, (int64_t)nd * M)) return 1; }
+    if (!v) { have_v = false; begun = false; }
+    else have_v = true;
+    return 0;
+  }
+
+  int get_state_f32(float* x, float* v, float* f, float* fixf, float* colv, float* thermo) override {
+    CU(cudaSetDevice(cfg.device));
+    if (x && (download_f32(d_x, x, (int64_t)nd * M) || unpermute_host(x, nd))) return 1;
+    if (v && (download_f32(d_v, v, (int64_t)nd * M) || unpermute_host(v, nd))) return 1;
+    if (f && (download_f32(d_f, f, (int64_t)nd * M) || unpermute_host(f, nd))) return 1;
+    if (fixf && (download_f32(d_fixf, fixf, (int64_t)nd * M) || unpermute_host(fixf, nd))) return 1;
+    if (colv && (download_f32(d_colv, colv, (int64_t)cd * M) || unpermute_host(colv, cd))) return 1;
+    if (thermo && (download_f32(d_thermo, thermo, (int64_t)5 * M) || unpermute_host(thermo, 5))) return 1;
     return 0;
   }
 
@@ -1190,6 +1247,10 @@ int nds_run(nds_engine* e, int64_t n) { return e->run(n); }
 int nds_sync(nds_engine* e) { return e->sync(); }
 int nds_get_state(nds_engine* e, double* x, double* v, double* f, double* fixf, double* colv, double* thermo) {
   return e->get_state(x, v, f, fixf, colv, thermo);
+}
+int nds_set_state_f32(nds_engine* e, const float* x, const float* v) { return e->set_state_f32(x, v); }
+int nds_get_state_f32(nds_engine* e, float* x, float* v, float* f, float* fixf, float* colv, float* thermo) {
+  return e->get_state_f32(x, v, f, fixf, colv, thermo);
 }
 int64_t nds_step(const nds_engine* e) { return e->step; }
 double nds_time(const nds_engine* e) { return e->time; }

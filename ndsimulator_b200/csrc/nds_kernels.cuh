@@ -546,6 +546,11 @@ __global__ void fill_hills_kernel(long long n_records, int rs, int cd, R* hills)
   for (int k = 0; k < rs; k++) hills[i * rs + k] = (k > cd) ? (R)(-INFINITY) : (R)0;
 }
 
+template <typename A, typename B>
+__global__ void cast_kernel(long long n, const A* __restrict__ in, B* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (B)in[i];
+}
 template <typename T>
 __global__ void convert_kernel(long long n, const double* __restrict__ in, T* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

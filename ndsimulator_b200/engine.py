@@ -58,6 +58,27 @@ class Engine:
         v = None if v is None else _f64(v, (self.ndim, self.M))
         self._check(self.lib.nds_set_state(self.h, _p(x), _p(v)))
 
+    def set_state_f32(self, x, v=None):
+        """Same as :meth:`set_state` with float32 host arrays (direct copies for fp32 engines)."""
+        fp = C.POINTER(C.c_float)
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.ndim, self.M)
+        v = None if v is None else np.ascontiguousarray(v, dtype=np.float32).reshape(self.ndim, self.M)
+        self._check(self.lib.nds_set_state_f32(self.h, x.ctypes.data_as(fp),
+                                               None if v is None else v.ctypes.data_as(fp)))
+
+    def get_state_f32(self, fields=("x", "v", "thermo")):
+        fp = C.POINTER(C.c_float)
+        M, nd, cd = self.M, self.ndim, self.cd
+        shapes = dict(x=(nd, M), v=(nd, M), f=(nd, M), fixf=(nd, M), colv=(cd, M), thermo=(5, M))
+        bufs = {k: np.empty(shapes[k], dtype=np.float32) for k in fields}
+        args = [(bufs[k].ctypes.data_as(fp) if k in bufs else None) for k in ("x", "v", "f", "fixf", "colv", "thermo")]
+        self._check(self.lib.nds_get_state_f32(self.h, *args))
+        out = {k: bufs[k] for k in fields if k != "thermo"}
+        if "thermo" in bufs:
+            t = bufs["thermo"]
+            out.update(T=t[0], pe=t[1], ke=t[2], biase=t[3], totale=t[4])
+        return out
+
     def set_walker_bias(self, k, r0):
         k = _f64(k, (self.cd, self.M))
         r0 = _f64(r0, (self.cd, self.M))

@@ -670,3 +670,23 @@ def test_committor_temperature_zero_minimize():
     assert (bg >= 0).sum() > 100
     # ulp-level differences can flip a dE >= 0 stop by a step for walkers sitting at a minimum
     assert (bg != bo).mean() < 0.002 and (np.abs(sg - so) > 1).mean() < 0.01
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_f32_host_buffers_roundtrip(precision):
+    """nds_set_state_f32 / nds_get_state_f32 move the same state as the fp64 calls (to fp32 rounding)."""
+    M = 1000
+    spec = spec_from(dict(MD2D, integrate="nve"), n_walkers=M, precision=precision)
+    eng = Engine(spec.to_struct())
+    rng = np.random.RandomState(0)
+    x0 = np.stack([rng.uniform(15, 30, M), rng.uniform(10, 35, M)]).astype(np.float32)
+    v0 = rng.normal(scale=0.01, size=(2, M)).astype(np.float32)
+    eng.set_state_f32(x0, v0)
+    eng.begin()
+    a32 = eng.get_state_f32(fields=("x", "v", "colv", "thermo"))
+    a64 = eng.get_state()
+    assert np.array_equal(a32["x"], x0) and np.array_equal(a32["v"], v0)
+    assert np.allclose(a32["pe"], a64["pe"], rtol=1e-6) and np.allclose(a32["colv"], a64["colv"], rtol=1e-6)
+    eng.run(10)
+    b32, b64 = eng.get_state_f32(), eng.get_state()
+    assert np.allclose(b32["x"], b64["x"], rtol=1e-6) and np.allclose(b32["T"], b64["T"], rtol=1e-5)
