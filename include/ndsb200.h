@@ -223,6 +223,19 @@ NDS_API int nds_get_state_f32(nds_engine* e, float* x, float* v, float* f, float
 NDS_API int64_t nds_step(const nds_engine* e);   /* NDRun.step  */
 NDS_API double nds_time(const nds_engine* e);    /* NDRun.time (accumulated in fp64 like ndrun.py:240) */
 
+/* checkpoint / resume.  Philox noise is indexed by (global walker id, global step), so a run is fully
+ * described by x, v (nds_get_state), the hill table + VR (nds_get_hills, nds_get_vr) and this clock.
+ * nds_set_clock restores NDRun.step / NDRun.time (ndrun.py:199-200,232,240), the number of depositions
+ * done (Gaussian._dep_count, gaus.py:107) and MD.rescale_count (md.py:77) on a begun engine.          */
+NDS_API int nds_get_clock(const nds_engine* e, int64_t* step, double* time, int64_t* dep_count,
+                          int64_t* rescale_count);
+NDS_API int nds_set_clock(nds_engine* e, int64_t step, double time, int64_t dep_count,
+                          int64_t rescale_count);
+NDS_API int nds_set_vr(nds_engine* e, const double* vr);
+
+/* walkers whose position or velocity is not finite (the reference only logs T > 10000, ndrun.py:253) */
+NDS_API int64_t nds_count_nonfinite(nds_engine* e);
+
 /* deterministic parity entry: replaces potential.compute(x) (potentials/potential.py:14),
  * colvar.compute / jacobian (colvars/colvar.py:16-20) and the sum of fix.compute(x0, col0)
  * (md.py:182-188) at n given configurations x[ndim][n], using the engine's current hill table

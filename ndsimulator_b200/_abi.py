@@ -119,6 +119,11 @@ _PROTOTYPES = {
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
     "nds_get_mc": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "nds_get_clock": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nds_set_clock": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_int64]),
+    "nds_set_vr": (C.c_int, [C.c_void_p, _dp]),
+    "nds_count_nonfinite": (C.c_int64, [C.c_void_p]),
     "nds_frame_width": (C.c_int, [C.c_void_p]),
     "nds_frames_pending": (C.c_int64, [C.c_void_p]),
     "nds_drain_frames": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.POINTER(C.c_int64)]),

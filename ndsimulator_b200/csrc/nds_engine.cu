@@ -44,6 +44,10 @@ struct nds_engine {
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
   virtual int get_mc(int64_t* accepted) = 0;
+  virtual int get_clock(int64_t* step, double* time, int64_t* dep, int64_t* resc) const = 0;
+  virtual int set_clock(int64_t step, double time, int64_t dep, int64_t resc) = 0;
+  virtual int set_vr(const double* vr) = 0;
+  virtual int64_t count_nonfinite() = 0;
   virtual int64_t count_alive() = 0;
   virtual int drain_frames(double* out, int64_t max_frames, int64_t* n_frames) = 0;
   virtual int fes_grid(int64_t walker, double x0, double dx, int64_t nx, double y0, double dy,
@@ -370,6 +374,18 @@ static __global__ void alive_flags_kernel(long long n, const unsigned char* aliv
   if (i < n) flags[i] = alive[i] ? 1 : 0;
 }
 
+
+template <typename R>
+static __global__ void count_nonfinite_kernel(long long M, int nd, const R* x, const R* v, unsigned long long* out) {
+  unsigned long long local = 0;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < M; w += (long long)gridDim.x * blockDim.x) {
+    bool bad = false;
+    for (int d = 0; d < nd; d++) bad |= !isfinite((double)x[d * M + w]) || !isfinite((double)v[d * M + w]);
+    local += bad ? 1ull : 0ull;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
 
 static __global__ void count_alive_kernel(long long M, const unsigned char* alive, unsigned long long* out) {
   unsigned long long local = 0;
@@ -864,6 +880,34 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  int get_clock(int64_t* s, double* t, int64_t* dep, int64_t* resc) const override {
+    if (s) *s = step;
+    if (t) *t = time;
+    if (dep) *dep = dep_count;
+    if (resc) *resc = rescale_count;
+    return 0;
+  }
+  int set_clock(int64_t s, double t, int64_t dep, int64_t resc) override {
+    if (!begun) return fail(this, "nds_set_clock before nds_begin");
+    step = s; time = t; dep_count = dep; rescale_count = resc;
+    need_refresh_vr = false;  // VR comes from the checkpoint (nds_set_vr), not from this launch entry
+    return 0;
+  }
+  int set_vr(const double* vr) override {
+    CU(cudaSetDevice(cfg.device));
+    return upload(vr, d_vr, M);
+  }
+  int64_t count_nonfinite() override {
+    cudaSetDevice(cfg.device);
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+    count_nonfinite_kernel<R><<<296, 256, 0, stream>>>(M, nd, d_x, d_v, d_counter);
+    launches++;
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, d_counter, sizeof h, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    return (int64_t)h;
+  }
+
   int get_mc(int64_t* accepted) override {
     CU(cudaSetDevice(cfg.device));
     if (cfg.method != NDS_METHOD_MC) return fail(this, "nds_get_mc: method is not mc");
@@ -1272,6 +1316,14 @@ int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
 int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e->get_commit(basin, exit_step); }
 int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
 int nds_get_mc(nds_engine* e, int64_t* accepted) { return e->get_mc(accepted); }
+int nds_get_clock(const nds_engine* e, int64_t* step, double* time, int64_t* dep, int64_t* resc) {
+  return e->get_clock(step, time, dep, resc);
+}
+int nds_set_clock(nds_engine* e, int64_t step, double time, int64_t dep, int64_t resc) {
+  return e->set_clock(step, time, dep, resc);
+}
+int nds_set_vr(nds_engine* e, const double* vr) { return e->set_vr(vr); }
+int64_t nds_count_nonfinite(nds_engine* e) { return e->count_nonfinite(); }
 int nds_frame_width(const nds_engine* e) { return e->frame_width; }
 int64_t nds_frames_pending(const nds_engine* e) { return e->frames_written; }
 int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int64_t* n) { return e->drain_frames(out, max_frames, n); }

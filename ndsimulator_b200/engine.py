@@ -195,6 +195,44 @@ class Engine:
                                                   counts.ctypes.data_as(C.POINTER(C.c_int64))))
         return counts
 
+    # ---- checkpoint / resume
+    def get_clock(self):
+        s, d, r = C.c_int64(), C.c_int64(), C.c_int64()
+        t = C.c_double()
+        self._check(self.lib.nds_get_clock(self.h, C.byref(s), C.byref(t), C.byref(d), C.byref(r)))
+        return dict(step=s.value, time=t.value, dep_count=d.value, rescale_count=r.value)
+
+    def set_clock(self, step, time, dep_count=0, rescale_count=0):
+        self._check(self.lib.nds_set_clock(self.h, int(step), float(time), int(dep_count), int(rescale_count)))
+
+    def set_vr(self, vr):
+        vr = _f64(vr, (self.M,))
+        self._check(self.lib.nds_set_vr(self.h, _p(vr)))
+
+    def checkpoint(self):
+        """Everything needed to continue the run bit for bit on a fresh engine of the same config."""
+        st = self.get_state(fields=("x", "v"))
+        ck = dict(x=st["x"], v=st["v"], **self.get_clock())
+        if self.cfg.mtd_enabled:
+            if self.cfg.mtd_shared:
+                c, h = self.get_hills(0)
+                ck.update(hills_centers=c, hills_heights=h)
+            else:
+                raise NdsError("checkpoint of per-walker hill tables is not implemented")
+            ck["vr"] = self.get_vr()
+        return ck
+
+    def restore(self, ck):
+        self.set_state(ck["x"], ck["v"])
+        self.begin()
+        if "hills_heights" in ck:
+            self.set_hills(ck["hills_centers"], ck["hills_heights"])
+            self.set_vr(ck["vr"])
+        self.set_clock(ck["step"], ck["time"], ck["dep_count"], ck["rescale_count"])
+
+    def count_nonfinite(self):
+        return int(self.lib.nds_count_nonfinite(self.h))
+
     # ---- committor
     def get_commit(self):
         basin = np.empty(self.M, dtype=np.int32)

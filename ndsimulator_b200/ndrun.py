@@ -284,6 +284,19 @@ class NDRun:
         ny = int(np.ceil((boundary[1][1] - boundary[1][0]) / increment[1]))
         return self.engine.colvar_histogram(boundary[0][0], increment[0], nx, boundary[1][0], increment[1], ny)
 
+    def save_checkpoint(self, path):
+        """(x, v, clock, hill table, VR) -> .npz; with the same config + seed the run continues bit for bit."""
+        ck = self.engine.checkpoint()
+        np.savez(path, **{k: np.asarray(v) for k, v in ck.items()})
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        ck = {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
+        self.engine.restore(ck)
+        self.step, self.time = int(ck["step"]), float(ck["time"])
+        self._dep_steps = []
+        self._cache = None
+
     @classmethod
     def from_dict(cls, dictionary):  # ndrun.py:270-282
         return cls(**dict(dictionary))
