@@ -91,11 +91,30 @@ class NDRun:
         self.n_walkers = spec.n_walkers
         self.x0 = spec.x0
         self._x0 = np.repeat(spec.x0.reshape(-1, 1), spec.n_walkers, axis=1)
+        spread = float(all_kwargs.get("x0_spread", 0.0) or 0.0)
+        if spread > 0:  # new key: walkers start from a Gaussian cloud around x0 (seeded, rank independent)
+            gid = spec.walker_offset + np.arange(spec.n_walkers)
+            rs = np.random.RandomState(spec.seed & 0x7FFFFFFF)
+            cloud = rs.normal(scale=spread, size=(spec.ndim, spec.n_walkers_global or spec.n_walkers))
+            self._x0 = self._x0 + cloud[:, gid]
         self._v0 = None
         self._window = None
         self.engine = Engine(spec.to_struct())
         if spec.path_ref is not None:
             self.engine.set_path(spec.path_ref, spec.path_ind, spec.path_sigma)
+        grid = all_kwargs.get("umb_window_grid")
+        if grid is not None:  # new key: one umbrella window per walker (walker w -> window w mod n_windows)
+            axes = [np.linspace(lo, hi, int(n)) for lo, hi, n in grid]
+            mesh = np.stack([m.reshape(-1) for m in np.meshgrid(*axes, indexing="xy")])
+            gid = spec.walker_offset + np.arange(spec.n_walkers)
+            r0 = mesh[:, gid % mesh.shape[1]]
+            k = np.repeat(np.asarray(spec.umb_k[0], dtype=float).reshape(-1, 1), spec.n_walkers, axis=1)
+            self._window = (k, r0)
+            self.engine.set_walker_bias(k, r0)
+            if spec.colvar == "Proj5dto2d":  # start on the window centre: xi1 = |(x0,x1)|, xi2 = |(x2,x3)|
+                self._x0 = np.stack([r0[0], np.zeros_like(r0[0]), r0[1], np.zeros_like(r0[0]), self._x0[4]])
+            elif spec.colvar == "Original":
+                self._x0 = r0.copy()
         self.engine.set_state(self._x0)
         self.atoms = _Atoms(self)
         self.modify = _Modify(self)

@@ -25,13 +25,29 @@ def parse_command_line(args=None):
     for kv in ns.set:
         k, v = kv.split("=", 1)
         config[k] = yaml.safe_load(v)
+    # one rank per GPU under torchrun: walkers shard by global id (ndsimulator_b200/distributed.py)
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from ndsimulator_b200.distributed import shard_config
+        config = shard_config(config)
+        config["run_name"] = f"{config['run_name']}_rank{os.environ.get('RANK', '0')}"
     return config
 
 
 def main(args=None):
     start = time.time()
     config = parse_command_line(args)
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     simulation = NDRun(**config)
+    if world > 1 and "mtd" in simulation.biases and simulation.spec.mtd_shared:
+        from ndsimulator_b200.distributed import attach_peer_hill_exchange
+        attach_peer_hill_exchange(simulation.engine)
     simulation.begin()
     simulation.run()
     simulation.end()

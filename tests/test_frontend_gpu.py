@@ -109,3 +109,21 @@ def test_user_defined_python_colvar_is_rejected(tmp_path):
     with pytest.raises(ValueError, match="cannot run on the B200 engine"):
         NDRun(ndim=2, potential="Mueller2d", x0=[1.0, 2.0], colvar_name="my_colvar.NewColvar",
               root=str(tmp_path), screen=False)
+
+
+@pytest.mark.parametrize("name", ["c2-2d-mueller-langevin", "c3-2d-committor", "c4-5d-umbrella-windows",
+                                  "c5-5d-multiwalker-mtd"])
+def test_shipped_examples_run(name, tmp_path):
+    """examples/*.yaml (the BASELINE configurations) through the CLI, shortened."""
+    from ndsimulator_b200.scripts.run import main
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sim = main([os.path.join(root, "examples", name + ".yaml"), "--set", f"root={tmp_path}", "steps=300",
+                "n_walkers=4096"])
+    assert sim.step == 300 or sim.spec.method == "committor"
+    assert sim.engine.count_nonfinite() == 0
+    if name.startswith("c4"):
+        c = sim.colv
+        k, r0 = sim._window
+        assert np.abs(c - r0).mean() < 2.0          # walkers stay near their own window
+    if name.startswith("c5"):
+        assert sim.engine.n_hills() == 3 * 4096 and sim.engine.kernel_name.startswith("mtd_block")
