@@ -188,3 +188,66 @@ def test_c5_full_size_hill_table_identities():
     assert scaled_err(g, host) < 1e-5
     assert np.isfinite(st["x"]).all() and st["biase"].min() > 0
     assert kBdT > 0 and sub is not None
+
+
+def test_c2_long_horizon_fp32_vs_oracle():
+    """The full 10^5-step horizon of C2 in fp32 (packed kernel, approximate MUFU functions): after 10^5
+    steps the ensemble still agrees with an oracle ensemble of the same length (KS on x, y, pe; <T>)."""
+    M, Mo, n = 8192, 1024, 100000
+    spec = spec_from(C2, n_walkers=M, precision="f32")
+    eng = Engine(spec.to_struct())
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(n)
+    a = eng.get_state()
+    assert eng.count_nonfinite() == 0
+    orc = oracle.OracleSim(spec_from(C2, n_walkers=Mo).to_struct(), seeds=np.arange(7000, 7000 + Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(x0[:, :Mo])
+    orc.begin()
+    orc.run(n)
+    b = orc.get_state()
+    for name, u, v in (("x", a["x"][0], b["x"][0]), ("y", a["x"][1], b["x"][1]), ("pe", a["pe"], b["pe"])):
+        assert stats.ks_2samp(u, v).pvalue > 1e-3, name
+    se = np.sqrt(a["T"].var() / M + b["T"].var() / Mo)
+    assert abs(a["T"].mean() - b["T"].mean()) < 4 * se
+
+
+def test_c5_multiwalker_fes_fp32_vs_oracle():
+    """Multiple-walker metadynamics (shared table, fp32 mtd_block with MUFU.EX2 / packed FP32) against the
+    oracle's shared-table ensemble: the free-energy estimate (sum of hills on the reference's 48 x 40 grid)
+    agrees within the run-to-run spread of the oracle itself plus 0.1 kT."""
+    M, n = 256, 3000
+    cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
+               true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
+               temperature=300, biases=["mtd"], mtd_w=0.002, mtd_sigma=[2.0, 2.0], mtd_dep_freq=100,
+               mtd_biasf=10.0, steps=n, mtd_shared=True, seed=1)
+    rng = np.random.RandomState(0)
+    x0 = np.stack([rng.uniform(14, 26, M), rng.uniform(-2, 2, M), rng.uniform(20, 32, M),
+                   rng.uniform(-2, 2, M), np.full(M, 12.0)])
+    grids = []
+    eng = Engine(spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=100).to_struct())
+    assert eng.kernel_name.startswith("mtd_block")
+    eng.set_state(x0)
+    eng.begin()
+    eng.run(n)
+    grids.append(eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40))
+    for seed0 in (100, 900):
+        orc = oracle.OracleSim(spec_from(cfg, n_walkers=M).to_struct(), seeds=np.arange(seed0, seed0 + M))
+        orc.set_threads(oracle.max_threads())
+        orc.set_state(x0)
+        orc.begin()
+        orc.run(n)
+        grids.append(orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40))
+    kT = kB * 300
+    mask = grids[1] > 2 * kT
+
+    def rms(u, v):
+        d = (u - v)[mask]
+        return np.sqrt(((d - d.mean()) ** 2).mean())
+
+    assert mask.sum() > 100
+    spread = rms(grids[1], grids[2])                      # oracle vs oracle, different seeds
+    assert rms(grids[0], grids[1]) < 2 * spread + 0.1 * kT, (rms(grids[0], grids[1]) / kT, spread / kT)
+    assert rms(grids[0], grids[2]) < 2 * spread + 0.1 * kT
