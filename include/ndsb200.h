@@ -37,7 +37,9 @@ extern "C" {
 enum { NDS_F32 = 0, NDS_F64 = 1 };
 
 /* method: engines/__init__.py:11-31: md, committor, mc (Metropolis Monte Carlo, engines/mc.py) */
-enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1, NDS_METHOD_MC = 2 };
+enum { NDS_METHOD_MD = 0, NDS_METHOD_COMMITTOR = 1, NDS_METHOD_MC = 2,
+       NDS_METHOD_WL = 3 /* Wang-Landau MC, engines/wang_landau.py:65-161 (one basin, f = 2) */ };
+#define NDS_WL_GRID 101   /* energy bins over [-1.5, 0.2], wang_landau.py:12-19 */
 
 /* integrate: engines/md.py:59; NDS_INT_MINIMIZE = the fixed-step steepest descent of
  * engines/minimize.py:41-82 (the inner engine of a committor run at temperature 0,
@@ -282,6 +284,8 @@ NDS_API int64_t nds_count_alive(nds_engine* e);
  *   propose "single": [step][3][M] = (coordinate pick, displacement, acceptance);
  *   propose "all":    [step][ndim + 1][M] = (displacements..., acceptance).                       */
 NDS_API int nds_get_mc(nds_engine* e, int64_t* accepted);
+/* Wang-Landau: the energy histogram hE[NDS_WL_GRID] of one walker (WangLandau.hE[0]) */
+NDS_API int nds_get_wl_histogram(nds_engine* e, int64_t walker, double* hE);
 
 /* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
  * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],

@@ -13,7 +13,8 @@ NDS_MAX_UMB = 4
 NDS_MAX_BASINS = 8
 
 NDS_F32, NDS_F64 = 0, 1
-NDS_METHOD_MD, NDS_METHOD_COMMITTOR, NDS_METHOD_MC = 0, 1, 2
+NDS_METHOD_MD, NDS_METHOD_COMMITTOR, NDS_METHOD_MC, NDS_METHOD_WL = 0, 1, 2, 3
+NDS_WL_GRID = 101
 NDS_INT_LANGEVIN, NDS_INT_LANGEVIN2, NDS_INT_NVE, NDS_INT_RESCALE, NDS_INT_MINIMIZE = 0, 1, 2, 3, 4
 NDS_NOISE_PHILOX, NDS_NOISE_EXTERNAL = 0, 1
 
@@ -119,6 +120,7 @@ _PROTOTYPES = {
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
     "nds_get_mc": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "nds_get_wl_histogram": (C.c_int, [C.c_void_p, C.c_int64, _dp]),
     "nds_get_clock": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nds_set_clock": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_int64]),

@@ -126,9 +126,9 @@ class RunSpec:
                        "f64": _abi.NDS_F64, "fp64": _abi.NDS_F64, "float64": _abi.NDS_F64}[
             str(self.precision).lower()]
         c.ndim = self.ndim
-        c.method = {"committor": _abi.NDS_METHOD_COMMITTOR, "mc": _abi.NDS_METHOD_MC}.get(
-            self.method, _abi.NDS_METHOD_MD)
-        if self.method == "mc":
+        c.method = {"committor": _abi.NDS_METHOD_COMMITTOR, "mc": _abi.NDS_METHOD_MC,
+                    "wl-mc": _abi.NDS_METHOD_WL}.get(self.method, _abi.NDS_METHOD_MD)
+        if self.method in ("mc", "wl-mc"):
             for d in range(self.ndim):
                 c.mc_bounds[d] = float(self.mc_bounds[d])
                 c.mc_global_bounds[d] = float(self.mc_global_bounds[d])
@@ -219,9 +219,9 @@ def parse(config: dict) -> RunSpec:
         eng_prefix = ["engine_method", "committor", "engine"]
     elif method == "minimize":
         eng_prefix = ["minimize", "engine"]
-    elif method == "mc":
-        eng_prefix = ["mc", "engine"]
-    elif method in ("wl-mc", "read_dump"):
+    elif method in ("mc", "wl-mc"):
+        eng_prefix = [method, "engine"]
+    elif method in ("read_dump",):
         raise NotImplementedError(
             f"method '{method}' is not part of the B200 multi-walker MD path (SURVEY.md section 8f)")
     else:
@@ -239,7 +239,7 @@ def parse(config: dict) -> RunSpec:
     if spec.integrate == "rescale" and spec.rescale_freq is None:
         raise TypeError("integrate: rescale needs rescale_freq (md.py:220)")
 
-    if method == "mc":  # engines/mc.py:7-32
+    if method in ("mc", "wl-mc"):  # engines/mc.py:7-32 (WangLandau subclasses MC)
         spec.mc_bounds = np.array(pick(cfg, "bounds", eng_prefix, [1.0, 1.0]), dtype=float).reshape(-1)
         spec.mc_global_bounds = np.array(pick(cfg, "global_bounds", eng_prefix, [20.0, 20.0]), dtype=float).reshape(-1)
         spec.mc_propose_dim = pick(cfg, "propose_dim", eng_prefix, "single")
@@ -355,7 +355,7 @@ def parse(config: dict) -> RunSpec:
         else:
             raise UnboundLocalError(f"unknown bias {b}")  # bias/__init__.py:40 would fail on `instance`
 
-    if method == "mc":
+    if method in ("mc", "wl-mc"):
         if "mtd" in biases:
             raise NotImplementedError("metadynamics under Metropolis MC (per-walker clocks) is not supported")
         cfg["dump"] = False  # the reference dumps only on accepted moves (ndrun.py:234-251): not recorded

@@ -44,6 +44,7 @@ struct nds_engine {
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
   virtual int get_mc(int64_t* accepted) = 0;
+  virtual int get_wl_histogram(int64_t walker, double* hE) = 0;
   virtual int get_clock(int64_t* step, double* time, int64_t* dep, int64_t* resc) const = 0;
   virtual int set_clock(int64_t step, double time, int64_t dep, int64_t resc) = 0;
   virtual int set_vr(const double* vr) = 0;
@@ -132,9 +133,8 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "unknown integrator %d", c->integrator);
   if (c->integrator == NDS_INT_RESCALE && !(c->rescale_freq > 0))  // md.py:220 (TypeError on None)
     return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
-  if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR && c->method != NDS_METHOD_MC)
-    return fail(nullptr, "unknown method %d", c->method);
-  if (c->method == NDS_METHOD_MC) {
+  if (c->method < NDS_METHOD_MD || c->method > NDS_METHOD_WL) return fail(nullptr, "unknown method %d", c->method);
+  if (c->method == NDS_METHOD_MC || c->method == NDS_METHOD_WL) {
     if (c->mtd_enabled) return fail(nullptr, "metadynamics under Metropolis MC is not supported");
     for (int d = 0; d < c->ndim; d++)
       if (c->mc_periodic && !(c->mc_global_bounds[d] != 0)) return fail(nullptr, "mc_global_bounds[%d] must be non-zero", d);
@@ -415,6 +415,7 @@ struct Engine : nds_engine {
   double* d_frames = nullptr;
   R *d_path_ref = nullptr, *d_path_ind = nullptr;
   long long* d_mc_accepted = nullptr;
+  R* d_wl = nullptr;
   double* d_noise = nullptr;
   int64_t noise_first = 0, noise_steps = 0;
   double* d_stage = nullptr;  // fp64 staging for host <-> device conversion
@@ -441,7 +442,7 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
                     (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
-                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_ids, (void*)d_flags, (void*)d_scan,
+                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_wl, (void*)d_ids, (void*)d_flags, (void*)d_scan,
                     (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
                     (void*)d_counter})
       if (p) cudaFree(p);
@@ -549,10 +550,15 @@ struct Engine : nds_engine {
       CU(cudaMalloc(&d_cub, cub_bytes));
       iota_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, d_ids);
     }
-    if (c.method == NDS_METHOD_MC) {
+    if (c.method == NDS_METHOD_MC || c.method == NDS_METHOD_WL) {
       CU(cudaMalloc(&d_mc_accepted, sizeof(long long) * sM));
       CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * sM, stream));
       kernel_name = sizeof(R) == 4 ? "mc_block<f32>" : "mc_block<f64>";
+      if (c.method == NDS_METHOD_WL) {
+        CU(cudaMalloc(&d_wl, sizeof(R) * NDS_WL_GRID * sM));
+        CU(cudaMemsetAsync(d_wl, 0, sizeof(R) * NDS_WL_GRID * sM, stream));
+        kernel_name = sizeof(R) == 4 ? "mc_block<f32,wang-landau>" : "mc_block<f64,wang-landau>";
+      }
     }
     CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     frame_width = 2 + 3 * nd + cd + 6;
@@ -681,7 +687,7 @@ struct Engine : nds_engine {
   int set_noise(const double* noise, int64_t first, int64_t nsteps) override {
     CU(cudaSetDevice(cfg.device));
     if (cfg.noise_mode != NDS_NOISE_EXTERNAL) return fail(this, "nds_set_noise: noise_mode is not NDS_NOISE_EXTERNAL");
-    const int nn = cfg.method == NDS_METHOD_MC ? (cfg.mc_propose_all ? nd + 1 : 3) : normals_per_step(cfg.integrator, nd);
+    const int nn = (cfg.method == NDS_METHOD_MC || cfg.method == NDS_METHOD_WL) ? (cfg.mc_propose_all ? nd + 1 : 3) : normals_per_step(cfg.integrator, nd);
     if (d_noise) { CU(cudaFree(d_noise)); d_noise = nullptr; }
     const size_t n = (size_t)nsteps * nn * (size_t)M;
     if (n) {
@@ -735,6 +741,7 @@ struct Engine : nds_engine {
       return fail(this, "path colvar: call nds_set_path() before nds_begin()");
     step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
     if (d_mc_accepted) CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * (size_t)M, stream));
+    if (d_wl) CU(cudaMemsetAsync(d_wl, 0, sizeof(R) * NDS_WL_GRID * (size_t)M, stream));
     if (cfg.method == NDS_METHOD_COMMITTOR) {
       if (permuted && unpermute_device()) return 1;
       CU(cudaMemsetAsync(d_alive, 1, (size_t)M, stream));
@@ -869,7 +876,7 @@ struct Engine : nds_engine {
     while (remaining > 0) {
       const int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
       BlockArgs<R> A = make_args(k);
-      cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, stream);
+      cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, d_wl, stream);
       if (err != cudaSuccess) return fail(this, "mc_block launch failed: %s", cudaGetErrorString(err));
       launches++;
       step += k;
@@ -877,6 +884,17 @@ struct Engine : nds_engine {
     }
     CU(cudaEventRecord(ev1, stream));
     timed = true;
+    return 0;
+  }
+
+  int get_wl_histogram(int64_t walker, double* hE) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_WL) return fail(this, "nds_get_wl_histogram: method is not wl-mc");
+    if (walker < 0 || walker >= M) return fail(this, "nds_get_wl_histogram: bad walker");
+    CU(cudaStreamSynchronize(stream));
+    std::vector<R> h(NDS_WL_GRID);
+    CU(cudaMemcpy2D(h.data(), sizeof(R), d_wl + walker, sizeof(R) * (size_t)M, sizeof(R), NDS_WL_GRID, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < NDS_WL_GRID; i++) hE[i] = (double)h[(size_t)i];
     return 0;
   }
 
@@ -910,7 +928,7 @@ struct Engine : nds_engine {
 
   int get_mc(int64_t* accepted) override {
     CU(cudaSetDevice(cfg.device));
-    if (cfg.method != NDS_METHOD_MC) return fail(this, "nds_get_mc: method is not mc");
+    if (cfg.method != NDS_METHOD_MC && cfg.method != NDS_METHOD_WL) return fail(this, "nds_get_mc: method is not mc / wl-mc");
     CU(cudaStreamSynchronize(stream));
     CU(cudaMemcpy(accepted, d_mc_accepted, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
     return 0;
@@ -919,7 +937,7 @@ struct Engine : nds_engine {
   int run(int64_t nsteps) override {  // the NDRun.run loop (ndrun.py:214-251)
     CU(cudaSetDevice(cfg.device));
     if (!begun) return fail(this, "nds_run before nds_begin");
-    if (cfg.method == NDS_METHOD_MC) return run_mc(nsteps);
+    if (cfg.method == NDS_METHOD_MC || cfg.method == NDS_METHOD_WL) return run_mc(nsteps);
     if (cfg.noise_mode == NDS_NOISE_EXTERNAL && normals_per_step(cfg.integrator, nd) > 0) {
       if (!d_noise || step < noise_first || step + nsteps > noise_first + noise_steps)
         return fail(this, "external noise table does not cover steps [%lld, %lld)", (long long)step,
@@ -1316,6 +1334,7 @@ int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
 int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e->get_commit(basin, exit_step); }
 int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
 int nds_get_mc(nds_engine* e, int64_t* accepted) { return e->get_mc(accepted); }
+int nds_get_wl_histogram(nds_engine* e, int64_t walker, double* hE) { return e->get_wl_histogram(walker, hE); }
 int nds_get_clock(const nds_engine* e, int64_t* step, double* time, int64_t* dep, int64_t* resc) {
   return e->get_clock(step, time, dep, resc);
 }

@@ -11,12 +11,33 @@
 
 namespace nds {
 
+// np.argmin(np.abs(Elist - e)), Elist = arange(101)/100*(Emax-Emin)+Emin (wang_landau.py:12-20); the
+// nearest grid point is found among the neighbours of the analytic position, ties go to the lower index
+template <typename R>
+NDS_DEV int wl_bin(R e) {
+  const R Emin = (R)-1.5, Emax = (R)0.2;
+  const R t = (e - Emin) / (Emax - Emin) * (R)(NDS_WL_GRID - 1);
+  int i0 = (int)floor((double)t) - 1;
+  if (i0 < 0) i0 = 0;
+  if (i0 > NDS_WL_GRID - 1) i0 = NDS_WL_GRID - 1;
+  int best = i0;
+  R bd = (R)0;
+  for (int i = i0; i <= i0 + 3 && i < NDS_WL_GRID; i++) {
+    const R El = (R)i / (R)(NDS_WL_GRID - 1.0) * (Emax - Emin) + Emin;
+    R d = El - e;
+    d = d < (R)0 ? -d : d;
+    if (i == i0 || d < bd) { bd = d; best = i; }
+  }
+  return best;
+}
+
 NDS_DEV double u01(uint32_t w, double) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
 NDS_DEV float u01(uint32_t w, float) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
 template <typename R, int ND>
 __global__ void __launch_bounds__(NDS_BLOCK)
-mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<R> A, long long* accepted) {
+mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<R> A, long long* accepted,
+         R* wl_hE /* [NDS_WL_GRID][M] per-walker histograms, Wang-Landau only */) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long M = A.M;
   if (w >= M) return;
@@ -86,8 +107,22 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     Eval<R, ND> tr;
     eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, A.hills, A.n_hills, 1, tr);
     const R pe = cur.pe + cur.be, pe_new = tr.pe + tr.be;  // mc.py:64-76
-    const R pb = (pe_new > pe) ? nds_exp(-(pe_new - pe) / K.kBT) : (R)1.0;
+    R pb = (pe_new > pe) ? nds_exp(-(pe_new - pe) / K.kBT) : (R)1.0;
+    int eid1 = 0;
+    if (K.method == NDS_METHOD_WL) {  // wang_landau.py:113-126, one basin
+      if (pe_new > (R)0.2) pb = (R)-1.0;  // pb = 0: never accepted
+      else {
+        eid1 = wl_bin<R>(pe_new);
+        const R h1 = wl_hE[eid1 * M + w];
+        if (h1 == (R)0) pb = (R)1.0;
+        else { const R r = wl_hE[wl_bin<R>(pe) * M + w] / h1; pb = r < (R)1.0 ? r : (R)1.0; }
+      }
+    }
     if (u[k] <= pb) {  // mc.py:83-96
+      if (K.method == NDS_METHOD_WL) {  // scaleup (wang_landau.py:51-55), f = 2
+        const R h1 = wl_hE[eid1 * M + w];
+        wl_hE[eid1 * M + w] = (h1 == (R)0) ? (R)1.0 : h1 * (R)2.0;
+      }
 #pragma unroll
       for (int d = 0; d < ND; d++) x[d] = xn[d];
       cur = tr;
@@ -106,11 +141,15 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     A.thermo[2 * M + w] = (R)0;
     A.thermo[4 * M + w] = cur.pe;
   }
+  if (K.method == NDS_METHOD_WL && acc > 0) {  // np.copyto(atoms.forces, forces_new), wang_landau.py:152
+#pragma unroll
+    for (int d = 0; d < ND; d++) A.f[d * M + w] = cur.fp[d];
+  }
   if (acc != acc0) accepted[w] = acc;
 }
 
 template <typename R>
 cudaError_t launch_mc_block(int nd, const Consts<R>& K, const BlockArgs<R>& A, long long* accepted,
-                            cudaStream_t st);
+                            R* wl_hE, cudaStream_t st);
 
 }  // namespace nds

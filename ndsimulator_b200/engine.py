@@ -247,6 +247,12 @@ class Engine:
         self._check(self.lib.nds_get_mc(self.h, acc.ctypes.data_as(C.POINTER(C.c_int64))))
         return acc
 
+    def get_wl_histogram(self, walker=0):
+        """WangLandau.hE[0] of one walker (engines/wang_landau.py:17)."""
+        h = np.empty(_abi.NDS_WL_GRID)
+        self._check(self.lib.nds_get_wl_histogram(self.h, int(walker), _p(h)))
+        return h
+
     def count_alive(self):
         return int(self.lib.nds_count_alive(self.h))
 

@@ -265,12 +265,12 @@ class NDRun:
             nostop = bool(np.any(basin < 0))
             if self.n_walkers == 1:
                 self.step = int(exit_step[0])
-        if spec.method == "mc":  # ndrun.py:235-238,265-268: time advances on accepted moves only
+        if spec.method in ("mc", "wl-mc"):  # ndrun.py:235-238,265-268: time advances on accepted moves only
             self.accepted = self.engine.get_mc()
             self.accept_rate = float(self.accepted[0])
             self.time = float(self.accepted[0]) * spec.dt
         self.logger.info(f"end condition {self.step} {total} {nostop}")
-        if spec.method == "mc" and spec.screen:
+        if spec.method in ("mc", "wl-mc") and spec.screen:
             self.logger.info(f"!! MC acceptance ratio: {self.accept_rate / max(total, 1)}")
         if spec.method == "committor" and spec.screen:
             self.logger.info(f"!! Commit to basin {self.commit_basin}")

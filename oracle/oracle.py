@@ -60,6 +60,7 @@ def lib():
         L.oracle_get_commit.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.oracle_get_vr.argtypes = [C.c_void_p, _dp]
         L.oracle_get_mc.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.oracle_get_wl_histogram.argtypes = [C.c_void_p, C.c_int64, _dp]
         L.oracle_n_hills.argtypes = [C.c_void_p, C.c_int64]
         L.oracle_n_hills.restype = C.c_int64
         L.oracle_get_hills.argtypes = [C.c_void_p, C.c_int64, _dp, _dp]
@@ -185,6 +186,11 @@ class OracleSim:
         acc = np.zeros(self.M, dtype=np.int64)
         self.L.oracle_get_mc(self.h, acc.ctypes.data_as(C.POINTER(C.c_int64)))
         return acc
+
+    def get_wl_histogram(self, walker=0):
+        h = np.zeros(101)
+        self.L.oracle_get_wl_histogram(self.h, int(walker), _p(h))
+        return h
 
     def get_vr(self):
         vr = np.zeros(self.M)

@@ -117,3 +117,67 @@ def test_ndrun_mc_frontend(tmp_path):
     assert sim.accepted.shape == (256,) and 0 < sim.accept_rate <= 500
     assert sim.time == sim.accept_rate * 0.5  # dt default 0.5, advanced on accepted moves only
     assert "!! MC acceptance ratio" not in open(str(tmp_path / "mc" / "log")).read()  # screen: false
+
+
+# --------------------------------------------------------------------------- Wang-Landau (wl-mc)
+WL = dict(ndim=2, potential="Mueller2d", x0=[22.0, 30.0], method="wl-mc", bounds=[2.0, 2.0],
+          global_bounds=[48.0, 40.0], mass=1.0, temperature=300, seed=0)
+
+
+def test_oracle_wang_landau_flattens_visits():
+    """WangLandau.update (engines/wang_landau.py:65-161): visited bins grow by factors of f = 2, so the
+    walk is pushed out of the minimum it starts in and covers a wide energy range."""
+    M, n = 64, 4000
+    spec = spec_from(WL, n_walkers=M)
+    o = oracle.OracleSim(spec.to_struct(), seeds=np.arange(M))
+    o.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
+    o.begin()
+    o.run(n)
+    h = o.get_wl_histogram(0)
+    assert (h > 0).sum() > 30                      # many energy bins visited
+    assert np.all((h == 0) | (np.log2(np.where(h > 0, h, 1)) % 1 == 0))  # 1, 2, 4, ... (f = 2)
+    pe = o.get_state()["pe"]
+    assert pe.max() <= 0.2 + 1e-12                 # moves above Emax are never accepted
+
+
+@pytest.mark.gpu
+def test_gpu_wang_landau_external_uniforms_match_oracle():
+    from ndsimulator_b200.engine import Engine
+    M, n = 48, 1500
+    spec = spec_from(WL, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=400)
+    st = spec.to_struct()
+    eng, orc = Engine(st), oracle.OracleSim(st, seeds=np.arange(M))
+    assert "wang-landau" in eng.kernel_name
+    u = np.random.RandomState(11).uniform(size=(n, 3, M))
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    for sim in (eng, orc):
+        sim.set_state(x0)
+        sim.set_noise(u)
+        sim.begin()
+        sim.run(n)
+    assert np.array_equal(eng.get_mc(), orc.get_mc())
+    for wk in (0, 7, M - 1):
+        assert np.array_equal(eng.get_wl_histogram(wk), orc.get_wl_histogram(wk))
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "pe", "f"):
+        assert scaled_err(a[k], b[k]) < 1e-10, k
+
+
+@pytest.mark.gpu
+def test_gpu_wang_landau_philox_statistics():
+    """Philox-driven WL walkers explore like the oracle's: distribution of visited-bin counts (KS)."""
+    from ndsimulator_b200.engine import Engine
+    M, n = 2048, 3000
+    spec = spec_from(WL, n_walkers=M)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
+    eng.begin()
+    eng.run(n)
+    Mo = 512
+    orc = oracle.OracleSim(spec_from(WL, n_walkers=Mo).to_struct(), seeds=np.arange(Mo))
+    orc.set_threads(oracle.max_threads())
+    orc.set_state(np.repeat(spec.x0.reshape(-1, 1), Mo, axis=1))
+    orc.begin()
+    orc.run(n)
+    assert stats.ks_2samp(eng.get_mc(), orc.get_mc()).pvalue > 1e-3
+    assert stats.ks_2samp(eng.get_state()["pe"], orc.get_state()["pe"]).pvalue > 1e-3
