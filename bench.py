@@ -331,7 +331,6 @@ def main():
         tdt, cty, esz = (torch.float32, C.c_float, 4) if f32 else (torch.float64, C.c_double, 8)
         bufs = [dict(x=torch.empty((nd, M), dtype=tdt).pin_memory(),
                      v=torch.empty((nd, M), dtype=tdt).pin_memory()) for _ in range(2)]
-        oth = torch.empty((5, M), dtype=tdt).pin_memory()
         st = eng.get_state(fields=("x", "v"))
         bufs[0]["x"].numpy()[:] = st["x"]
         bufs[0]["v"].numpy()[:] = st["v"]
@@ -342,32 +341,81 @@ def main():
         def ptr(tens):
             return C.cast(tens.data_ptr(), cp)
 
-        flip = [0]
+        class Batch:
+            """One ensemble with its two pinned host buffer sets (ping-pong: the state read back from pass n
+            is the input of pass n+1)."""
 
-        def e2e_step():
-            src, dst = bufs[flip[0]], bufs[1 - flip[0]]
-            # positions AND velocities are supplied, so the run continues (no re-draw, no re-begin)
-            eng._check(set_fn(eng.h, ptr(src["x"]), ptr(src["v"])))                           # H2D
-            eng._check(eng.lib.nds_run(eng.h, md_steps))
-            eng._check(get_fn(eng.h, ptr(dst["x"]), ptr(dst["v"]), None, None, None, ptr(oth)))  # D2H
-            flip[0] = 1 - flip[0]
+            def __init__(self, engine, first):
+                self.eng, self.flip = engine, 0
+                self.bufs = first if first is not None else [
+                    dict(x=torch.empty((nd, M), dtype=tdt).pin_memory(),
+                         v=torch.empty((nd, M), dtype=tdt).pin_memory()) for _ in range(2)]
+                self.oth = torch.empty((5, M), dtype=tdt).pin_memory()
 
-        e2e_n = max(3, min(args.steps, 20))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_n):
-            e2e_step()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-        e2e = {"value": world * M * md_steps * e2e_n / e2e_s, "unit": "walker-steps/s",
+            def submit(self):
+                src = self.bufs[self.flip]
+                # positions AND velocities are supplied, so the run continues (no re-draw, no re-begin)
+                self.eng._check(set_fn(self.eng.h, ptr(src["x"]), ptr(src["v"])))            # H2D
+                self.eng._check(self.eng.lib.nds_run(self.eng.h, md_steps))                  # async launch
+
+            def collect(self):
+                dst = self.bufs[1 - self.flip]
+                self.eng._check(get_fn(self.eng.h, ptr(dst["x"]), ptr(dst["v"]), None, None, None,
+                                       ptr(self.oth)))                                        # D2H (blocks)
+                self.flip = 1 - self.flip
+
+        def timed(fn, n):
+            barrier()
+            t0 = time.perf_counter()
+            fn(n)
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+
+        batches = [Batch(eng, bufs)]
+
+        def serial(n):
+            for _ in range(n):
+                batches[0].submit()
+                batches[0].collect()
+
+        def pipelined(n):
+            # two ensembles in flight: while one integrates, the other's D2H / H2D run on the copy engines
+            batches[0].submit()
+            for i in range(n):
+                if i + 1 < n:
+                    batches[(i + 1) % 2].submit()
+                batches[i % 2].collect()
+
+        e2e_n = max(4, min(args.steps, 20))
+        serial(2)
+        serial_s = timed(serial, e2e_n)
+        e2e = {"value": world * M * md_steps * e2e_n / serial_s, "unit": "walker-steps/s",
                "h2d_bytes_per_step": 2 * nd * M * esz, "d2h_bytes_per_step": (2 * nd + 5) * M * esz,
-               "steps": e2e_n}
+               "steps": e2e_n, "mode": "one ensemble, copy -> integrate -> copy in series"}
+        if name in ("c2", "c4"):
+            # second, independent ensemble (its own walker ids -> its own Philox streams)
+            cfg2 = dict(cfg, walker_offset=(world + rank) * M, n_walkers_global=2 * world * M)
+            eng2 = Engine(config.parse(cfg2).to_struct())
+            x02, extra2 = initial_state(name, spec, M, (world + rank) * M)
+            eng2.set_state(x02)
+            if extra2:
+                eng2.set_walker_bias(extra2["k"], extra2["r0"])
+            eng2.begin()
+            eng2.run(md_steps)
+            b2 = Batch(eng2, None)
+            st2 = eng2.get_state(fields=("x", "v"))
+            b2.bufs[0]["x"].numpy()[:] = st2["x"]
+            b2.bufs[0]["v"].numpy()[:] = st2["v"]
+            batches.append(b2)
+            pipelined(4)
+            pipe_s = timed(pipelined, 2 * e2e_n)
+            e2e = dict(e2e, value=world * M * md_steps * 2 * e2e_n / pipe_s, steps=2 * e2e_n,
+                       serial_value=e2e["value"],
+                       mode="two independent ensembles in flight (double-buffered): every pass still copies its "
+                            "inputs H2D from pinned memory and its result D2H; serial_value = one ensemble")
 
     clocks = sampler.stop() if sampler else None
 
