@@ -26,6 +26,11 @@ const Variant* variants_hot(int* n) {
       // C3: committor shooting on the same surface
       make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, CM, PHX, OFF>>(
           "md_block<f32,nd2,Mueller2d,Original,langevin,committor>"),
+      make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, CM, PHX, OFF, 2>>(
+          "md_block<f32,nd2,Mueller2d,Original,langevin,committor,2 basins>"),
+      // two shots per thread (packed FP32); a stopped lane parks its exit state and rides along
+      make_variant<Spec<f2, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, CM, PHX, OFF, 2>>(
+          "md_block<f32x2,nd2,Mueller2d,Original,langevin,committor,2 basins>"),
       // C4: 5-D umbrella windows, 2nd-order Langevin, per-walker (k, r0)
       make_variant<Spec<float, 5, NDS_POT_MUELLER5D, P52, P52, NDS_INT_LANGEVIN2, BIAS_UMB | BIAS_UMB_WALKER, MD, PHX, OFF>>(
           "md_block<f32,nd5,Mueller5d,Proj5dto2d,2nd-langevin,umb-windows>"),

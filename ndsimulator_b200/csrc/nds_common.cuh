@@ -21,7 +21,7 @@ constexpr int BIAS_PE = 4;          // potential-energy bias (bias/pe.py)
 constexpr int BIAS_UMB_WALKER = 8;  // restraint 0 takes (k, r0) per walker
 
 template <typename R_, int ND_, int POT_ = DYN, int CV_ = DYN, int TCV_ = DYN, int INTEG_ = DYN,
-          int BIAS_ = DYN, int METHOD_ = DYN, int NOISE_ = DYN, int DUMP_ = DYN>
+          int BIAS_ = DYN, int METHOD_ = DYN, int NOISE_ = DYN, int DUMP_ = DYN, int NBASIN_ = DYN>
 struct Spec {
   using R = R_;
   static constexpr int ND = ND_;
@@ -33,6 +33,7 @@ struct Spec {
   static constexpr int METHOD = METHOD_;
   static constexpr int NOISE = NOISE_;
   static constexpr int DUMP = DUMP_;
+  static constexpr int NBASIN = NBASIN_;  // committor: number of basin boxes when known at compile time
 };
 
 // Uniform constants of a run (one copy per engine, passed by value to every kernel).

@@ -289,17 +289,19 @@ static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dump
                                     variants_generic_f64_nd2, variants_generic_f64_nd5};
   const Variant* best = nullptr;
   int best_score = -1;
-  const int want[10] = {prec_override >= 0 ? prec_override : c.precision, c.ndim, c.potential, c.colvar,
-                        c.true_colvar, c.integrator, bias_mask, c.method, c.noise_mode, dumping ? 1 : 0};
+  const int want[11] = {prec_override >= 0 ? prec_override : c.precision, c.ndim, c.potential, c.colvar,
+                        c.true_colvar, c.integrator, bias_mask, c.method, c.noise_mode, dumping ? 1 : 0,
+                        c.n_basins};
   for (table_fn t : tables) {
     int n = 0;
     const Variant* v = t(&n);
     for (int i = 0; i < n; i++) {
-      const int have[10] = {v[i].key.prec, v[i].key.nd, v[i].key.pot, v[i].key.cv, v[i].key.tcv,
-                            v[i].key.integ, v[i].key.bias, v[i].key.method, v[i].key.noise, v[i].key.dump};
+      const int have[11] = {v[i].key.prec, v[i].key.nd, v[i].key.pot, v[i].key.cv, v[i].key.tcv,
+                            v[i].key.integ, v[i].key.bias, v[i].key.method, v[i].key.noise, v[i].key.dump,
+                            v[i].key.nbasin};
       bool ok = true;
       int score = 0;
-      for (int k = 0; k < 10 && ok; k++) {
+      for (int k = 0; k < 11 && ok; k++) {
         if (have[k] == DYN) continue;
         if (have[k] != want[k]) ok = false; else score++;
       }
@@ -980,6 +982,9 @@ struct Engine : nds_engine {
         P.x = (f2*)A.x; P.v = (f2*)A.v; P.f = (f2*)A.f; P.fixf = (f2*)A.fixf; P.colv = (f2*)A.colv;
         P.thermo = (f2*)A.thermo; P.vr = (f2*)A.vr;
         P.umb_k = (const f2*)A.umb_k; P.umb_r0 = (const f2*)A.umb_r0;
+        // committor: a thread owns slots 2t and 2t+1 of the (compacted) slot order
+        P.alive = A.alive; P.basin = A.basin; P.exit_step = A.exit_step; P.ids = A.ids;
+        P.n_active = A.n_active > 0 ? (A.n_active + 1) / 2 : 0;
         err = launch_packed(K2, P, stream);
       } else {
         err = launch_block(K, A, stream);

@@ -95,16 +95,23 @@ NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w,
   row[(r++) * st] = (bias_mask & BIAS_MTD) ? (double)A.vr[w] : 0.0;
 }
 
+// resident CTAs per SM asked of ptxas (register cap): the packed committor kernel is held to 64 registers
 template <class S>
-__global__ void __launch_bounds__(NDS_BLOCK)
+constexpr int md_block_min_ctas() {
+  return (pack_of<typename S::R>::value == 2 && S::METHOD == NDS_METHOD_COMMITTOR) ? 8 : 1;
+}
+
+template <class S>
+__global__ void __launch_bounds__(NDS_BLOCK, md_block_min_ctas<S>())
 md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
   using R = typename S::R;
   constexpr int ND = S::ND;
   constexpr int INTEG = S::INTEG;  // always compile-time
   constexpr int PACK = pack_of<R>::value;  // walkers per thread (2 for the packed-FP32 real type f2)
-  static_assert(PACK == 1 || (S::METHOD == NDS_METHOD_MD && S::NOISE == NDS_NOISE_PHILOX && S::DUMP == 0 &&
+  static_assert(PACK == 1 || ((S::METHOD == NDS_METHOD_MD || S::METHOD == NDS_METHOD_COMMITTOR) &&
+                              S::NOISE == NDS_NOISE_PHILOX && S::DUMP == 0 && INTEG != NDS_INT_MINIMIZE &&
                               S::BIAS >= 0 && (S::BIAS & (BIAS_PE | BIAS_MTD)) == 0),
-                "packed kernels: md, Philox noise, no frames, no PE / metadynamics bias");
+                "packed kernels: md / committor, Philox noise, no frames, no PE / metadynamics bias");
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
   constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
@@ -112,7 +119,9 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
   if (w >= (A.n_active > 0 ? A.n_active : M)) return;
-  const long long lw = A.ids ? A.ids[w] : w;  // local walker index of this slot (Philox stream, noise row)
+  // local walker index of this slot (Philox stream, noise row); a packed thread owns slots 2w and 2w+1
+  const long long lw = A.ids ? A.ids[w * PACK] : w * PACK;
+  const long long lw_b = PACK == 2 ? (A.ids ? A.ids[w * PACK + 1] : lw + 1) : lw;
 
   const int pot = S::POT >= 0 ? S::POT : K.pot;
   const int cv = S::CV >= 0 ? S::CV : K.cv;
@@ -123,9 +132,17 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   const bool ext_noise = S::NOISE >= 0 ? (S::NOISE == NDS_NOISE_EXTERNAL) : (K.noise == NDS_NOISE_EXTERNAL);
   const bool dumping = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0)) && w < K.dump_walkers;
 
+  // committor: lanes that stopped in an earlier launch (packed: a0 / a1 for slots 2w, 2w+1)
+  bool a0 = true, a1 = true;
   if constexpr (PACK == 1) {
     if (committor && !A.alive[w]) return;
+  } else {
+    if (committor) {
+      a0 = A.alive[2 * w] != 0; a1 = A.alive[2 * w + 1] != 0;
+      if (!a0 && !a1) return;
+    }
   }
+  const bool was0 = a0, was1 = a1;
 
   // ---- load walker state (coalesced SoA)
   R x[ND], v[ND];
@@ -139,7 +156,8 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     for (int k = 0; k < ND; k++)
       if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
-  const unsigned long long gid = (unsigned long long)(A.walker_offset + lw * PACK);
+  const unsigned long long gid = (unsigned long long)(A.walker_offset + lw);
+  const unsigned long long gid_b = (unsigned long long)(A.walker_offset + lw_b);
   const long long hstride = K.mtd_shared ? 1 : M;
   const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
 
@@ -147,7 +165,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     R z[4];
 #pragma unroll
     for (int d = 0; d < ND; d++) {
-      if ((d & 3) == 0) normals4<R>(K.rk_init, (unsigned long long)(d >> 2), gid, z);
+      if ((d & 3) == 0) normals4_pair<R>(K.rk_init, (unsigned long long)(d >> 2), gid, gid_b, z);
       v[d] = K.vel_scale * z[d & 3];
     }
   }
@@ -169,11 +187,19 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   bool alive = true;
   int basin = -1;
 
-  long long exit_s = 0;
+  long long exit_s = 0, exit_b = 0;
+  int basin_b = -1;
   bool min_stop = false;
+  // packed committor: a stopped lane keeps integrating (its results are ignored); its state at the exit
+  // step is parked here and restored at launch exit
+  R xf[PACK == 2 ? ND : 1], vf[PACK == 2 ? ND : 1];
+  if constexpr (PACK == 2) {
+#pragma unroll
+    for (int d = 0; d < ND; d++) { xf[d] = x[d]; vf[d] = v[d]; }
+  }
   while (s < s_end) {
     // the step counter stays warp-uniform: a stopped walker idles its lane until the whole warp is done
-    if (PACK == 1 && committor && !__any_sync(0xffffffffu, alive)) break;
+    if (committor && !__any_sync(0xffffffffu, PACK == 1 ? alive : (a0 || a1))) break;
     const long long grp = s / G;
     const int first = (int)(s - grp * G);
     R zb[G * NN > 0 ? G * NN : 1];
@@ -181,7 +207,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CG; c++) {
         R z4[4];
-        normals4<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, z4);
+        normals4_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z4);
 #pragma unroll
         for (int j = 0; j < 4; j++)
           if (4 * c + j < G * NN) zb[4 * c + j] = z4[j];
@@ -309,7 +335,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           if (committor && alive) {
             bool stopped = (INTEG == NDS_INT_MINIMIZE) && min_stop;  // committor.py:95-97
             if ((s - 1) >= K.diffusion_time) {  // committor.py:100-111
-              basin = commit_test<R, ND>(K, cd, e.cv.c, e.pe);
+              basin = commit_test<R, ND, INTEG == NDS_INT_MINIMIZE, S::NBASIN>(K, cd, e.cv.c, e.pe);
               if (basin >= 0) stopped = true;
             }
             if (stopped) { alive = false; exit_s = s; }
@@ -323,12 +349,42 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           }
           }
           if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
+        } else {
+          if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111, once per lane
+            float c0[ND], c1[ND];
+#pragma unroll
+            for (int k = 0; k < ND; k++) { c0[k] = e.cv.c[k].v.x; c1[k] = e.cv.c[k].v.y; }
+            const int b0 = commit_test<float, ND, false, S::NBASIN>(K, cd, c0, 0.f);
+            const int b1 = commit_test<float, ND, false, S::NBASIN>(K, cd, c1, 0.f);
+            const bool hit0 = a0 && b0 >= 0, hit1 = a1 && b1 >= 0;
+            if (hit0 || hit1) {  // rare
+              if (hit0) {
+                a0 = false; exit_s = s; basin = b0;
+#pragma unroll
+                for (int d = 0; d < ND; d++) { xf[d].v.x = x[d].v.x; vf[d].v.x = v[d].v.x; }
+              }
+              if (hit1) {
+                a1 = false; exit_b = s; basin_b = b1;
+#pragma unroll
+                for (int d = 0; d < ND; d++) { xf[d].v.y = x[d].v.y; vf[d].v.y = v[d].v.y; }
+              }
+            }
+          }
         }
       }
     }
   }
 
   // ---- launch exit: observables at the final positions (md.py:210-217,226-229) and state write-back
+  if constexpr (PACK == 2) {
+    if (committor) {  // stopped lanes go back to the state of their exit step (or of launch entry)
+#pragma unroll
+      for (int d = 0; d < ND; d++) {
+        if (!a0) { x[d].v.x = xf[d].v.x; v[d].v.x = vf[d].v.x; }
+        if (!a1) { x[d].v.y = xf[d].v.y; v[d].v.y = vf[d].v.y; }
+      }
+    }
+  }
   Eval<R, ND> o;
   if constexpr (INTEG == NDS_INT_MINIMIZE) o = e;  // pe / forces / colv of the last (trial) point, minimize.py:61-67
   else eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
@@ -357,6 +413,17 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
     }
     // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
     if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
+  } else {
+    if (committor) {
+      if (was0) {
+        if (!a0) { A.alive[2 * w] = 0; A.exit_step[2 * w] = exit_s; }
+        A.basin[2 * w] = basin;
+      }
+      if (was1) {
+        if (!a1) { A.alive[2 * w + 1] = 0; A.exit_step[2 * w + 1] = exit_b; }
+        A.basin[2 * w + 1] = basin_b;
+      }
+    }
   }
 }
 

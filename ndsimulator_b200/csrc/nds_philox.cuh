@@ -112,6 +112,23 @@ __device__ __forceinline__ void normals4<f2>(const PhiloxKeys& rk, unsigned long
 #pragma unroll
   for (int j = 0; j < 4; j++) z[j] = f2(a[j], b[j]);
 }
+
+// the same for a pair of walkers that are not neighbours (compacted committor lanes)
+template <typename R>
+__device__ __forceinline__ void normals4_pair(const PhiloxKeys& rk, unsigned long long call,
+                                              unsigned long long walker, unsigned long long, R (&z)[4]) {
+  normals4<R>(rk, call, walker, z);
+}
+template <>
+__device__ __forceinline__ void normals4_pair<f2>(const PhiloxKeys& rk, unsigned long long call,
+                                                  unsigned long long walker_a, unsigned long long walker_b,
+                                                  f2 (&z)[4]) {
+  float a[4], b[4];
+  normals4<float>(rk, call, walker_a, a);
+  normals4<float>(rk, call, walker_b, b);
+#pragma unroll
+  for (int j = 0; j < 4; j++) z[j] = f2(a[j], b[j]);
+}
 #endif
 
 }  // namespace nds

@@ -514,25 +514,33 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
 }
 
 // committor.py:118-142: inclusive boxes in colvar space; the last matching basin wins
-template <typename R, int ND>
-NDS_DEV int commit_test(const Consts<R>& K, int cd, const R (&c)[ND], R pe) {
+// ZT: the engine is the minimiser (the only case in which temperature can be 0); NB: compile-time basin count
+// or DYN.  T is the scalar type of one walker; the constant block may be the packed one (KT = Consts<f2>),
+// whose entries carry the same value in both lanes.
+NDS_DEV float lane0(float a) { return a; }
+NDS_DEV double lane0(double a) { return a; }
+NDS_DEV float lane0(f2 a) { return a.v.x; }
+
+template <typename T, int ND, bool ZT = true, int NB = DYN, typename KT>
+NDS_DEV int commit_test(const KT& K, int cd, const T (&c)[ND], T pe) {
   // at temperature 0 a basin additionally needs pe < emin (committor.py:128-131)
-  if (K.zero_temperature && !(pe < K.emin)) return -1;
-  int ib = -1;
+  if (ZT && K.zero_temperature && !(pe < lane0(K.emin))) return -1;
+  const int n_basins = NB >= 0 ? NB : K.n_basins;
+  // branch-free: every comparison is evaluated (constant-bank operands) and combined with bit ops, so a
+  // warp never diverges on the test.  "outside" is (c < lo || c > hi) like the reference, so a NaN
+  // colvar counts as inside, exactly as there.
   auto in_box = [&](int b) {
-    bool in = true;
+    unsigned out = 0u;
 #pragma unroll
     for (int k = 0; k < ND; k++)
-      if (k < cd && (c[k] < K.crit[b][k][0] || c[k] > K.crit[b][k][1])) in = false;
-    return in;
+      if (k < cd) out |= (unsigned)(c[k] < lane0(K.crit[b][k][0])) | (unsigned)(c[k] > lane0(K.crit[b][k][1]));
+    return out == 0u;
   };
-  // the usual case (two basins) is straight-line code on fixed constant-bank slots
-  if (in_box(0)) ib = 0;
-  if (K.n_basins > 1 && in_box(1)) ib = 1;
-  if (K.n_basins > 2) {  // rare: skipped by one uniform branch
-#pragma unroll
-    for (int b = 2; b < NDS_MAX_BASINS; b++)
-      if (b < K.n_basins && in_box(b)) ib = b;
+  int ib = in_box(0) ? 0 : -1;
+  if (n_basins > 1) ib = in_box(1) ? 1 : ib;  // uniform
+  if (n_basins > 2) {  // rare: skipped by one uniform branch
+#pragma unroll 1
+    for (int b = 2; b < n_basins; b++) ib = in_box(b) ? b : ib;
   }
   return ib;
 }

@@ -8,7 +8,7 @@
 namespace nds {
 
 struct VariantKey {
-  int prec, nd, pot, cv, tcv, integ, bias, method, noise, dump;
+  int prec, nd, pot, cv, tcv, integ, bias, method, noise, dump, nbasin;
 };
 
 struct Variant {
@@ -37,7 +37,7 @@ template <> struct prec_of<f2> { static constexpr int value = PREC_F32_PACKED; }
 template <class S>
 Variant make_variant(const char* name) {
   return Variant{VariantKey{prec_of<typename S::R>::value, S::ND, S::POT, S::CV, S::TCV, S::INTEG,
-                            S::BIAS, S::METHOD, S::NOISE, S::DUMP},
+                            S::BIAS, S::METHOD, S::NOISE, S::DUMP, S::NBASIN},
                  name, (void*)&launch_md_block<S>};
 }
 

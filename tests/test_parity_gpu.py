@@ -635,6 +635,43 @@ def test_committor_compaction_is_invisible(monkeypatch):
         assert np.array_equal(s0[k], s1[k]), k
 
 
+def test_packed_committor_matches_scalar(monkeypatch):
+    """Two shots per thread (packed fp32 committor kernel) against the scalar fp32 committor kernel: same
+    Philox numbers, same arithmetic up to FMA contraction, so over a few steps from start points around the
+    basin boxes the basins / exit steps agree (a stopped lane must keep the state of its exit step while
+    its partner lane keeps integrating)."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], steps=40, seed=11, diffusion_time=3)
+    M = 8192
+    rng = np.random.RandomState(5)
+    x0 = np.stack([rng.uniform(18, 52, M), rng.uniform(0, 37, M)])
+    outs = {}
+    for mode in ("packed", "scalar"):
+        if mode == "scalar":
+            monkeypatch.setenv("NDS_NO_PACKED", "1")
+        spec = spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=16)
+        eng = Engine(spec.to_struct())
+        assert ("f32x2" in eng.kernel_name) == (mode == "packed"), eng.kernel_name
+        eng.set_state(x0)
+        eng.begin()
+        eng.run(40)
+        outs[mode] = (eng.get_commit(), eng.get_state(), eng.count_alive())
+    (bp, ep), sp, ap = outs["packed"]
+    (bs, es), ss, as_ = outs["scalar"]
+    assert 500 < (bs >= 0).sum() < M - 500          # both committed and live lanes are exercised
+    assert (bp != bs).mean() < 1e-3 and (ep != es).mean() < 1e-3 and abs(ap - as_) <= 8
+    same = (bp == bs) & (ep == es)
+    for k in ("x", "v", "colv", "pe"):
+        assert scaled_err(sp[k][..., same], ss[k][..., same]) < 1e-3, k
+    # a committed walker sits inside its basin box, at the state of its exit step
+    crit = np.array(g["config"]["criteria"])
+    for b in range(crit.shape[0]):
+        sel = bp == b
+        assert sel.any()
+        for k in range(2):
+            assert (sp["colv"][k][sel] >= crit[b, k, 0]).all() and (sp["colv"][k][sel] <= crit[b, k, 1]).all()
+
+
 def test_committor_temperature_zero_minimize():
     """T = 0 committor on the GPU (steepest-descent inner engine, pe < emin criterion): basin ids and exit
     steps identical to the reference's runs, positions / energies within the trajectory tolerance; plus a
