@@ -21,8 +21,15 @@ __host__ __device__ constexpr int normals_per_step(int integ, int nd) {
   return integ == NDS_INT_LANGEVIN ? nd : (integ == NDS_INT_LANGEVIN2 ? 2 * nd : 0);
 }
 __host__ __device__ constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
-// steps per noise group: the smallest G with G*NN a multiple of 4 (one Philox call = 4 normals)
-__host__ __device__ constexpr int noise_group(int nn) { return nn == 0 ? 1 : 4 / gcd_(nn, 4); }
+// Steps per noise group and Philox calls per group (one call = NDS_NPC = 6 normals).  G*NN is a multiple
+// of 6 except for NN = 5 (5-D Langevin), where one call per step wastes a normal rather than unrolling six
+// 5-D steps.  NN: 1 -> G 6, 2 -> 3, 4 -> 3, 5 -> 1, 10 -> 3.
+__host__ __device__ constexpr int noise_group(int nn) {
+  return nn == 0 ? 1 : (nn == 5 ? 1 : NDS_NPC / gcd_(nn, NDS_NPC));
+}
+__host__ __device__ constexpr int noise_calls(int nn) {
+  return nn == 0 ? 1 : (noise_group(nn) * nn + NDS_NPC - 1) / NDS_NPC;
+}
 
 // frame events (io/dump.py:76-102 + the lagged thermo row): a frame is recorded after the
 // step that makes NDRun.step == s when s is a dump step, or when s is the last stat sample strictly
@@ -114,7 +121,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
                 "packed kernels: md / committor, Philox noise, no frames, no PE / metadynamics bias");
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
-  constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
+  constexpr int CG = noise_calls(NN);
 
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
@@ -162,12 +169,11 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
 
   if (A.need_init_v) {  // Modify.set_velocity(T=initial_temperature), engines/modify.py:44-54
-    R z[4];
+    static_assert(ND <= NDS_NPC, "one Philox call covers the initial velocities");
+    R z[NDS_NPC];
+    normals6_pair<R>(K.rk_init, 0ull, gid, gid_b, z);
 #pragma unroll
-    for (int d = 0; d < ND; d++) {
-      if ((d & 3) == 0) normals4_pair<R>(K.rk_init, (unsigned long long)(d >> 2), gid, gid_b, z);
-      v[d] = K.vel_scale * z[d & 3];
-    }
+    for (int d = 0; d < ND; d++) v[d] = K.vel_scale * z[d];
   }
 
   // ---- forces at the current positions: MD.begin (md.py:101-110) / refresh after a deposition
@@ -179,8 +185,15 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
   for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];  // md.py:133
 
-  long long s = A.step0;
+  // Loop control in 32-bit: `left` steps remain in this launch; NDRun.step is s_end - left (64-bit only
+  // where it is really needed: rare paths).  Noise groups are counted separately.
   const long long s_end = A.step0 + A.nsteps;
+  long long grp = A.step0 / G;
+  int first = (int)(A.step0 - grp * G);
+  int left = (int)A.nsteps;
+  // committor.py:100: (s - 1) >= diffusion_time with s = s_end - left  <=>  left <= commit_left
+  const long long thr_ = s_end - 1 - K.diffusion_time;
+  const int commit_left = thr_ < -1 ? -1 : (thr_ > 0x7fffffffLL ? 0x7fffffff : (int)thr_);
   double time = A.time0;
   long long rescale_count = A.rescale_count;
   long long frame = A.frame_base;
@@ -197,25 +210,24 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
     for (int d = 0; d < ND; d++) { xf[d] = x[d]; vf[d] = v[d]; }
   }
-  while (s < s_end) {
+  while (left > 0) {
     // the step counter stays warp-uniform: a stopped walker idles its lane until the whole warp is done
     if (committor && !__any_sync(0xffffffffu, PACK == 1 ? alive : (a0 || a1))) break;
-    const long long grp = s / G;
-    const int first = (int)(s - grp * G);
     R zb[G * NN > 0 ? G * NN : 1];
     if (NN > 0 && !ext_noise) {
 #pragma unroll
       for (int c = 0; c < CG; c++) {
-        R z4[4];
-        normals4_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z4);
+        R z6[NDS_NPC];
+        normals6_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z6);
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (4 * c + j < G * NN) zb[4 * c + j] = z4[j];
+        for (int j = 0; j < NDS_NPC; j++)
+          if (NDS_NPC * c + j < G * NN) zb[NDS_NPC * c + j] = z6[j];
       }
     }
 #pragma unroll
     for (int i = 0; i < G; i++) {
-      if (i >= first && s < s_end) {
+      if (i >= first && left > 0) {
+        long long s = s_end - left;  // NDRun.step before this update
        if (alive) {
         R xi[ND], eta[ND];
         if (NN > 0) {
@@ -329,12 +341,13 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           }
         }
        }  // alive
+        left -= 1;
         s += 1;            // ndrun.py:232
         time += K.dt64;    // ndrun.py:240
         if constexpr (PACK == 1) {
           if (committor && alive) {
             bool stopped = (INTEG == NDS_INT_MINIMIZE) && min_stop;  // committor.py:95-97
-            if ((s - 1) >= K.diffusion_time) {  // committor.py:100-111
+            if (left <= commit_left) {  // committor.py:100-111
               basin = commit_test<R, ND, INTEG == NDS_INT_MINIMIZE, S::NBASIN>(K, cd, e.cv.c, e.pe);
               if (basin >= 0) stopped = true;
             }
@@ -350,7 +363,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           }
           if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
         } else {
-          if (committor && (s - 1) >= K.diffusion_time) {  // committor.py:100-111, once per lane
+          if (committor && left <= commit_left) {  // committor.py:100-111, once per lane
             float c0[ND], c1[ND];
 #pragma unroll
             for (int k = 0; k < ND; k++) { c0[k] = e.cv.c[k].v.x; c1[k] = e.cv.c[k].v.y; }
@@ -373,7 +386,10 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
         }
       }
     }
+    first = 0;
+    grp += 1;
   }
+  const long long s = s_end - left;
 
   // ---- launch exit: observables at the final positions (md.py:210-217,226-229) and state write-back
   if constexpr (PACK == 2) {

@@ -195,7 +195,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   constexpr int INTEG = S::INTEG;
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
-  constexpr int CG = (G * NN) / 4 > 0 ? (G * NN) / 4 : 1;
+  constexpr int CG = noise_calls(NN);
   static_assert(W <= 32, "one lane per walker of the warp");
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -239,12 +239,10 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   const unsigned long long gid = (unsigned long long)(A.walker_offset + (owner ? w : 0));
 
   if (A.need_init_v) {
-    R z[4];
+    R z[NDS_NPC];
+    normals6<R>(K.rk_init, 0ull, gid, z);
 #pragma unroll
-    for (int d = 0; d < ND; d++) {
-      if ((d & 3) == 0) normals4<R>(K.rk_init, (unsigned long long)(d >> 2), gid, z);
-      v[d] = K.vel_scale * z[d & 3];
-    }
+    for (int d = 0; d < ND; d++) v[d] = K.vel_scale * z[d];
   }
 
   // full evaluation at x: colvar + potential + other biases on the owner lanes, hill pass by the warp
@@ -298,11 +296,11 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
     if (NN > 0 && !ext_noise) {
 #pragma unroll
       for (int c = 0; c < CG; c++) {
-        R z4[4];
-        normals4<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, z4);
+        R z6[NDS_NPC];
+        normals6<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, z6);
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (4 * c + j < G * NN) zb[4 * c + j] = z4[j];
+        for (int j = 0; j < NDS_NPC; j++)
+          if (NDS_NPC * c + j < G * NN) zb[NDS_NPC * c + j] = z6[j];
       }
     }
 #pragma unroll

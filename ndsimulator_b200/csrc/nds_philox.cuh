@@ -8,8 +8,11 @@
 // Stream layout (results do not depend on the number of ranks or on launch boundaries):
 //   key     = (seed_lo, seed_hi ^ domain)          domain 0: per-step noise, 1: initial velocities
 //   counter = (call_lo, call_hi, walker_lo, walker_hi)   walker = GLOBAL walker id
-//   normal n of a walker (n = step * normals_per_step + j) comes from call n >> 2, lane n & 3;
-//   lanes (0,1) and (2,3) are the two Box-Muller pairs of a call.
+//   one call yields SIX normals: its 128 bits are cut into six 21-bit fields (three Box-Muller pairs of
+//   a 21-bit radius variate and a 21-bit angle).  32x32 -> 64-bit multiplies run at a quarter of the FP32
+//   rate on sm_100 (profiles/microbench), so Philox is the most expensive part of a 2-D step; fp32 keeps
+//   24 bits at most anyway.  Radius cut-off: sqrt(2 ln 2^21) = 5.40 sigma (24 bits: 5.77).
+//   Steps are grouped so that a group of G steps uses whole calls (noise_group() in nds_kernels.cuh).
 #pragma once
 #include <cstdint>
 #include "nds_f2.cuh"
@@ -67,24 +70,26 @@ __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.appro
 __device__ __forceinline__ float sin_approx(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// Two standard normals from two 32-bit words (Box-Muller).
-// fp32: u1 in (0,1] from 24 bits feeds lg2.approx / sqrt.approx, the angle uses sin/cos.approx
-//       (MUFU pipe); fp64: full-precision log / sqrt / sincospi on 32-bit uniforms.
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  // u1 = n * 2^-24 with n = (a >> 8) + 1 in [1, 2^24]  (never 0, never denormal):
-  //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 24)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
-  // angle = 2 pi * (b >> 8) * 2^-24                  -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
-  const float n = (float)((a >> 8) + 1u);
-  // |.|: at n = 2^24 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
-  const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), -1.3862943611198906f, 33.271064666877374f)));
-  const float ang = (float)(b >> 8) * 3.7450702829239655e-07f;  // 2 pi 2^-24
+constexpr int NDS_NPC = 6;  // normals per Philox call
+
+// Two standard normals from two 21-bit fields (Box-Muller).
+// fp32: u1 in (0,1] feeds lg2.approx / sqrt.approx, the angle uses sin/cos.approx (MUFU pipe);
+// fp64: full-precision log / sqrt / sincospi on the same 21-bit uniforms.
+__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, float& z0, float& z1) {
+  // u1 = n * 2^-21 with n = a + 1 in [1, 2^21]  (never 0):
+  //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 21)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
+  // angle = 2 pi * b * 2^-21                   -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
+  const float n = (float)(a + 1u);
+  // |.|: at n = 2^21 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
+  const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), -1.3862943611198906f, 29.112181583517703f)));
+  const float ang = (float)b * 2.9960562263391724e-06f;  // 2 pi 2^-21
   z0 = r * cos_approx(ang);
   z1 = r * sin_approx(ang);
 }
 
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, double& z1) {
-  const double u1 = ((double)a + 1.0) * 2.3283064365386963e-10;  // (0, 1]
-  const double u2 = (double)b * 2.3283064365386963e-10;          // [0, 1)
+__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, double& z0, double& z1) {
+  const double u1 = ((double)a + 1.0) * 4.76837158203125e-07;  // (0, 1], 2^-21
+  const double u2 = (double)b * 4.76837158203125e-07;          // [0, 1)
   const double r = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi(2.0 * u2, &s, &c);
@@ -92,42 +97,34 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, d
   z1 = r * s;
 }
 
-// Fill z[0..3] with the four normals of Philox call `call` of one walker (for f2: of the walker pair
-// (walker, walker + 1), one Philox call each).
+// Fill z[0..5] with the six normals of Philox call `call` of one walker.  Fields: pair 0 = top 21 bits of
+// words 0, 1; pair 1 = top 21 bits of words 2, 3; pair 2 = the leftovers (low 11 bits of word 0 | low 10
+// bits of word 1, low 11 bits of word 2 | low 10 bits of word 3).
 template <typename R>
-__device__ __forceinline__ void normals4(const PhiloxKeys& rk, unsigned long long call,
-                                         unsigned long long walker, R (&z)[4]) {
+__device__ __forceinline__ void normals6(const PhiloxKeys& rk, unsigned long long call,
+                                         unsigned long long walker, R (&z)[NDS_NPC]) {
   const u32x4 r = philox4x32_10(
       u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
-  box_muller(r.x, r.y, z[0], z[1]);
-  box_muller(r.z, r.w, z[2], z[3]);
+  box_muller21(r.x >> 11, r.y >> 11, z[0], z[1]);
+  box_muller21(r.z >> 11, r.w >> 11, z[2], z[3]);
+  box_muller21((r.x & 0x7FFu) | ((r.y & 0x3FFu) << 11), (r.z & 0x7FFu) | ((r.w & 0x3FFu) << 11), z[4], z[5]);
 }
 
-template <>
-__device__ __forceinline__ void normals4<f2>(const PhiloxKeys& rk, unsigned long long call,
-                                             unsigned long long walker, f2 (&z)[4]) {
-  float a[4], b[4];
-  normals4<float>(rk, call, walker, a);
-  normals4<float>(rk, call, walker + 1ull, b);
-#pragma unroll
-  for (int j = 0; j < 4; j++) z[j] = f2(a[j], b[j]);
-}
-
-// the same for a pair of walkers that are not neighbours (compacted committor lanes)
+// f2: the walker pair (walker_a, walker_b), one Philox call each (neighbours, or any two compacted lanes)
 template <typename R>
-__device__ __forceinline__ void normals4_pair(const PhiloxKeys& rk, unsigned long long call,
-                                              unsigned long long walker, unsigned long long, R (&z)[4]) {
-  normals4<R>(rk, call, walker, z);
+__device__ __forceinline__ void normals6_pair(const PhiloxKeys& rk, unsigned long long call,
+                                              unsigned long long walker, unsigned long long, R (&z)[NDS_NPC]) {
+  normals6<R>(rk, call, walker, z);
 }
 template <>
-__device__ __forceinline__ void normals4_pair<f2>(const PhiloxKeys& rk, unsigned long long call,
+__device__ __forceinline__ void normals6_pair<f2>(const PhiloxKeys& rk, unsigned long long call,
                                                   unsigned long long walker_a, unsigned long long walker_b,
-                                                  f2 (&z)[4]) {
-  float a[4], b[4];
-  normals4<float>(rk, call, walker_a, a);
-  normals4<float>(rk, call, walker_b, b);
+                                                  f2 (&z)[NDS_NPC]) {
+  float a[NDS_NPC], b[NDS_NPC];
+  normals6<float>(rk, call, walker_a, a);
+  normals6<float>(rk, call, walker_b, b);
 #pragma unroll
-  for (int j = 0; j < 4; j++) z[j] = f2(a[j], b[j]);
+  for (int j = 0; j < NDS_NPC; j++) z[j] = f2(a[j], b[j]);
 }
 #endif
 

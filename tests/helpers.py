@@ -69,9 +69,12 @@ def philox_normals_f64(seed, walker, n_normals, domain=0):
     call = 0
     while len(out) < n_normals:
         r = philox4x32_10((call & 0xFFFFFFFF, call >> 32, walker & 0xFFFFFFFF, walker >> 32), (k0, k1))
-        for a, b in ((r[0], r[1]), (r[2], r[3])):
-            u1 = (a + 1.0) * 2.3283064365386963e-10
-            u2 = b * 2.3283064365386963e-10
+        # six normals per call: three Box-Muller pairs of 21-bit fields (nds_philox.cuh normals6)
+        fields = ((r[0] >> 11, r[1] >> 11), (r[2] >> 11, r[3] >> 11),
+                  ((r[0] & 0x7FF) | ((r[1] & 0x3FF) << 11), (r[2] & 0x7FF) | ((r[3] & 0x3FF) << 11)))
+        for a, b in fields:
+            u1 = (a + 1.0) * 2.0 ** -21
+            u2 = b * 2.0 ** -21
             rad = np.sqrt(-2.0 * np.log(u1))
             out += [rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)]
         call += 1
