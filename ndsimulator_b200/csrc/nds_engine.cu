@@ -135,7 +135,7 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
   if (c->method < NDS_METHOD_MD || c->method > NDS_METHOD_WL) return fail(nullptr, "unknown method %d", c->method);
   if (c->method == NDS_METHOD_MC || c->method == NDS_METHOD_WL) {
-    if (c->mtd_enabled) return fail(nullptr, "metadynamics under Metropolis MC is not supported");
+    if (c->mtd_enabled && c->method == NDS_METHOD_WL) return fail(nullptr, "metadynamics under Wang-Landau MC is not supported");
     for (int d = 0; d < c->ndim; d++)
       if (c->mc_periodic && !(c->mc_global_bounds[d] != 0)) return fail(nullptr, "mc_global_bounds[%d] must be non-zero", d);
   }
@@ -876,11 +876,28 @@ struct Engine : nds_engine {
     CU(cudaEventRecord(ev0, stream));
     int64_t remaining = nsteps;
     while (remaining > 0) {
-      const int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
+      int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
+      if (cfg.mtd_enabled) {
+        // fix.update(step, time) runs before engine.update for every engine (ndrun.py:227-228); the
+        // launch ends right before the next move that would deposit, like the MD loop below
+        if ((int64_t)std::floor(time / cfg.mtd_dep_freq) + 1 > dep_count) {
+          if (deposit()) return 1;
+        }
+        double t = time;
+        int64_t j = 0;
+        while (j < k) {
+          t += cfg.dt; j++;
+          if ((int64_t)std::floor(t / cfg.mtd_dep_freq) + 1 > dep_count) break;
+        }
+        k = j;
+      }
       BlockArgs<R> A = make_args(k);
+      A.refresh_vr = need_refresh_vr ? 1 : 0;
       cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, d_wl, stream);
       if (err != cudaSuccess) return fail(this, "mc_block launch failed: %s", cudaGetErrorString(err));
       launches++;
+      need_refresh_vr = false;
+      for (int64_t j = 0; j < k; j++) time += cfg.dt;  // ndrun.py:240 (MC.current_dt = dt, mc.py:25)
       step += k;
       remaining -= k;
     }

@@ -57,14 +57,23 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     for (int k = 0; k < ND; k++)
       if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
-  // MC.begin (mc.py:34-40): energies at the current point
+  const long long hstride = K.mtd_shared ? 1 : M;
+  const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
+  // MC.begin (mc.py:34-40): energies at the current point.  After a deposition this is the refresh of
+  // Gaussian.update (gaus.py:138-146): pe, forces, fixf, biase with the new hill, VR, totale.
   Eval<R, ND> cur;
-  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, A.hills, A.n_hills, 1, cur);
+  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, cur);
+  if (A.refresh_vr && (bias_mask & BIAS_MTD)) {
+    A.vr[w] = cur.vm;
+#pragma unroll
+    for (int d = 0; d < ND; d++) { A.f[d * M + w] = cur.fp[d]; A.fixf[d * M + w] = cur.fb[d]; }
+    A.thermo[4 * M + w] = A.thermo[2 * M + w] + cur.pe + cur.be;
+  }
   long long acc = accepted[w];
   const long long acc0 = acc;
 
   for (long long s = A.step0; s < A.step0 + A.nsteps; s++) {
-    R u[ND + 1];
+    R u[ND + 1 > 3 ? ND + 1 : 3];  // "single": pick, displacement, acceptance; "all": ND displacements + acceptance
     if (ext) {
       const double* row = A.noise + ((s - A.noise_first) * nu) * M + w;
       for (int j = 0; j < nu; j++) u[j] = (R)row[(long long)j * M];
@@ -105,7 +114,7 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
       }
     }
     Eval<R, ND> tr;
-    eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, A.hills, A.n_hills, 1, tr);
+    eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, hills, A.n_hills, hstride, tr);
     const R pe = cur.pe + cur.be, pe_new = tr.pe + tr.be;  // mc.py:64-76
     R pb = (pe_new > pe) ? nds_exp(-(pe_new - pe) / K.kBT) : (R)1.0;
     int eid1 = 0;
@@ -137,11 +146,11 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     if (q < cd) A.colv[q * M + w] = cur.cv.c[q];
   A.thermo[1 * M + w] = cur.pe;
   A.thermo[3 * M + w] = cur.be;
-  if (acc > 0) {  // mc.py:93-94 on the first accepted move: ke = 0, totale = pe
+  if (acc != acc0) {  // mc.py:93-94 on an accepted move: ke = 0, totale = pe
     A.thermo[2 * M + w] = (R)0;
     A.thermo[4 * M + w] = cur.pe;
   }
-  if (K.method == NDS_METHOD_WL && acc > 0) {  // np.copyto(atoms.forces, forces_new), wang_landau.py:152
+  if (K.method == NDS_METHOD_WL && acc != acc0) {  // np.copyto(atoms.forces, forces_new), wang_landau.py:152
 #pragma unroll
     for (int d = 0; d < ND; d++) A.f[d * M + w] = cur.fp[d];
   }

@@ -25,8 +25,10 @@ def test_config_mc():
     assert not s.dump
     with pytest.raises(NameError):
         config.parse(dict(M2, mc_bounds=[1.0]))  # mc.py:31-32
+    m = config.parse(dict(M2, biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0, steps=100)).to_struct()
+    assert m.mtd_enabled == 1 and m.method == _abi.NDS_METHOD_MC
     with pytest.raises(NotImplementedError):
-        config.parse(dict(M2, biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0))
+        config.parse(dict(M2, method="wl-mc", biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0))
 
 
 def test_oracle_mc_samples_boltzmann():
@@ -181,3 +183,40 @@ def test_gpu_wang_landau_philox_statistics():
     orc.run(n)
     assert stats.ks_2samp(eng.get_mc(), orc.get_mc()).pvalue > 1e-3
     assert stats.ks_2samp(eng.get_state()["pe"], orc.get_state()["pe"]).pvalue > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shared", [True, False])
+def test_gpu_mc_metadynamics_matches_oracle(shared):
+    """Metadynamics under Metropolis MC: fix.update runs before every engine.update (ndrun.py:227-228), so
+    hills are deposited at atoms.colv every dep_freq / dt moves, tempered with the VR of the LAST deposition
+    refresh (MC passes col0 to fix.energy, which leaves VR alone, gaus.py:361-362).  Deterministic against
+    the oracle with caller-supplied uniforms: accept counts, positions, bias energies, VR and the hill
+    tables (shared and per-walker)."""
+    from ndsimulator_b200.engine import Engine
+    M, n = 32, 400
+    cfg = dict(M2, dt=0.5, biases=["mtd"], mtd_w=0.02, mtd_sigma=[1.5, 1.5], mtd_dep_freq=10, mtd_biasf=8.0,
+               mtd_shared=shared, steps=n)
+    spec = spec_from(cfg, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    st = spec.to_struct()
+    eng, orc = Engine(st), oracle.OracleSim(st, seeds=np.arange(M))
+    assert eng.kernel_name.startswith("mc_block")
+    u = np.random.RandomState(3).uniform(size=(n, 3, M))
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    for sim in (eng, orc):
+        sim.set_state(x0)
+        sim.set_noise(u)
+        sim.begin()
+        sim.run(n)
+    assert eng.time == orc.time == n * 0.5
+    assert np.array_equal(eng.get_mc(), orc.get_mc())
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "colv", "pe", "biase", "f", "fixf", "totale"):
+        assert scaled_err(a[k], b[k]) < 1e-10, k
+    assert scaled_err(eng.get_vr(), orc.get_vr()) < 1e-10
+    for wk in ((0,) if shared else (0, M - 1)):
+        (cg, hg), (co, ho) = eng.get_hills(wk), orc.get_hills(wk)
+        assert len(hg) == len(ho) == (20 * M if shared else 20)      # one deposition per 20 moves of dt 0.5
+        assert scaled_err(cg, co) < 1e-10 and scaled_err(hg, ho) < 1e-10
+        assert hg.min() < 0.9 * 0.02                                   # the tempering is active
+    assert b["biase"].max() > 0.01
