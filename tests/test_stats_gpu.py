@@ -40,6 +40,61 @@ def test_initial_velocities_are_philox_normals():
     assert st["T"].mean() == pytest.approx(300.0, rel=0.02)
 
 
+@pytest.mark.parametrize("case", ["1d", "5d", "2d_langevin2"])
+def test_step_noise_is_the_documented_philox_stream(case):
+    """Every lane of the six-normals-per-call layout, and the step grouping (1-D: six steps per call, 5-D: one
+    call per step with the sixth normal dropped, 2-D 2nd-order Langevin: four normals per step, two calls per
+    three steps): on a flat potential the Langevin update is linear in the noise, so the normals the kernel
+    used can be solved from consecutive velocities and compared with the Python restatement of the stream
+    (tests/helpers.py).  Launch boundaries fall inside groups on purpose."""
+    M, n = 64, 13
+    if case == "1d":
+        cfg, nd, nn, grp = dict(ndim=1, potential="Flat1d", x0=0.0, integrate="langevin"), 1, 1, 6
+    elif case == "5d":
+        cfg, nd, nn, grp = dict(ndim=5, potential="Mueller5d", colvar_name="Proj5dto2d", true_colvar_name="Proj5dto2d",
+                                x0=[12.0] * 5, integrate="langevin"), 5, 5, 1
+    else:
+        cfg, nd, nn, grp = dict(ndim=2, potential="Flat2d", x0=[0.0, 0.0], integrate="2nd-langevin"), 2, 4, 3
+    cfg = dict(cfg, mass=1.0, method="md", temperature=300, dt=1.0, gamma=0.1, seed=42)
+    spec = spec_from(cfg, n_walkers=M, steps_per_launch=4, walker_offset=3, n_walkers_global=M + 3)
+    eng = Engine(spec.to_struct())
+    x0 = np.repeat(np.asarray(spec.x0, dtype=float).reshape(-1, 1), M, axis=1)
+    eng.set_state(x0, np.zeros((nd, M)))
+    eng.begin()
+    st = eng.get_state()
+    vs, fs = [st["v"].copy()], [st["f"].copy()]
+    for _ in range(n):
+        eng.run(1)
+        st = eng.get_state()
+        vs.append(st["v"].copy())
+        fs.append(st["f"].copy())
+    vs, fs = np.array(vs), np.array(fs)                    # [n+1][nd][M]
+    m = 104.23315626367025
+    calls_per_group = -(-grp * nn // 6)
+    for w in (0, 17, M - 1):
+        z = philox_normals_f64(42, w + 3, 6 * calls_per_group * (n // grp + 1))
+        for s in range(n):
+            g, i = divmod(s, grp)
+            zs = z[6 * calls_per_group * g + i * nn: 6 * calls_per_group * g + (i + 1) * nn]
+            if case != "2d_langevin2":   # v' = c1 (c1 (v + h f) + c2 xi + h f') + c2 xi, h = dt / 2m  (md.py:164-198)
+                c1 = np.exp(-0.05)
+                c2 = np.sqrt((1 - c1 ** 2) * kB * 300 / m)
+                h = 0.5 / m
+                got = (vs[s + 1, :, w] - c1 * h * fs[s + 1, :, w] - c1 * c1 * (vs[s, :, w] + h * fs[s, :, w])) / (c2 * (1 + c1))
+                assert np.allclose(got, zs[:nd], rtol=1e-7, atol=1e-9), (w, s)
+            else:                                          # two half updates v += -c2 v + c3 xi - c4 eta
+                frdt = 8 * (1 - np.exp(-0.05))
+                sig = np.sqrt(2 * kB * 300 * frdt / m)
+                k2 = frdt / 2 - frdt ** 2 / 8
+                k3 = sig / 2 * (1 - frdt / 4)
+                k5 = sig / (2 * np.sqrt(nd))
+                k4 = frdt / 2 * k5
+                xi, eta = zs[:nd], zs[nd:]
+                v1 = vs[s, :, w] * (1 - k2) + k3 * xi - k4 * eta
+                want = v1 * (1 - k2) + k3 * xi - k4 * eta
+                assert np.allclose(vs[s + 1, :, w], want, rtol=1e-9, atol=1e-15), (w, s)
+
+
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_fp32_normals_moments(precision):
     """Per-step noise: on a flat potential one Langevin step from v=0 gives v = c2 (1 + c1) xi."""
