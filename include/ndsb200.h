@@ -26,7 +26,7 @@ extern "C" {
 #define NDS_API
 #endif
 
-#define NDS_ABI_VERSION 1
+#define NDS_ABI_VERSION 2
 #define NDS_MAX_DIM 5     /* ndim of the built-in potentials is 1, 2 or 5                       */
 #define NDS_MAX_CV 5      /* colvardim <= ndim for every built-in colvar                         */
 #define NDS_MAX_UMB 4     /* harmonic restraints acting on one walker (umb_n, bias/__init__.py:31) */
@@ -135,6 +135,11 @@ typedef struct nds_config {
   double mtd_dep_freq;        /* deposition period in TIME units (gaus.py:134) */
   double mtd_biasf;           /* bias factor, must be > 1 */
   int64_t mtd_capacity;       /* hills the table can hold (per walker when !mtd_shared) */
+  int32_t mtd_adapsig_geo;    /* adapsig + adapsig_geo (gaus.py:162-165,189-192,263-288): every hill carries its
+                                 own variance J.J^T (first hill) / J.J^T * sigma^2 (later hills) taken at the
+                                 deposition point.  colvardim 1 only: for 2-D colvars the reference takes the
+                                 element-wise reciprocal of a matrix with zero off-diagonals (inf / NaN bias). */
+  int32_t reserved3;
 
   /* potential-energy bias, bias/pe.py:30-51 */
   int32_t pe_enabled;
@@ -250,6 +255,10 @@ NDS_API int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, do
  * Per-walker tables (!mtd_shared): `walker` selects the table.                                  */
 NDS_API int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* centers, double* heights,
                   int64_t capacity);
+/* per-hill variances of an adaptive table (Gaussian._sigma_history; the sigma^2 of the config for a
+ * fixed-sigma table, first colvar).  nds_set_hill_sigma2 follows nds_set_hills when a table is restored. */
+NDS_API int nds_get_hill_sigma2(nds_engine* e, int64_t walker, double* sigma2, int64_t cap);
+NDS_API int nds_set_hill_sigma2(nds_engine* e, int64_t walker, int64_t n, const double* sigma2);
 NDS_API int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* centers,
                   const double* heights);
 /* stale bias energy per walker used by the well-tempered height (fix.VR): [M] */

@@ -6,7 +6,7 @@ There is no CPU fallback: :func:`load_library` raises if ``libndsb200.so`` has n
 import ctypes as C
 import os
 
-NDS_ABI_VERSION = 1
+NDS_ABI_VERSION = 2
 NDS_MAX_DIM = 5
 NDS_MAX_CV = 5
 NDS_MAX_UMB = 4
@@ -73,6 +73,7 @@ class NdsConfig(C.Structure):
         ("mtd_enabled", C.c_int32), ("mtd_shared", C.c_int32),
         ("mtd_w", C.c_double), ("mtd_sigma", C.c_double * NDS_MAX_CV),
         ("mtd_dep_freq", C.c_double), ("mtd_biasf", C.c_double), ("mtd_capacity", C.c_int64),
+        ("mtd_adapsig_geo", C.c_int32), ("reserved3", C.c_int32),
         ("pe_enabled", C.c_int32), ("reserved1", C.c_int32), ("pe_thred", C.c_double),
         ("n_basins", C.c_int32), ("reserved2", C.c_int32), ("diffusion_time", C.c_int64),
         ("criteria", ((C.c_double * 2) * NDS_MAX_CV) * NDS_MAX_BASINS),
@@ -112,6 +113,8 @@ _PROTOTYPES = {
     "nds_eval_at": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
     "nds_get_hills": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), _dp, _dp, C.c_int64]),
     "nds_set_hills": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]),
+    "nds_get_hill_sigma2": (C.c_int, [C.c_void_p, C.c_int64, _dp, C.c_int64]),
+    "nds_set_hill_sigma2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
     "nds_get_vr": (C.c_int, [C.c_void_p, _dp]),
     "nds_set_exchange": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
     "nds_hills_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),

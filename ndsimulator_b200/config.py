@@ -90,6 +90,7 @@ class RunSpec:
     mtd_biasf: float = 1.0
     mtd_shared: bool = True
     mtd_capacity: int = 0
+    mtd_adapsig_geo: bool = False
     pe_thred: float = 0.0
     n_basins: int = 0
     criteria: Optional[np.ndarray] = None
@@ -167,6 +168,7 @@ class RunSpec:
             c.mtd_dep_freq = float(self.mtd_dep_freq)
             c.mtd_biasf = float(self.mtd_biasf)
             c.mtd_capacity = int(self.mtd_capacity)
+            c.mtd_adapsig_geo = int(self.mtd_adapsig_geo)
         c.pe_enabled = int("pe" in self.biases)
         c.pe_thred = float(self.pe_thred)
         c.n_basins = int(self.n_basins)
@@ -318,8 +320,16 @@ def parse(config: dict) -> RunSpec:
     cd = spec.colvardim
     for b in biases:
         if b == "mtd":  # bias/gaus.py:48-128
-            if pick(cfg, "adapsig", "mtd", False) or pick(cfg, "adapsig_geo", "mtd", False):
-                raise NotImplementedError("adaptive-sigma metadynamics is outside the B200 hot path")
+            adapsig, geo = pick(cfg, "adapsig", "mtd", False), pick(cfg, "adapsig_geo", "mtd", False)
+            if adapsig and not geo:  # gaus.py:166-181: variance from the Stat history of the colvar
+                raise NotImplementedError("mtd_adapsig without mtd_adapsig_geo needs the host-side Stat history "
+                                          "(gaus.py:166-181) and is outside the B200 hot path")
+            if adapsig and geo:      # gaus.py:162-165,189-192: every hill gets the variance J.J^T (* sigma^2)
+                if cd != 1:
+                    raise ValueError("mtd_adapsig_geo needs a 1-D colvar: for colvardim > 1 the reference takes the "
+                                     "element-wise reciprocal of J.J^T (gaus.py:268-275), which is inf / NaN for "
+                                     "the built-in colvars")
+                spec.mtd_adapsig_geo = True
             spec.mtd_w = pick(cfg, "w", "mtd", None)
             sigma = pick(cfg, "sigma", "mtd", None)
             if isinstance(sigma, float):  # gaus.py:76-78

@@ -41,7 +41,8 @@ template <typename R>
 struct Consts {
   int ndim, cd, tcd;
   int pot, cv, tcv, integ, method, noise, bias_mask, n_umb, n_basins;
-  int mtd_shared, hill_stride;  // reals per hill record (cd + 1, padded to 4 when cd == 2)
+  int mtd_shared, hill_stride;  // reals per hill record (cd + 1, padded to 4 when cd == 2 or adaptive)
+  int mtd_adaptive;             // per-hill variance (adapsig_geo, colvardim 1): record = (c, w, 1/s, s)
   // units / integrator (engines/md.py:81-99, data.py:26-28, constant.py)
   R m, inv_m, dt, kB, kBT;
   R c1, c2, c3, c4, c5, v_target;
@@ -63,6 +64,7 @@ struct Consts {
   // biases
   R umb_k[NDS_MAX_UMB][NDS_MAX_CV], umb_r0[NDS_MAX_UMB][NDS_MAX_CV];
   R mtd_w, mtd_invsig2[NDS_MAX_CV], mtd_kBdT;  // kB*(biasf-1)*T, gaus.py:102-103
+  R mtd_sig2[NDS_MAX_CV];                      // sigma^2 (gaus.py:90)
   R mtd_pre[NDS_MAX_CV];  // fp32 fast form: sqrt(log2(e) / 2) / sigma
   R pe_thred;
   R crit[NDS_MAX_BASINS][NDS_MAX_CV][2];

@@ -41,6 +41,8 @@ struct nds_engine {
                       double* Vb, double* Fb) = 0;
   virtual int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) = 0;
   virtual int set_hills(int64_t walker, int64_t n, const double* centers, const double* heights) = 0;
+  virtual int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) = 0;
+  virtual int set_hill_sigma2(int64_t walker, int64_t n, const double* sigma2) = 0;
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
   virtual int get_mc(int64_t* accepted) = 0;
@@ -151,6 +153,9 @@ static int validate(const nds_config* c) {
     if (c->mtd_capacity <= 0) return fail(nullptr, "mtd_capacity must be positive");
     for (int k = 0; k < nds_colvar_dim(c->colvar, c->ndim); k++)
       if (!(c->mtd_sigma[k] > 0)) return fail(nullptr, "mtd_sigma[%d] must be positive", k);
+    if (c->mtd_adapsig_geo && nds_colvar_dim(c->colvar, c->ndim) != 1)
+      return fail(nullptr, "mtd_adapsig_geo needs a 1-D colvar: for colvardim > 1 the reference takes the "
+                           "element-wise reciprocal of J.J^T (gaus.py:268-275), which is inf / NaN");
   }
   if (c->method == NDS_METHOD_COMMITTOR) {
     if (c->n_basins < 1 || c->n_basins > NDS_MAX_BASINS) return fail(nullptr, "n_basins out of range");
@@ -182,7 +187,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.bias_mask = (c.n_umb > 0 ? BIAS_UMB : 0) | (c.mtd_enabled ? BIAS_MTD : 0) |
                 (c.pe_enabled ? BIAS_PE : 0) | ((c.n_umb > 0 && c.umb_per_walker) ? BIAS_UMB_WALKER : 0);
   K.mtd_shared = c.mtd_shared;
-  K.hill_stride = (K.cd == 2) ? 4 : K.cd + 1;
+  K.mtd_adaptive = (c.mtd_enabled && c.mtd_adapsig_geo) ? 1 : 0;
+  K.hill_stride = (K.cd == 2 || K.mtd_adaptive) ? 4 : K.cd + 1;
   const double m = au_mass_() * c.mass;        // data.py:27-28
   const double kBT = kB_ * c.temperature;      // data.py:26
   // Minimize multiplies the configured time step by 10 (engines/minimize.py:18)
@@ -257,6 +263,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
     K.mtd_w = (R)c.mtd_w;
     for (int k = 0; k < K.cd; k++) {
       K.mtd_invsig2[k] = (R)(1.0 / (c.mtd_sigma[k] * c.mtd_sigma[k]));  // gaus.py:90-91
+      K.mtd_sig2[k] = (R)(c.mtd_sigma[k] * c.mtd_sigma[k]);
       K.mtd_pre[k] = (R)(std::sqrt(kfast) / c.mtd_sigma[k]);
     }
     K.mtd_kBdT = (R)(kB_ * ((c.mtd_biasf - 1) * c.temperature));  // gaus.py:102-103
@@ -768,7 +775,7 @@ struct Engine : nds_engine {
     if (n_hills + add > cfg.mtd_capacity)
       return fail(this, "hill table full: %lld + %lld > mtd_capacity %lld", (long long)n_hills,
                   (long long)add, (long long)cfg.mtd_capacity);
-    if (cfg.mtd_shared && d_peer_tables && cfg.n_walkers_global > M) {
+    if (cfg.mtd_shared && d_peer_tables && cfg.n_walkers_global > M && !K.mtd_adaptive) {
       // fused deposition + exchange: records go straight into every rank's table over NVLink
       deposit_p2p_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
           K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_peer_tables, n_peers, n_hills,
@@ -788,6 +795,15 @@ struct Engine : nds_engine {
         K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, dep_count == 0 ? 1 : 0);
     CU(cudaGetLastError());
     launches++;
+    if (K.mtd_adaptive) {  // per-hill variance J.J^T (* sigma^2) at the deposition point
+      const unsigned g = (unsigned)((M + 127) / 128);
+      const int first = dep_count == 0 ? 1 : 0;
+      if (nd == 1) hill_variance_kernel<R, 1><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
+      else if (nd == 2) hill_variance_kernel<R, 2><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
+      else hill_variance_kernel<R, 5><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
+      CU(cudaGetLastError());
+      launches++;
+    }
     if (cfg.mtd_shared && exchange && cfg.n_walkers_global > M) {
       // multi-GPU: complete the segment [n_hills, n_hills + n_walkers_global) with every rank's
       // records.  The callback runs an in-place allgather on its own stream.
@@ -1086,6 +1102,47 @@ struct Engine : nds_engine {
     return rc;
   }
 
+  int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!cfg.mtd_enabled) return fail(this, "nds_get_hill_sigma2: metadynamics is not enabled");
+    if (n_hills == 0 || !sigma2) return 0;
+    if (cap < n_hills) return fail(this, "nds_get_hill_sigma2: capacity %lld < %lld hills", (long long)cap, (long long)n_hills);
+    if (!cfg.mtd_shared && (walker < 0 || walker >= M)) return fail(this, "nds_get_hill_sigma2: bad walker");
+    if (!K.mtd_adaptive) {
+      for (int64_t i = 0; i < n_hills; i++) sigma2[i] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
+      return 0;
+    }
+    const int rs = K.hill_stride;
+    const int64_t es = cfg.mtd_shared ? 1 : M;
+    const int64_t span = cfg.mtd_shared ? n_hills * rs : n_hills * rs * M;
+    std::vector<double> h((size_t)span);
+    if (download(d_hills, h.data(), span)) return 1;
+    const int64_t off = cfg.mtd_shared ? 0 : walker;
+    for (int64_t i = 0; i < n_hills; i++) sigma2[i] = h[(size_t)((i * rs + 3) * es + off)];
+    return 0;
+  }
+
+  // follows set_hills() when an adaptive table is restored
+  int set_hill_sigma2(int64_t walker, int64_t n, const double* sigma2) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!K.mtd_adaptive) return fail(this, "nds_set_hill_sigma2: the table is not adaptive (mtd_adapsig_geo = 0)");
+    if (n != n_hills) return fail(this, "nds_set_hill_sigma2: %lld values for %lld hills", (long long)n, (long long)n_hills);
+    if (n == 0) return 0;
+    const int rs = K.hill_stride;
+    const int64_t es = cfg.mtd_shared ? 1 : M;
+    const int64_t span = cfg.mtd_shared ? n * rs : n * rs * M;
+    std::vector<double> h((size_t)span);
+    if (download(d_hills, h.data(), span)) return 1;
+    for (int64_t w = 0; w < (cfg.mtd_shared ? 1 : M); w++) {
+      if (!cfg.mtd_shared && walker >= 0 && w != walker) continue;
+      for (int64_t i = 0; i < n; i++) {
+        h[(size_t)((i * rs + 2) * es + w)] = 1.0 / sigma2[i];
+        h[(size_t)((i * rs + 3) * es + w)] = sigma2[i];
+      }
+    }
+    return upload(h.data(), d_hills, span);
+  }
+
   int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) override {
     CU(cudaSetDevice(cfg.device));
     if (n) *n = n_hills;
@@ -1117,6 +1174,10 @@ struct Engine : nds_engine {
         for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
         h[(size_t)(i * rs + cd)] = heights[i];
         for (int k = cd + 1; k < rs; k++) h[(size_t)(i * rs + k)] = std::log2(heights[i]);
+        if (K.mtd_adaptive) {  // default variance sigma^2 until nds_set_hill_sigma2 supplies the history
+          h[(size_t)(i * rs + 2)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
+          h[(size_t)(i * rs + 3)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
+        }
       }
       if (clear_hills()) return 1;  // padding records stay (0, 0, 0, -inf)
       if (n && upload(h.data(), d_hills, n * rs)) return 1;
@@ -1129,6 +1190,10 @@ struct Engine : nds_engine {
         for (int64_t i = 0; i < n; i++) {
           for (int k = 0; k < cd; k++) h[(size_t)((i * rs + k) * M + w)] = centers[i * cd + k];
           h[(size_t)((i * rs + cd) * M + w)] = heights[i];
+          if (K.mtd_adaptive) {
+            h[(size_t)((i * rs + 2) * M + w)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
+            h[(size_t)((i * rs + 3) * M + w)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
+          }
         }
       }
       if (upload(h.data(), d_hills, (int64_t)h.size())) return 1;
@@ -1248,6 +1313,7 @@ struct Engine : nds_engine {
   int set_peer_tables(void* const* tables, int nranks, int rank, bool opened_by_ipc) override {
     CU(cudaSetDevice(cfg.device));
     if (!d_hills || !cfg.mtd_shared) return fail(this, "peer tables need a shared hill table");
+    if (K.mtd_adaptive) return fail(this, "peer tables do not carry per-hill variances (mtd_adapsig_geo): use the allgather exchange");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(this, "bad rank / nranks");
     std::vector<R*> t((size_t)nranks);
     for (int r = 0; r < nranks; r++) t[(size_t)r] = (r == rank) ? d_hills : (R*)tables[r];
@@ -1347,6 +1413,12 @@ int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* c, double* 
 }
 int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* c, const double* h) {
   return e->set_hills(walker, n, c, h);
+}
+int nds_get_hill_sigma2(nds_engine* e, int64_t walker, double* sigma2, int64_t cap) {
+  return e->get_hill_sigma2(walker, sigma2, cap);
+}
+int nds_set_hill_sigma2(nds_engine* e, int64_t walker, int64_t n, const double* sigma2) {
+  return e->set_hill_sigma2(walker, n, sigma2);
 }
 int nds_get_vr(nds_engine* e, double* vr) { return e->get_vr(vr); }
 int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {

@@ -503,10 +503,43 @@ __global__ void deposit_kernel(const __grid_constant__ Consts<R> K, long long M,
     rec[cd] = h;
     // colvardim 2: the 4th word carries log2(height) for the MUFU-bound fp32 loop of mtd_block
     // (-inf for a zero-height record, which then contributes exactly 0)
-    for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
+    if (!K.mtd_adaptive)
+      for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
   } else {
     for (int k = 0; k < cd; k++) hills[(n_hills * rs + k) * M + w] = colv[k * M + w];
     hills[(n_hills * rs + cd) * M + w] = h;
+  }
+}
+
+// adapsig_geo (gaus.py:162-165, 189-192): variance of the new hill of every walker, s = J.J^T at the
+// deposition point (first hill of a table) or J.J^T * sigma^2 (later hills); fields 2, 3 of the record
+// get 1/s and s.  Runs right after deposit_kernel, before any exchange.  colvardim 1.
+template <typename R, int ND>
+__global__ void hill_variance_kernel(const __grid_constant__ Consts<R> K, long long M, long long walker_offset,
+                                     const R* __restrict__ x, R* hills, long long n_hills, int first) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= M) return;
+  R xx[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) xx[d] = x[d * M + w];
+  CvOut<R, ND> o;
+  cv_eval<R, ND>(K, K.cv, K.rot, xx, o);
+  R g[ND], row[ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) g[d] = d == 0 ? (R)1 : (R)0;
+  cv_pullback<R, ND>(K.cv, K.rot, xx, o, g, row);  // row 0 of colvar.jacobian(x)
+  R jj = (R)0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) jj += row[d] * row[d];
+  const R s = first ? jj : jj * K.mtd_sig2[0];
+  const R inv = (R)1.0 / s;
+  const int rs = K.hill_stride;
+  if (K.mtd_shared) {
+    R* rec = hills + (n_hills + walker_offset + w) * rs;
+    rec[2] = inv; rec[3] = s;
+  } else {
+    hills[(n_hills * rs + 2) * M + w] = inv;
+    hills[(n_hills * rs + 3) * M + w] = s;
   }
 }
 
@@ -564,6 +597,7 @@ __global__ void fes_grid_kernel(const __grid_constant__ Consts<R> K, const R* __
     const R* h = hills + k * rs * elem_stride;
     const double hx = (double)h[0];
     double ex = -((X - hx) * (X - hx)) / s0 / 2.0;
+    if (K.mtd_adaptive) ex = -(((X - hx) * (X - hx)) * (double)h[2 * elem_stride] / 2.0);  // gaus.py:428-434
     if (cd > 1) {
       const double hy = (double)h[elem_stride];
       ex += -((Y - hy) * (Y - hy)) / s1 / 2.0;

@@ -432,6 +432,7 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
       }
     }
   } else {
+    const bool adaptive = K.mtd_adaptive != 0;  // colvardim 1: 1/sigma^2 of each hill is field 2 of its record
     for (long long i = 0; i < n_hills; i++) {
       const R* h = hills + i * rs * elem_stride;
       R ex = (R)0, ds[ND];
@@ -439,8 +440,9 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
       for (int k = 0; k < ND; k++)
         if (k < cd) {
           const R dc = c[k] - h[k * elem_stride];
-          ds[k] = dc * K.mtd_invsig2[k];
-          ex += (dc * dc) / (R)2.0 * K.mtd_invsig2[k];
+          const R inv = adaptive ? h[2 * elem_stride] : K.mtd_invsig2[k];  // gaus.py:268-275 / :240-248
+          ds[k] = dc * inv;
+          ex += (dc * dc) / (R)2.0 * inv;
         }
       const R vr = h[cd * elem_stride] * nds_exp(-ex);
       v += vr;

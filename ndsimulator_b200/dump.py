@@ -61,8 +61,8 @@ class DumpWriter:
         self.files = []
 
     def write_frames(self, frames, names, hills=None, hills_at=None):
-        """frames: [n][width][walkers] as returned by Engine.drain_frames(); hills = (centers, heights)
-        of the current table (walker 0 / shared) for fix{i}.dat; hills_at(step) = number of hills that
+        """frames: [n][width][walkers] as returned by Engine.drain_frames(); hills = (centers, heights
+        [, per-hill variances of an adaptive table]) of the current table (walker 0 / shared) for fix{i}.dat; hills_at(step) = number of hills that
         existed when the dump row of that step was written."""
         spec = self.spec
         nd, cd = spec.ndim, spec.colvardim
@@ -99,12 +99,14 @@ class DumpWriter:
                     f["thermo"].write(line + "\n")
                     for i, name in enumerate(self.fix_names):
                         if name == "mtd" and hills is not None and w == 0:
-                            c, h = hills
+                            c, h = hills[0], hills[1]
+                            s2 = hills[2] if len(hills) > 2 else None  # adaptive: _sigma_history[idx].flat
                             out = ""
                             upto = len(h) if hills_at is None else min(len(h), hills_at(step))
                             for j in range(self.hills_dumped, upto):
+                                widths = [s2[j]] if s2 is not None else spec.mtd_sigma
                                 out += f"{j} " + " ".join(_fmt(v) for v in c[j]) + " " + \
-                                       " ".join(_fmt(v) for v in spec.mtd_sigma) + " " + _fmt(h[j]) + "\n"
+                                       " ".join(_fmt(v) for v in widths) + " " + _fmt(h[j]) + "\n"
                             f[f"fix{i}"].write(out + "\n")
                         elif name == "umb":
                             f[f"fix{i}"].write("None\n")

@@ -146,10 +146,20 @@ class Engine:
         self._check(self.lib.nds_get_hills(self.h, walker, C.byref(nn), _p(c), _p(w), n))
         return c, w
 
-    def set_hills(self, centers, heights, walker=-1):
+    def get_hill_sigma2(self, walker=0):
+        """Per-hill variances (Gaussian._sigma_history for mtd_adapsig_geo; sigma^2 otherwise)."""
+        n = self.n_hills(walker)
+        s2 = np.empty(n)
+        self._check(self.lib.nds_get_hill_sigma2(self.h, walker, _p(s2), n))
+        return s2
+
+    def set_hills(self, centers, heights, walker=-1, sigma2=None):
         c = _f64(centers).reshape(-1, self.cd)
         w = _f64(heights).reshape(-1)
         self._check(self.lib.nds_set_hills(self.h, walker, len(w), _p(c), _p(w)))
+        if sigma2 is not None:
+            s2 = _f64(sigma2).reshape(-1)
+            self._check(self.lib.nds_set_hill_sigma2(self.h, walker, len(s2), _p(s2)))
 
     def get_vr(self):
         vr = np.empty(self.M)
@@ -217,6 +227,8 @@ class Engine:
             if self.cfg.mtd_shared:
                 c, h = self.get_hills(0)
                 ck.update(hills_centers=c, hills_heights=h)
+                if self.cfg.mtd_adapsig_geo:
+                    ck["hills_sigma2"] = self.get_hill_sigma2(0)
             else:
                 raise NdsError("checkpoint of per-walker hill tables is not implemented")
             ck["vr"] = self.get_vr()
@@ -226,7 +238,7 @@ class Engine:
         self.set_state(ck["x"], ck["v"])
         self.begin()
         if "hills_heights" in ck:
-            self.set_hills(ck["hills_centers"], ck["hills_heights"])
+            self.set_hills(ck["hills_centers"], ck["hills_heights"], sigma2=ck.get("hills_sigma2"))
             self.set_vr(ck["vr"])
         self.set_clock(ck["step"], ck["time"], ck["dep_count"], ck["rescale_count"])
 

@@ -225,6 +225,8 @@ class NDRun:
         if len(frames) == 0:
             return
         hills = self.engine.get_hills(0) if "mtd" in self.spec.biases else None
+        if hills is not None and self.spec.mtd_adapsig_geo:
+            hills = hills + (self.engine.get_hill_sigma2(0),)
         self._dump.write_frames(frames, self.engine.frame_fields(), hills=hills, hills_at=self._hills_at)
         if self.spec.screen:  # ndrun.py:222-224: "<step> temperature: <T>" every dump.freq steps
             names = self.engine.frame_fields()

@@ -217,6 +217,8 @@ def run_traj(cfg, sample_every, v0=None):
         if type(fix).__name__ == "Gaussian" and fix._history is not None:
             rec["hills_centers"] = np.asarray(fix._history, dtype=float).tolist()
             rec["hills_heights"] = tolist(fix._w)
+            if fix.adapsig:
+                rec["hills_sigma2"] = [float(np.asarray(m).reshape(-1)[0]) for m in fix._sigma_history]
             rec["VR"] = float(fix.VR)
     if sim.method == "committor":
         rec["commit_basin"] = int(sim.commit_basin)
@@ -263,6 +265,15 @@ def trajectories():
     out["2d_doublewell_pe_seed6"] = run_traj(
         base_cfg(ndim=2, potential="DoubleWell", x0=[20.0, 12.0], gamma=0.05, seed=6, biases=["pe"],
                  pe_thred=-0.45, steps=1500), 150)
+    # adapsig_geo with 1-D colvars (the only case in which gaus.py:263-288 is finite): constant Jacobian
+    # (XmY), position-dependent Jacobian (Proj5dto1d, note its 2.0*1e-7 term)
+    adap = dict(integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05, mtd_sigma=2.0, mtd_dep_freq=50,
+                mtd_biasf=10.0, mtd_adapsig=True, mtd_adapsig_geo=True)
+    out["2d_mtd_adapsig_geo_XmY_seed2"] = run_traj(
+        base_cfg(ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], seed=2, steps=1200, **adap), 100)
+    out["5d_mtd_adapsig_geo_Proj5dto1d_seed3"] = run_traj(
+        base_cfg(ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
+                 x0=[12.0] * 5, seed=3, steps=1000, **adap), 100)
     dump("trajectories.json", out)
 
 

@@ -65,6 +65,8 @@ def lib():
         L.oracle_n_hills.restype = C.c_int64
         L.oracle_get_hills.argtypes = [C.c_void_p, C.c_int64, _dp, _dp]
         L.oracle_set_hills.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]
+        L.oracle_get_hill_sigma2.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.oracle_set_hill_sigma2.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp]
         L.oracle_eval_at.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]
         L.oracle_fes_grid.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int64,
                                       C.c_double, C.c_double, C.c_int64, _dp]
@@ -207,6 +209,16 @@ class OracleSim:
         c = _f64(np.asarray(centers).reshape(-1, self.cd))
         w = _f64(heights)
         self.L.oracle_set_hills(self.h, walker, len(w), _p(c), _p(w))
+
+    def get_hill_sigma2(self, walker=0):
+        n = self.L.oracle_n_hills(self.h, walker)
+        s2 = np.zeros(n)
+        self.L.oracle_get_hill_sigma2(self.h, walker, _p(s2))
+        return s2
+
+    def set_hill_sigma2(self, sigma2, walker=0):
+        s2 = _f64(sigma2)
+        self.L.oracle_set_hill_sigma2(self.h, walker, len(s2), _p(s2))
 
     def eval_at(self, x):
         x = _f64(np.asarray(x).reshape(self.ndim, -1))

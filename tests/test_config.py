@@ -92,6 +92,12 @@ def test_out_of_scope_is_refused_loudly():
     assert config.parse(base(method="minimize")).integrate == "minimize"
     with pytest.raises(NotImplementedError):
         config.parse(base(biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=2.0, mtd_adapsig=True))
+    with pytest.raises(ValueError):  # adapsig_geo with a 2-D colvar: inf / NaN in the reference (gaus.py:268-275)
+        config.parse(base(biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=2.0, mtd_adapsig=True,
+                          mtd_adapsig_geo=True))
+    a = config.parse(base(colvar_name="XmY", biases=["mtd"], mtd_w=0.1, mtd_sigma=1.5, mtd_biasf=2.0,
+                          mtd_adapsig=True, mtd_adapsig_geo=True)).to_struct()
+    assert a.mtd_adapsig_geo == 1 and a.mtd_sigma[0] == 1.5
 
 
 def test_user_defined_python_plugins_are_rejected():

@@ -111,6 +111,8 @@ def test_trajectory(name):
         assert np.allclose(w, rec["hills_heights"], rtol=1e-10)
         assert np.allclose(c, np.array(rec["hills_centers"]), rtol=1e-10)
         assert o.get_vr()[0] == pytest.approx(rec["VR"], rel=1e-9)
+    if "hills_sigma2" in rec:  # adapsig_geo: Gaussian._sigma_history, J.J^T (first hill) / J.J^T sigma^2
+        assert np.allclose(o.get_hill_sigma2(), rec["hills_sigma2"], rtol=1e-12)
 
 
 def test_mtd_first_hill_heights():

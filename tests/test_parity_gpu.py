@@ -247,6 +247,58 @@ def test_mtd_multi_walker_external_noise(shared):
         assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
 
 
+@pytest.mark.parametrize("case", ["XmY_shared", "Proj5dto1d_per_walker"])
+def test_mtd_adapsig_geo_external_noise(case):
+    """adapsig_geo with a 1-D colvar (gaus.py:162-165,189-192,263-288): every hill carries its own variance
+    J.J^T (first hill of a table) / J.J^T sigma^2 taken at the deposition point.  Hill tables incl. variances,
+    states, VR, the FES grid (gaus.py:428-434) and point evaluations must equal the oracle, which is pinned to
+    the reference's own adaptive runs (tests/golden/trajectories.json)."""
+    M = 10
+    adap = dict(integrate="langevin", gamma=0.1, dt=1.0, temperature=300, mass=1.0, biases=["mtd"], mtd_w=0.05,
+                mtd_sigma=2.0, mtd_dep_freq=50, mtd_biasf=10.0, mtd_adapsig=True, mtd_adapsig_geo=True, steps=600)
+    if case == "XmY_shared":
+        cfg = dict(adap, ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], mtd_shared=True)
+    else:
+        cfg = dict(adap, ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
+                   x0=[12.0] * 5, mtd_shared=False)
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    nd = spec.ndim
+    noise = noise_table(21, 600, nd, M)
+    rng = np.random.RandomState(2)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.5, size=(nd, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, np.zeros((nd, M)))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(600)
+    shared = cfg["mtd_shared"]
+    for wk in (0, M - 1):
+        (ce, we), (co, wo) = eng.get_hills(wk), orc.get_hills(wk)
+        se, so = eng.get_hill_sigma2(wk), orc.get_hill_sigma2(wk)
+        assert len(we) == len(wo) == len(se) == (12 * M if shared else 12)
+        assert np.allclose(we, wo, rtol=1e-9) and np.allclose(ce, co, rtol=1e-9) and np.allclose(se, so, rtol=1e-12)
+    s0 = eng.get_hill_sigma2(0)
+    if case == "XmY_shared":
+        assert np.all(s0[:M] == 2.0) and np.all(s0[M:] == 8.0)       # J = (1, -1): 2, then 2 * sigma^2
+    else:
+        assert np.all(np.abs(s0[:1] - 1.0) < 1e-6) and np.all(np.abs(s0[1:] - 4.0) < 1e-5) and s0[1] != s0[2]
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "fixf", "biase", "totale"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+    assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
+    lo = float(min(ce.min(), co.min())) - 5.0
+    assert scaled_err(eng.fes_grid(lo, 0.25, 120), orc.fes_grid(lo, 0.25, 120)) < 1e-9
+    pts = x0 + 0.3
+    ea, eb = eng.eval_at(pts), orc.eval_at(pts)
+    assert scaled_err(ea["Vb"], eb["Vb"]) < 1e-11 and scaled_err(ea["Fb"], eb["Fb"]) < 1e-11
+    if shared:  # checkpoint / restore carries the variances
+        ck = eng.checkpoint()
+        eng2 = Engine(spec.to_struct())
+        eng2.restore(ck)
+        assert np.array_equal(eng2.get_hill_sigma2(0), s0)
+        assert scaled_err(eng2.eval_at(pts)["Vb"], ea["Vb"]) < 1e-14
+
+
 def test_committor_external_noise():
     """Basin id and exit step must be identical (same inclusive fp64 comparisons, committor.py:127-140)."""
     g = load_golden("committor.json")
