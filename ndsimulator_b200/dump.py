@@ -18,6 +18,7 @@ import os
 
 import numpy as np
 
+_INT_JACOBIAN_CVS = {"ExtractX", "ExtractY", "XmY", "XpY", "Proj5dto1dx0"}  # integer jacob arrays (two.py, five.py:7)
 _BRACKET_CVS = {"ExtractX", "ExtractY", "XmY", "XpY", "Proj5dto1dx0", "Proj5dto1dx2", "Proj5dto1d"}
 
 
@@ -104,9 +105,14 @@ class DumpWriter:
                             out = ""
                             upto = len(h) if hills_at is None else min(len(h), hills_at(step))
                             for j in range(self.hills_dumped, upto):
-                                widths = [s2[j]] if s2 is not None else spec.mtd_sigma
-                                out += f"{j} " + " ".join(_fmt(v) for v in c[j]) + " " + \
-                                       " ".join(_fmt(v) for v in widths) + " " + _fmt(h[j]) + "\n"
+                                if s2 is None:
+                                    widths = " ".join(_fmt(v) for v in spec.mtd_sigma)
+                                elif j == 0 and spec.colvar in _INT_JACOBIAN_CVS:
+                                    # first hill: J.J^T of an INTEGER Jacobian array prints as an int (two.py:8,19,30,41)
+                                    widths = str(int(round(s2[j])))
+                                else:
+                                    widths = _fmt(s2[j])
+                                out += f"{j} " + " ".join(_fmt(v) for v in c[j]) + " " + widths + " " + _fmt(h[j]) + "\n"
                             f[f"fix{i}"].write(out + "\n")
                         elif name == "umb":
                             f[f"fix{i}"].write("None\n")

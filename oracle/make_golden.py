@@ -391,6 +391,13 @@ def dump_files():
         "2d_xmy_nve": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
                            integrate="nve", colvar_name="XmY", temperature=300, dt=1.0, seed=7, steps=20,
                            dump=True, dump_freq=10, screen=False),
+        # adaptive variances are listed in fix0.dat instead of sigma (gaus.py:455-456); "[c]" colvar tokens (A28)
+        "2d_mtd_adapsig_geo_xmy_gamma0": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 30.0],
+                                               method="md", integrate="langevin", gamma=0.0, temperature=300,
+                                               dt=1.0, seed=3, steps=150, colvar_name="XmY", biases=["mtd"],
+                                               mtd_w=0.05, mtd_sigma=2.0, mtd_dep_freq=50, mtd_biasf=10.0,
+                                               mtd_adapsig=True, mtd_adapsig_geo=True, dump=True, dump_freq=50,
+                                               screen=False),
     }
     for name, cfg in cases.items():
         d = tempfile.mkdtemp()

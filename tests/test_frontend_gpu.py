@@ -30,7 +30,8 @@ def assert_same_text(got, want, rtol=1e-9, what=""):
             assert x.startswith("[") == y.startswith("["), (what, i, x, y)
 
 
-@pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve"])
+@pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve",
+                                  "2d_mtd_adapsig_geo_xmy_gamma0"])
 def test_dump_files_match_reference(name, tmp_path):
     """pos/force/velocity/colvar/thermo/fix*.dat of deterministic runs against the files the Python
     reference wrote (tests/golden/dump_files.json), including the lagged thermo row (A16)."""
