@@ -43,6 +43,7 @@ struct Consts {
   int pot, cv, tcv, integ, method, noise, bias_mask, n_umb, n_basins;
   int mtd_shared, hill_stride;  // reals per hill record (cd + 1, padded to 4 when cd == 2 or adaptive)
   int mtd_adaptive;             // per-hill variance (adapsig_geo, colvardim 1): record = (c, w, 1/s, s)
+  int hill_hidx;                // field of the height: 2 in the 4-word records (c0, c1 | 0, w, log2 w), else cd
   // units / integrator (engines/md.py:81-99, data.py:26-28, constant.py)
   R m, inv_m, dt, kB, kBT;
   R c1, c2, c3, c4, c5, v_target;

@@ -188,7 +188,11 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
                 (c.pe_enabled ? BIAS_PE : 0) | ((c.n_umb > 0 && c.umb_per_walker) ? BIAS_UMB_WALKER : 0);
   K.mtd_shared = c.mtd_shared;
   K.mtd_adaptive = (c.mtd_enabled && c.mtd_adapsig_geo) ? 1 : 0;
-  K.hill_stride = (K.cd == 2 || K.mtd_adaptive) ? 4 : K.cd + 1;
+  // 4-word records (c0, c1 | 0, w, log2 w) for every shared table with colvardim <= 2 (mtd_block streams them
+  // through TMA tiles); adaptive records are (c, w, 1/s, s); everything else is (c_0..c_{cd-1}, w)
+  const bool rec4 = !K.mtd_adaptive && (K.cd == 2 || (K.cd == 1 && c.mtd_shared));
+  K.hill_stride = (rec4 || K.mtd_adaptive) ? 4 : K.cd + 1;
+  K.hill_hidx = rec4 ? 2 : K.cd;
   const double m = au_mass_() * c.mass;        // data.py:27-28
   const double kBT = kB_ * c.temperature;      // data.py:26
   // Minimize multiplies the configured time step by 10 (engines/minimize.py:18)
@@ -266,6 +270,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
       K.mtd_sig2[k] = (R)(c.mtd_sigma[k] * c.mtd_sigma[k]);
       K.mtd_pre[k] = (R)(std::sqrt(kfast) / c.mtd_sigma[k]);
     }
+    for (int k = K.cd; k < NDS_MAX_CV; k++) { K.mtd_invsig2[k] = (R)0; K.mtd_pre[k] = (R)1; }  // unused components
     K.mtd_kBdT = (R)(kB_ * ((c.mtd_biasf - 1) * c.temperature));  // gaus.py:102-103
   }
   K.pe_thred = (R)c.pe_thred;
@@ -475,7 +480,7 @@ struct Engine : nds_engine {
     const int64_t n = hill_elems();
     if (cfg.mtd_shared) {
       const int64_t nrec = n / K.hill_stride;
-      fill_hills_kernel<R><<<(unsigned)((nrec + 255) / 256), 256, 0, stream>>>(nrec, K.hill_stride, cd, d_hills);
+      fill_hills_kernel<R><<<(unsigned)((nrec + 255) / 256), 256, 0, stream>>>(nrec, K.hill_stride, K.hill_hidx, d_hills);
       CU(cudaGetLastError());
     } else {
       CU(cudaMemsetAsync(d_hills, 0, sizeof(R) * (size_t)n, stream));
@@ -507,7 +512,7 @@ struct Engine : nds_engine {
         kernel_name = pv->name;
       }
     }
-    if (c.mtd_enabled && c.mtd_shared && cd == 2 && c.method == NDS_METHOD_MD && !dumping) {
+    if (c.mtd_enabled && c.mtd_shared && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping) {
       cudaDeviceProp prop;
       CU(cudaGetDeviceProperties(&prop, c.device));
       const MtdVariant* mv = pick_mtd_variant(c, K.bias_mask, prop.multiProcessorCount);
@@ -1158,7 +1163,7 @@ struct Engine : nds_engine {
     for (int64_t i = 0; i < n_hills; i++) {
       for (int k = 0; k < cd; k++)
         if (centers) centers[i * cd + k] = h[(size_t)((i * rs + k) * es + off)];
-      if (heights) heights[i] = h[(size_t)((i * rs + cd) * es + off)];
+      if (heights) heights[i] = h[(size_t)((i * rs + K.hill_hidx) * es + off)];
     }
     return 0;
   }
@@ -1172,8 +1177,8 @@ struct Engine : nds_engine {
       std::vector<double> h((size_t)(n * rs), 0.0);
       for (int64_t i = 0; i < n; i++) {
         for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
-        h[(size_t)(i * rs + cd)] = heights[i];
-        for (int k = cd + 1; k < rs; k++) h[(size_t)(i * rs + k)] = std::log2(heights[i]);
+        h[(size_t)(i * rs + K.hill_hidx)] = heights[i];
+        for (int k = K.hill_hidx + 1; k < rs; k++) h[(size_t)(i * rs + k)] = std::log2(heights[i]);
         if (K.mtd_adaptive) {  // default variance sigma^2 until nds_set_hill_sigma2 supplies the history
           h[(size_t)(i * rs + 2)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
           h[(size_t)(i * rs + 3)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
@@ -1189,7 +1194,7 @@ struct Engine : nds_engine {
         if (walker >= 0 && w != walker) continue;
         for (int64_t i = 0; i < n; i++) {
           for (int k = 0; k < cd; k++) h[(size_t)((i * rs + k) * M + w)] = centers[i * cd + k];
-          h[(size_t)((i * rs + cd) * M + w)] = heights[i];
+          h[(size_t)((i * rs + K.hill_hidx) * M + w)] = heights[i];
           if (K.mtd_adaptive) {
             h[(size_t)((i * rs + 2) * M + w)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
             h[(size_t)((i * rs + 3) * M + w)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];

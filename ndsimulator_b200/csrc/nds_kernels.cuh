@@ -496,18 +496,19 @@ __global__ void deposit_kernel(const __grid_constant__ Consts<R> K, long long M,
   const bool live = alive ? alive[w] != 0 : true;
   R h = first ? K.mtd_w : K.mtd_w * nds_exp(-vr[w] / K.mtd_kBdT);
   if (!live) h = (R)0;
-  const int cd = K.cd, rs = K.hill_stride;
+  const int cd = K.cd, rs = K.hill_stride, hi = K.hill_hidx;
   if (K.mtd_shared) {
     R* rec = hills + (n_hills + walker_offset + w) * rs;
     for (int k = 0; k < cd; k++) rec[k] = colv[k * M + w];
-    rec[cd] = h;
-    // colvardim 2: the 4th word carries log2(height) for the MUFU-bound fp32 loop of mtd_block
+    for (int k = cd; k < hi; k++) rec[k] = (R)0;  // colvardim 1 in a 4-word record: second centre = 0
+    rec[hi] = h;
+    // 4-word records: the last word carries log2(height) for the MUFU-bound fp32 loop of mtd_block
     // (-inf for a zero-height record, which then contributes exactly 0)
     if (!K.mtd_adaptive)
-      for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
+      for (int k = hi + 1; k < rs; k++) rec[k] = (R)log2((double)h);
   } else {
     for (int k = 0; k < cd; k++) hills[(n_hills * rs + k) * M + w] = colv[k * M + w];
-    hills[(n_hills * rs + cd) * M + w] = h;
+    hills[(n_hills * rs + hi) * M + w] = h;
   }
 }
 
@@ -557,11 +558,12 @@ __global__ void deposit_p2p_kernel(const __grid_constant__ Consts<R> K, long lon
   const bool live = alive ? alive[w] != 0 : true;
   R h = first ? K.mtd_w : K.mtd_w * nds_exp(-vr[w] / K.mtd_kBdT);
   if (!live) h = (R)0;
-  const int cd = K.cd, rs = K.hill_stride;
+  const int cd = K.cd, rs = K.hill_stride, hi = K.hill_hidx;
   R rec[8];
   for (int k = 0; k < cd; k++) rec[k] = colv[k * M + w];
-  rec[cd] = h;
-  for (int k = cd + 1; k < rs; k++) rec[k] = (R)log2((double)h);
+  for (int k = cd; k < hi; k++) rec[k] = (R)0;
+  rec[hi] = h;
+  for (int k = hi + 1; k < rs; k++) rec[k] = (R)log2((double)h);
   const long long slot = (n_hills + walker_offset + w) * rs;
   for (int r = 0; r < nranks; r++) {
     R* dst = tables[r] + slot;
@@ -602,7 +604,7 @@ __global__ void fes_grid_kernel(const __grid_constant__ Consts<R> K, const R* __
       const double hy = (double)h[elem_stride];
       ex += -((Y - hy) * (Y - hy)) / s1 / 2.0;
     }
-    acc += (double)h[cd * elem_stride] * exp(ex);
+    acc += (double)h[K.hill_hidx * elem_stride] * exp(ex);
   }
   grid[p] = acc;
 }
@@ -657,10 +659,10 @@ __global__ void compact_swap_kernel(long long M, int nd, int cd, const int* hole
 
 // empty hill records: height 0, log2(height) = -inf
 template <typename R>
-__global__ void fill_hills_kernel(long long n_records, int rs, int cd, R* hills) {
+__global__ void fill_hills_kernel(long long n_records, int rs, int hidx, R* hills) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_records) return;
-  for (int k = 0; k < rs; k++) hills[i * rs + k] = (k > cd) ? (R)(-INFINITY) : (R)0;
+  for (int k = 0; k < rs; k++) hills[i * rs + k] = (k > hidx) ? (R)(-INFINITY) : (R)0;
 }
 
 template <typename A, typename B>

@@ -215,7 +215,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   const int bias_mask = S::BIAS >= 0 ? S::BIAS : K.bias_mask;
   const int other_bias = bias_mask & ~BIAS_MTD;
   const bool ext_noise = S::NOISE >= 0 ? (S::NOISE == NDS_NOISE_EXTERNAL) : (K.noise == NDS_NOISE_EXTERNAL);
-  constexpr int cd = 2;
+  const int cd = S::CV >= 0 ? cv_dim(S::CV, ND) : K.cd;  // 1 or 2; a 1-D colvar runs the 2-D hill pass with c1 = 0
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -234,7 +234,8 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
   for (int k = 0; k < ND; k++) { wb.k[k] = (R)0; wb.r0[k] = (R)0; }
   if ((bias_mask & BIAS_UMB_WALKER) && owner) {
 #pragma unroll
-    for (int k = 0; k < cd; k++) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
+    for (int k = 0; k < ND; k++)
+      if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
   const unsigned long long gid = (unsigned long long)(A.walker_offset + (owner ? w : 0));
 
@@ -253,7 +254,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
 #pragma unroll
     for (int q = 0; q < W; q++) {
       c0[q] = __shfl_sync(0xffffffffu, e.cv.c[0], q);
-      c1[q] = __shfl_sync(0xffffffffu, e.cv.c[1], q);
+      c1[q] = cd > 1 ? __shfl_sync(0xffffffffu, e.cv.c[1], q) : (R)0;
     }
     R Vm, g[ND];
 #pragma unroll
@@ -369,7 +370,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
       v2 += v[d] * v[d];
     }
     A.colv[0 * M + w] = e.cv.c[0];
-    A.colv[1 * M + w] = e.cv.c[1];
+    if (cd > 1) A.colv[1 * M + w] = e.cv.c[1];
     const R ke = v2 * K.m / (R)2.0;
     A.thermo[0 * M + w] = A.begin_mode ? ke / (R)ND * (R)2.0 / K.kB : ke / (R)ND / K.kB * (R)2.0;
     A.thermo[1 * M + w] = e.pe;

@@ -444,7 +444,7 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
           ds[k] = dc * inv;
           ex += (dc * dc) / (R)2.0 * inv;
         }
-      const R vr = h[cd * elem_stride] * nds_exp(-ex);
+      const R vr = h[K.hill_hidx * elem_stride] * nds_exp(-ex);
       v += vr;
 #pragma unroll
       for (int k = 0; k < ND; k++)

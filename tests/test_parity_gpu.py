@@ -486,6 +486,55 @@ def test_mtd_block_many_tiles(integrate):
     assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
 
 
+@pytest.mark.parametrize("case", ["XmY_2d", "Proj5dto1d_umb"])
+def test_mtd_block_one_dimensional_colvar(case):
+    """Shared hill table over a 1-D colvar: the records become (c, 0, w, log2 w) and the TMA-tiled 2-D hill pass
+    runs with c1 = 0 and 1/sigma_1^2 = 0.  Against the oracle with external noise (fp64), plus fp32 vs fp64 of the
+    bias on the final table, FES grid and hill round trip."""
+    M, nsteps = 37, 400
+    base = dict(mass=1.0, integrate="langevin", gamma=0.1, dt=1.0, temperature=300, mtd_w=0.05, mtd_sigma=1.5,
+                mtd_dep_freq=10, mtd_biasf=10.0, steps=nsteps, mtd_shared=True)
+    if case == "XmY_2d":
+        cfg = dict(base, ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], biases=["mtd"])
+    else:
+        cfg = dict(base, ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
+                   x0=[12.0] * 5, biases=["umb", "mtd"], umb_k=0.02, umb_r0=[15.0])
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=100)
+    assert eng.kernel_name.startswith("mtd_block"), eng.kernel_name
+    nd = spec.ndim
+    noise = noise_table(17, nsteps, nd, M)
+    rng = np.random.RandomState(4)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.5, size=(nd, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, np.zeros((nd, M)))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(nsteps)
+    (ce, we), (co, wo) = eng.get_hills(), orc.get_hills()
+    assert ce.shape == co.shape == (40 * M, 1) and 40 * M > 1024
+    assert np.allclose(we, wo, rtol=1e-9) and np.allclose(ce, co, rtol=1e-9)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "f", "fixf", "colv", "biase", "pe", "totale"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
+    assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
+    lo = float(co.min()) - 4.0
+    assert scaled_err(eng.fes_grid(lo, 0.2, 100), orc.fes_grid(lo, 0.2, 100)) < 1e-9
+    # fp32 instantiation (MUFU.EX2, packed FP32) on the same table
+    spec32 = spec_from(cfg, n_walkers=M, precision="f32")
+    e32 = Engine(spec32.to_struct())
+    assert e32.kernel_name.startswith("mtd_block")
+    e32.set_state(a["x"], a["v"])
+    e32.begin()
+    e32.set_hills(ce, we)
+    e32.set_clock(nsteps + 1, nsteps + 1.0, 41)   # no deposition due: the launch runs on the frozen table
+    e32.run(1)
+    st = e32.get_state()
+    ref = eng.eval_at(st["x"])                   # fp64, generic hill sum, at the positions fp32 ended on
+    assert e32.n_hills() == 40 * M
+    assert scaled_err(st["biase"], ref["Vb"]) < 2e-5
+    assert scaled_err(st["fixf"], ref["Fb"]) < 2e-4
+
+
 def test_mtd_block_fp32_close_to_fp64():
     """fp32 mtd_block (prescaled exponent, MUFU.EX2) vs the fp64 instantiation on a frozen table."""
     M = 300
