@@ -55,6 +55,8 @@ struct Consts {
   R gA[4], ga[4], gb[4], gc[4], gx[4], gy[4];
   // fp32 fast form: G = k*grad (k = log2(e)/2), A2 = A / k  (see nds_physics.cuh)
   R fa[4], fb[4], fc[4], fA[4];
+  BmScale bm_c2;  // Box-Muller radius constants scaled by c2^2 (fp32 first-order Langevin: noise arrives as c2 * xi)
+  R flA[4];  // log2 |fA|: the amplitude rides in the exponent, its (class-constant) sign in the FMA operand
   R th_D, th_E, th_x1, th_y1, th_ref;
   R rot;            // 1/sqrt(2) as NumPy computes it (colvars/two.py:53)
   // path colvar (colvars/path.py): reference points [n][path_dim], indices [n] in device memory

@@ -204,6 +204,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   if (c.integrator == NDS_INT_LANGEVIN) {      // md.py:83-86
     const double c1 = std::exp(-gamma * dt / 2.0);
     K.c1 = (R)c1; K.c2 = (R)std::sqrt((1 - c1 * c1) * kBT / m);
+    K.bm_c2 = bm_scale(std::sqrt((1 - c1 * c1) * kBT / m));
   } else if (c.integrator == NDS_INT_LANGEVIN2) {  // md.py:87-97
     const double frdt = (1.0 - std::exp(-gamma * dt / 2.0)) * 8.0;
     const double sigma = std::sqrt(2 * kBT * frdt / m);
@@ -249,6 +250,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
     K.gx[i] = (R)gx[i]; K.gy[i] = (R)gy[i];
     K.fa[i] = (R)(2 * a[i] * kfast); K.fb[i] = (R)(b[i] * kfast); K.fc[i] = (R)(2 * cc[i] * kfast);
     K.fA[i] = (R)(A[i] / kfast);
+    K.flA[i] = (R)(A[i] != 0 ? std::log2(std::fabs(A[i] / kfast)) : 0.0);
   }
   K.rot = (R)(1.0 / std::sqrt(2.0));  // two.py:53
   if (pot == NDS_POT_DOUBLEWELL1D) {  // double_well.py:9-14

@@ -122,6 +122,9 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
   constexpr int CG = noise_calls(NN);
+  // fp32 first-order Langevin: the noise enters only as c2 * xi (md.py:170,196), so the Box-Muller radius is
+  // generated already multiplied by c2 and xi[] below holds c2 * xi
+  constexpr bool PRESCALED = is_f32<R>::value && INTEG == NDS_INT_LANGEVIN;
 
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
@@ -218,7 +221,8 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CG; c++) {
         R z6[NDS_NPC];
-        normals6_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z6);
+        if constexpr (PRESCALED) normals6_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z6, K.bm_c2);
+        else normals6_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z6);
 #pragma unroll
         for (int j = 0; j < NDS_NPC; j++)
           if (NDS_NPC * c + j < G * NN) zb[NDS_NPC * c + j] = z6[j];
@@ -236,6 +240,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
 #pragma unroll
             for (int d = 0; d < ND; d++) {
               xi[d] = (R)row[(long long)d * M];
+              if (PRESCALED) xi[d] = K.c2 * xi[d];
               if (INTEG == NDS_INT_LANGEVIN2) eta[d] = (R)row[(long long)(ND + d) * M];
             }
           } else {
@@ -275,7 +280,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           if constexpr (is_f32<R>::value) {
             if (INTEG == NDS_INT_LANGEVIN) {
               v[d] = fmaf(K.hdtm, f[d], v[d]);
-              v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
+              v[d] = fmaf(K.c1, v[d], xi[d]);  // xi = c2 * normal (PRESCALED)
               dx = v[d] * K.dt;
             } else if (INTEG == NDS_INT_LANGEVIN2) {
               // v += c1 f/m - c2 v + c3 xi - c4 eta  ==  a v + (c1/m) f + c3 xi - c4 eta,  a = 1 - c2
@@ -310,7 +315,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           if constexpr (is_f32<R>::value) {
             if (INTEG == NDS_INT_LANGEVIN) {
               v[d] = fmaf(K.hdtm, f[d], v[d]);
-              v[d] = fmaf(K.c1, v[d], K.c2 * xi[d]);
+              v[d] = fmaf(K.c1, v[d], xi[d]);
             } else if (INTEG == NDS_INT_LANGEVIN2) {
               v[d] = fmaf(K.l2_a, v[d], fmaf(K.l2_c1m, f[d], fmaf(K.c3, xi[d], -(K.c4 * eta[d]))));
             } else {

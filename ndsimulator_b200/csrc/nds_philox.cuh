@@ -75,19 +75,27 @@ constexpr int NDS_NPC = 6;  // normals per Philox call
 // Two standard normals from two 21-bit fields (Box-Muller).
 // fp32: u1 in (0,1] feeds lg2.approx / sqrt.approx, the angle uses sin/cos.approx (MUFU pipe);
 // fp64: full-precision log / sqrt / sincospi on the same 21-bit uniforms.
-__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, float& z0, float& z1) {
+// Radius constants: r^2 = ra * lg2(n) + rb with (ra, rb) = (-2 ln2, 42 ln2) * scale^2; scale = 1 gives
+// standard normals, scale = c2 gives the noise term c2 * xi of the Langevin kick without a multiply.
+struct BmScale { float ra, rb; };
+__host__ __device__ inline BmScale bm_scale(double scale) {
+  return BmScale{(float)(-1.3862943611198906 * scale * scale), (float)(29.112181583517703 * scale * scale)};
+}
+
+__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, float& z0, float& z1,
+                                             BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
   // u1 = n * 2^-21 with n = a + 1 in [1, 2^21]  (never 0):
   //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 21)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
   // angle = 2 pi * b * 2^-21                   -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
   const float n = (float)(a + 1u);
   // |.|: at n = 2^21 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
-  const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), -1.3862943611198906f, 29.112181583517703f)));
+  const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), k.ra, k.rb)));
   const float ang = (float)b * 2.9960562263391724e-06f;  // 2 pi 2^-21
   z0 = r * cos_approx(ang);
   z1 = r * sin_approx(ang);
 }
 
-__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, double& z0, double& z1) {
+__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, double& z0, double& z1, BmScale = BmScale{0.f, 0.f}) {
   const double u1 = ((double)a + 1.0) * 4.76837158203125e-07;  // (0, 1], 2^-21
   const double u2 = (double)b * 4.76837158203125e-07;          // [0, 1)
   const double r = sqrt(-2.0 * log(u1));
@@ -102,27 +110,29 @@ __device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, double& z0,
 // bits of word 1, low 11 bits of word 2 | low 10 bits of word 3).
 template <typename R>
 __device__ __forceinline__ void normals6(const PhiloxKeys& rk, unsigned long long call,
-                                         unsigned long long walker, R (&z)[NDS_NPC]) {
+                                         unsigned long long walker, R (&z)[NDS_NPC],
+                                         BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
   const u32x4 r = philox4x32_10(
       u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
-  box_muller21(r.x >> 11, r.y >> 11, z[0], z[1]);
-  box_muller21(r.z >> 11, r.w >> 11, z[2], z[3]);
-  box_muller21((r.x & 0x7FFu) | ((r.y & 0x3FFu) << 11), (r.z & 0x7FFu) | ((r.w & 0x3FFu) << 11), z[4], z[5]);
+  box_muller21(r.x >> 11, r.y >> 11, z[0], z[1], k);
+  box_muller21(r.z >> 11, r.w >> 11, z[2], z[3], k);
+  box_muller21((r.x & 0x7FFu) | ((r.y & 0x3FFu) << 11), (r.z & 0x7FFu) | ((r.w & 0x3FFu) << 11), z[4], z[5], k);
 }
 
 // f2: the walker pair (walker_a, walker_b), one Philox call each (neighbours, or any two compacted lanes)
 template <typename R>
 __device__ __forceinline__ void normals6_pair(const PhiloxKeys& rk, unsigned long long call,
-                                              unsigned long long walker, unsigned long long, R (&z)[NDS_NPC]) {
-  normals6<R>(rk, call, walker, z);
+                                              unsigned long long walker, unsigned long long, R (&z)[NDS_NPC],
+                                              BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
+  normals6<R>(rk, call, walker, z, k);
 }
 template <>
 __device__ __forceinline__ void normals6_pair<f2>(const PhiloxKeys& rk, unsigned long long call,
                                                   unsigned long long walker_a, unsigned long long walker_b,
-                                                  f2 (&z)[NDS_NPC]) {
+                                                  f2 (&z)[NDS_NPC], BmScale k) {
   float a[NDS_NPC], b[NDS_NPC];
-  normals6<float>(rk, call, walker_a, a);
-  normals6<float>(rk, call, walker_b, b);
+  normals6<float>(rk, call, walker_a, a, k);
+  normals6<float>(rk, call, walker_b, b, k);
 #pragma unroll
   for (int j = 0; j < NDS_NPC; j++) z[j] = f2(a[j], b[j]);
 }

@@ -274,23 +274,27 @@ NDS_DEV void cv_pullback(int cv, R rot, const R (&x)[ND], const CvOut<R, ND>& o,
 // gradient force g = -dV/dq.   potentials/mueller.py:30-44, potentials/three_hole.py:36-50.
 // BMASK: bit i set when term i has a non-zero cross coefficient b_i (class constants of the reference:
 // Mueller 0b1100, ThreeHole 0); lets the fp32 form drop the b terms at compile time.
-template <typename R, bool ENERGY, int BMASK = 0xF>
+// NMASK: bit i set when the amplitude A_i is negative (class constants too: Mueller 0b0111, ThreeHole 0b1110).
+template <typename R, bool ENERGY, int BMASK = 0xF, int NMASK = 0x0>
 NDS_DEV void four_gauss(const Consts<R>& K, R q0, R q1, R& V, R& g0, R& g1) {
   if constexpr (is_f32<R>::value) {
     // fast form: G = k * grad(exponent) with k = log2(e)/2, so that  exponent*log2(e) = dx*Gx + dy*Gy
-    // feeds MUFU.EX2 directly and the force is (A/k) * 2^s * G.  9-11 FP32 ops + 1 MUFU per term.
+    // feeds MUFU.EX2 directly; |A/k| rides in the exponent as log2 and the sign of A is an operand
+    // negation, so the force is +-2^s' * G.  8-10 FP32 ops + 1 MUFU per term.
     R fx = 0.f, fy = 0.f, e = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const R dx = q0 - K.gx[i], dy = q1 - K.gy[i];
       const bool cross = (BMASK >> i) & 1;
+      const bool neg = (NMASK >> i) & 1;
       const R Gx = cross ? fmaf(K.fb[i], dy, K.fa[i] * dx) : K.fa[i] * dx;
       const R Gy = cross ? fmaf(K.fb[i], dx, K.fc[i] * dy) : K.fc[i] * dy;
-      const R s = fmaf(dy, Gy, dx * Gx);
-      const R t = K.fA[i] * nds_exp2(s);
-      if (i == 0) { fx = -t * Gx; fy = -t * Gy; }
-      else { fx = fmaf(-t, Gx, fx); fy = fmaf(-t, Gy, fy); }
-      if (ENERGY) e = (i == 0) ? t : e + t;
+      const R s = fmaf(dy, Gy, fmaf(dx, Gx, K.flA[i]));
+      const R u = nds_exp2(s);  // |A_i| / k * exp(exponent)
+      // force = -A_i e^.. grad(exponent): for a negative amplitude that is +u G
+      if (i == 0) { fx = neg ? u * Gx : -u * Gx; fy = neg ? u * Gy : -u * Gy; }
+      else { fx = neg ? fmaf(u, Gx, fx) : fmaf(-u, Gx, fx); fy = neg ? fmaf(u, Gy, fy) : fmaf(-u, Gy, fy); }
+      if (ENERGY) e = (i == 0) ? (neg ? -u : u) : (neg ? e - u : e + u);
     }
     g0 = fx; g1 = fy;
     if (ENERGY) V = e * (R)0.72134752044448170368;  // k: A = fA * k
@@ -327,7 +331,7 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
   if constexpr (ND == 2) {
     switch (pot) {
       case NDS_POT_MUELLER2D: {  // mueller.py:25-45
-        four_gauss<R, ENERGY, 0xC>(K, x[0], x[1], V, f[0], f[1]);
+        four_gauss<R, ENERGY, 0xC, 0x7>(K, x[0], x[1], V, f[0], f[1]);
       } break;
       case NDS_POT_DOUBLEWELL: {  // double_well.py:44-53
         const R a0 = x[0] - K.dw_x1[0], a1 = x[1] - K.dw_x1[1];
@@ -367,8 +371,8 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
 #pragma unroll
       for (int d = 0; d < ND; d++) g[d] = (R)0;
       R v = (R)0;
-      if (threehole) four_gauss<R, ENERGY, 0x0>(K, o.c[0], o.c[1], v, g[0], g[1]);
-      else four_gauss<R, ENERGY, 0xC>(K, o.c[0], o.c[1], v, g[0], g[1]);
+      if (threehole) four_gauss<R, ENERGY, 0x0, 0xE>(K, o.c[0], o.c[1], v, g[0], g[1]);
+      else four_gauss<R, ENERGY, 0xC, 0x7>(K, o.c[0], o.c[1], v, g[0], g[1]);
       if (threehole) {  // quartic confinement, three_hole.py:51-55
         const R dx = o.c[0] - K.th_x1, dy = o.c[1] - K.th_y1;
         const R dx2 = dx * dx, dy2 = dy * dy;
