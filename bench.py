@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c3": 128.0, "c4": 289.0}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r01_*_raw.csv) at the default walker counts
-NCU_DRAM_BYTES_PER_LAUNCH = {"c2": 23.47e6, "c4": 7.37e6, "c5": 1.59e6}  # SURVEY.md section 8d (algorithmic, fixed)
+NCU_DRAM_BYTES_PER_LAUNCH = {"c2": 22.77e6, "c4": 7.37e6, "c5": 1.59e6}  # SURVEY.md section 8d (algorithmic, fixed)
 L2_FLUSH_BYTES = 256 << 20
 
 
