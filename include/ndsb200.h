@@ -60,7 +60,11 @@ enum {
   NDS_POT_GAUSSIAN = 8,    /* potentials/misc.py:32-43 (factory default, _build.py:10) */
   NDS_POT_FLAT1D = 9,      /* potentials/flat.py:17-24 */
   NDS_POT_FLAT2D = 10,     /* potentials/flat.py:5-14 */
-  NDS_POT_COUNT = 11
+  NDS_POT_HARMONIC_QUARTIC = 11, /* EXTENSION, no reference class: separable N-D well
+                                    V = sum_d k_d u_d^2 / 2 + q_d u_d^4 / 4, u = x - centre; ndim 1, 2 or 5.
+                                    pot_params: k[0..4], q[5..9], centre[10..14].  Pinned analytically
+                                    (harmonic velocity-Verlet map), not against the reference.           */
+  NDS_POT_COUNT = 12
 };
 
 /* colvar / true_colvar: class names of ndsimulator/colvars (colvars/_build.py:10-19) */

@@ -34,6 +34,7 @@ POTENTIALS = {
     "Gaussian": (8, 2, False),
     "Flat1d": (9, 1, False),
     "Flat2d": (10, 2, False),
+    "HarmonicQuartic": (11, None, False),  # extension (no reference class): ndim 1, 2 or 5
 }
 
 # class names of ndsimulator/colvars -> (id, required ndim or None, colvardim or None(=ndim))

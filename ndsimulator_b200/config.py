@@ -259,7 +259,7 @@ def parse(config: dict) -> RunSpec:
     pot = _builtin_name(cfg.get("potential", "Gaussian"), "potentials", _abi.POTENTIALS, "potential")
     spec.potential = pot
     _, pot_ndim, needs_tcv = _abi.POTENTIALS[pot]
-    assert ndim == pot_ndim, f"potential {pot} has ndim={pot_ndim} (potential.py:12)"
+    assert pot_ndim is None or ndim == pot_ndim, f"potential {pot} has ndim={pot_ndim} (potential.py:12)"
     pp = [0.0] * 16
     if pot.startswith("Mueller"):
         from .constant import lscale
@@ -279,6 +279,17 @@ def parse(config: dict) -> RunSpec:
         pp[2:4] = list(np.asarray(pick(cfg, "x1", "potential", [20.0, 10.0]), dtype=float))
         pp[4:6] = list(np.asarray(pick(cfg, "x2", "potential", [20.0, 30.0]), dtype=float))
         pp[6] = pick(cfg, "sigma", "potential", 10)
+    elif pot == "HarmonicQuartic":  # extension: V = sum_d k_d u_d^2 / 2 + q_d u_d^4 / 4, u = x - center
+        def per_dim(key, default):
+            v = np.asarray(pick(cfg, key, "potential", default), dtype=float).reshape(-1)
+            if v.size == 1:
+                v = np.repeat(v, ndim)
+            if v.size != ndim:
+                raise ValueError(f"potential_{key} needs 1 or ndim={ndim} values")
+            return [float(t) for t in v]
+        pp[0:ndim] = per_dim("k", 0.01)
+        pp[5:5 + ndim] = per_dim("q", 0.0)
+        pp[10:10 + ndim] = per_dim("center", 0.0)
     spec.pot_params = [float(v) for v in pp]
 
     # ---- colvars (colvars/_build.py:4-23)

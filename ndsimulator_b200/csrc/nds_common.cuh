@@ -58,6 +58,7 @@ struct Consts {
   BmScale bm_c2;  // Box-Muller radius constants scaled by c2^2 (fp32 first-order Langevin: noise arrives as c2 * xi)
   R flA[4];  // log2 |fA|: the amplitude rides in the exponent, its (class-constant) sign in the FMA operand
   R th_D, th_E, th_x1, th_y1, th_ref;
+  R hq_k[5], hq_q[5], hq_c[5];  // NDS_POT_HARMONIC_QUARTIC (extension)
   R rot;            // 1/sqrt(2) as NumPy computes it (colvars/two.py:53)
   // path colvar (colvars/path.py): reference points [n][path_dim], indices [n] in device memory
   const R* path_ref; const R* path_ind; int n_path, path_dim;

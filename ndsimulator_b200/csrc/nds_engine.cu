@@ -96,7 +96,7 @@ static int fail(nds_engine* e, const char* fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------------ validation
-static const int kPotNdim[NDS_POT_COUNT] = {2, 5, 5, 1, 2, 2, 5, 2, 2, 1, 2};
+static const int kPotNdim[NDS_POT_COUNT] = {2, 5, 5, 1, 2, 2, 5, 2, 2, 1, 2, 0};  // 0: any supported ndim
 static const bool kPotNeedsTcv[NDS_POT_COUNT] = {false, true, true, false, false, true, true,
                                                  false, false, false, false};
 
@@ -123,7 +123,7 @@ static int validate(const nds_config* c) {
   if (c->ndim != 1 && c->ndim != 2 && c->ndim != 5)
     return fail(nullptr, "ndim=%d: the built-in potentials have ndim 1, 2 or 5", c->ndim);
   if (c->potential < 0 || c->potential >= NDS_POT_COUNT) return fail(nullptr, "unknown potential id %d", c->potential);
-  if (kPotNdim[c->potential] != c->ndim)  // potentials/potential.py:12 (assert pointer.ndim == self.ndim)
+  if (kPotNdim[c->potential] != 0 && kPotNdim[c->potential] != c->ndim)  // potentials/potential.py:12 (assert pointer.ndim == self.ndim)
     return fail(nullptr, "potential %d has ndim=%d, run has ndim=%d", c->potential, kPotNdim[c->potential], c->ndim);
   if (nds_colvar_dim(c->colvar, c->ndim) < 0) return fail(nullptr, "colvar %d is not defined for ndim=%d", c->colvar, c->ndim);
   if (nds_colvar_dim(c->true_colvar, c->ndim) < 0) return fail(nullptr, "true_colvar %d is not defined for ndim=%d", c->true_colvar, c->ndim);
@@ -252,6 +252,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
     K.fA[i] = (R)(A[i] / kfast);
     K.flA[i] = (R)(A[i] != 0 ? std::log2(std::fabs(A[i] / kfast)) : 0.0);
   }
+  for (int d = 0; d < 5; d++) { K.hq_k[d] = (R)c.pot_params[d]; K.hq_q[d] = (R)c.pot_params[5 + d]; K.hq_c[d] = (R)c.pot_params[10 + d]; }
   K.rot = (R)(1.0 / std::sqrt(2.0));  // two.py:53
   if (pot == NDS_POT_DOUBLEWELL1D) {  // double_well.py:9-14
     K.dw_K1 = (R)c.pot_params[0]; K.dw_K2 = (R)c.pot_params[1];

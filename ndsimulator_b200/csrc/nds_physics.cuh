@@ -319,6 +319,15 @@ NDS_DEV void pot_eval(const Consts<R>& K, int pot, int tcv, const R (&x)[ND], R&
   V = (R)0;
 #pragma unroll
   for (int d = 0; d < ND; d++) f[d] = (R)0;
+  if (pot == NDS_POT_HARMONIC_QUARTIC) {  // extension: separable harmonic + quartic well
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      const R u = x[d] - K.hq_c[d], u2 = u * u;
+      if (ENERGY) V += K.hq_k[d] * u2 / (R)2.0 + K.hq_q[d] * (u2 * u2) / (R)4.0;
+      f[d] = -(K.hq_k[d] * u) - K.hq_q[d] * (u2 * u);
+    }
+    return;
+  }
   if constexpr (ND == 1) {
     if (pot == NDS_POT_DOUBLEWELL1D) {  // double_well.py:16-25
       const R d1 = x[0] - K.dw_x1[0], d2 = x[0] - K.dw_x2[0];
