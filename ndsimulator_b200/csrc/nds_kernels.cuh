@@ -200,6 +200,14 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   double time = A.time0;
   long long rescale_count = A.rescale_count;
   long long frame = A.frame_base;
+  // frame_event(s) evaluated incrementally: rd = s % dump_freq, rs = s % stat_freq are carried along instead
+  // of two 64-bit divisions per step
+  const bool any_frames = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0));
+  long long rd = 0, rs = 0;
+  if (any_frames) {
+    rd = A.step0 % K.dump_freq;
+    rs = K.stat_freq > 0 ? A.step0 % K.stat_freq : 0;
+  }
   bool alive = true;
   int basin = -1;
 
@@ -358,15 +366,21 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
             }
             if (stopped) { alive = false; exit_s = s; }
           }
+          bool event = false;
+          if (any_frames) {
+            rd += 1; if (rd == K.dump_freq) rd = 0;
+            if (K.stat_freq > 0) { rs += 1; if (rs == K.stat_freq) rs = 0; }
+            event = rd == 0 || (K.stat_freq > 0 && rs == 0 && K.dump_freq - rd <= K.stat_freq);
+          }
           if (alive || exit_s == s) {
-          if (dumping && frame_event(s, K.dump_freq, K.stat_freq)) {
+          if (dumping && event) {
             // io/dump.py:76-102: full observables of this walker at NDRun.step == s
             Eval<R, ND> o;
             eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
             write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
           }
           }
-          if (frame_event(s, K.dump_freq, K.stat_freq)) frame += 1;
+          if (event) frame += 1;
         } else {
           if (committor && left <= commit_left) {  // committor.py:100-111, once per lane
             float c0[ND], c1[ND];
