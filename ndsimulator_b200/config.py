@@ -407,7 +407,11 @@ def parse(config: dict) -> RunSpec:
     spec.device = int(cfg.get("device", 0))
     spec.noise_mode = int(cfg.get("noise_mode", _abi.NDS_NOISE_PHILOX))
     spec.dump_walkers = int(cfg.get("dump_walkers", 1))
-    spec.mtd_shared = bool(cfg.get("mtd_shared", True))
+    # under MC NDRun.time advances on accepted moves only (ndrun.py:234-237): every walker deposits on its own
+    # clock, so the tables are per walker
+    spec.mtd_shared = bool(cfg.get("mtd_shared", method not in ("mc", "wl-mc")))
+    if "mtd" in biases and method == "mc" and spec.mtd_shared:
+        raise ValueError("metadynamics under method: mc needs mtd_shared: false (per-walker deposition clocks)")
     spec.umb_per_walker = bool(cfg.get("umb_per_walker", False))
     if "mtd" in biases:
         cap = cfg.get("mtd_capacity", None)

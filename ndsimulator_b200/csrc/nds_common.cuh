@@ -69,6 +69,7 @@ struct Consts {
   R umb_k[NDS_MAX_UMB][NDS_MAX_CV], umb_r0[NDS_MAX_UMB][NDS_MAX_CV];
   R mtd_w, mtd_invsig2[NDS_MAX_CV], mtd_kBdT;  // kB*(biasf-1)*T, gaus.py:102-103
   R mtd_sig2[NDS_MAX_CV];                      // sigma^2 (gaus.py:90)
+  double mtd_dep_freq64; long long mtd_capacity;  // in-kernel deposition of the MC engine (per-walker clocks)
   R mtd_pre[NDS_MAX_CV];  // fp32 fast form: sqrt(log2(e) / 2) / sigma
   R pe_thred;
   R crit[NDS_MAX_BASINS][NDS_MAX_CV][2];

@@ -46,6 +46,7 @@ struct nds_engine {
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
   virtual int get_mc(int64_t* accepted) = 0;
+  virtual int mc_sync_walker(int64_t walker) = 0;
   virtual int get_wl_histogram(int64_t walker, double* hE) = 0;
   virtual int get_clock(int64_t* step, double* time, int64_t* dep, int64_t* resc) const = 0;
   virtual int set_clock(int64_t step, double time, int64_t dep, int64_t resc) = 0;
@@ -138,6 +139,9 @@ static int validate(const nds_config* c) {
   if (c->method < NDS_METHOD_MD || c->method > NDS_METHOD_WL) return fail(nullptr, "unknown method %d", c->method);
   if (c->method == NDS_METHOD_MC || c->method == NDS_METHOD_WL) {
     if (c->mtd_enabled && c->method == NDS_METHOD_WL) return fail(nullptr, "metadynamics under Wang-Landau MC is not supported");
+    if (c->mtd_enabled && c->mtd_shared)  // ndrun.py:234-237: time (hence the deposition schedule) is per walker
+      return fail(nullptr, "metadynamics under MC needs mtd_shared = 0: NDRun.time advances on accepted moves only, "
+                           "so every walker deposits on its own clock");
     for (int d = 0; d < c->ndim; d++)
       if (c->mc_periodic && !(c->mc_global_bounds[d] != 0)) return fail(nullptr, "mc_global_bounds[%d] must be non-zero", d);
   }
@@ -188,6 +192,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
                 (c.pe_enabled ? BIAS_PE : 0) | ((c.n_umb > 0 && c.umb_per_walker) ? BIAS_UMB_WALKER : 0);
   K.mtd_shared = c.mtd_shared;
   K.mtd_adaptive = (c.mtd_enabled && c.mtd_adapsig_geo) ? 1 : 0;
+  K.mtd_dep_freq64 = c.mtd_dep_freq; K.mtd_capacity = c.mtd_capacity;
   // 4-word records (c0, c1 | 0, w, log2 w) for every shared table with colvardim <= 2 (mtd_block streams them
   // through TMA tiles); adaptive records are (c, w, 1/s, s); everything else is (c_0..c_{cd-1}, w)
   const bool rec4 = !K.mtd_adaptive && (K.cd == 2 || (K.cd == 1 && c.mtd_shared));
@@ -432,6 +437,8 @@ struct Engine : nds_engine {
   double* d_frames = nullptr;
   R *d_path_ref = nullptr, *d_path_ind = nullptr;
   long long* d_mc_accepted = nullptr;
+  double* d_mc_time = nullptr;   // MC: per-walker NDRun.time (accepted moves * dt)
+  long long* d_mc_dep = nullptr; // MC + metadynamics: per-walker deposition count
   R* d_wl = nullptr;
   double* d_noise = nullptr;
   int64_t noise_first = 0, noise_steps = 0;
@@ -459,7 +466,7 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
                     (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
-                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_wl, (void*)d_ids, (void*)d_flags, (void*)d_scan,
+                    (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_mc_time, (void*)d_mc_dep, (void*)d_wl, (void*)d_ids, (void*)d_flags, (void*)d_scan,
                     (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
                     (void*)d_counter})
       if (p) cudaFree(p);
@@ -570,6 +577,12 @@ struct Engine : nds_engine {
     if (c.method == NDS_METHOD_MC || c.method == NDS_METHOD_WL) {
       CU(cudaMalloc(&d_mc_accepted, sizeof(long long) * sM));
       CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * sM, stream));
+      if (c.mtd_enabled) {
+        CU(cudaMalloc(&d_mc_time, sizeof(double) * sM));
+        CU(cudaMalloc(&d_mc_dep, sizeof(long long) * sM));
+        CU(cudaMemsetAsync(d_mc_time, 0, sizeof(double) * sM, stream));
+        CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * sM, stream));
+      }
       kernel_name = sizeof(R) == 4 ? "mc_block<f32>" : "mc_block<f64>";
       if (c.method == NDS_METHOD_WL) {
         CU(cudaMalloc(&d_wl, sizeof(R) * NDS_WL_GRID * sM));
@@ -758,6 +771,8 @@ struct Engine : nds_engine {
       return fail(this, "path colvar: call nds_set_path() before nds_begin()");
     step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
     if (d_mc_accepted) CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * (size_t)M, stream));
+    if (d_mc_time) CU(cudaMemsetAsync(d_mc_time, 0, sizeof(double) * (size_t)M, stream));
+    if (d_mc_dep) { CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (size_t)M, stream)); n_hills = 0; }
     if (d_wl) CU(cudaMemsetAsync(d_wl, 0, sizeof(R) * NDS_WL_GRID * (size_t)M, stream));
     if (cfg.method == NDS_METHOD_COMMITTOR) {
       if (permuted && unpermute_device()) return 1;
@@ -900,33 +915,34 @@ struct Engine : nds_engine {
     CU(cudaEventRecord(ev0, stream));
     int64_t remaining = nsteps;
     while (remaining > 0) {
-      int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
-      if (cfg.mtd_enabled) {
-        // fix.update(step, time) runs before engine.update for every engine (ndrun.py:227-228); the
-        // launch ends right before the next move that would deposit, like the MD loop below
-        if ((int64_t)std::floor(time / cfg.mtd_dep_freq) + 1 > dep_count) {
-          if (deposit()) return 1;
-        }
-        double t = time;
-        int64_t j = 0;
-        while (j < k) {
-          t += cfg.dt; j++;
-          if ((int64_t)std::floor(t / cfg.mtd_dep_freq) + 1 > dep_count) break;
-        }
-        k = j;
-      }
+      const int64_t k = remaining < cfg.steps_per_launch ? remaining : cfg.steps_per_launch;
       BlockArgs<R> A = make_args(k);
-      A.refresh_vr = need_refresh_vr ? 1 : 0;
-      cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, d_wl, stream);
+      // metadynamics: every walker deposits inside the kernel on its own clock (accepted moves * dt)
+      cudaError_t err = launch_mc_block<R>(nd, K, A, d_mc_accepted, d_wl, d_mc_time, d_mc_dep, d_hills, stream);
       if (err != cudaSuccess) return fail(this, "mc_block launch failed: %s", cudaGetErrorString(err));
       launches++;
-      need_refresh_vr = false;
-      for (int64_t j = 0; j < k; j++) time += cfg.dt;  // ndrun.py:240 (MC.current_dt = dt, mc.py:25)
       step += k;
       remaining -= k;
     }
     CU(cudaEventRecord(ev1, stream));
     timed = true;
+    return 0;
+  }
+
+  // MC: NDRun.time and Gaussian._dep_count are per walker; the engine-level values mirror one walker
+  int mc_sync_walker(int64_t walker) override {
+    if (!(cfg.method == NDS_METHOD_MC || cfg.method == NDS_METHOD_WL)) return 0;
+    if (walker < 0 || walker >= M) walker = 0;
+    CU(cudaStreamSynchronize(stream));
+    long long acc = 0;
+    CU(cudaMemcpy(&acc, d_mc_accepted + walker, sizeof acc, cudaMemcpyDeviceToHost));
+    time = 0.0;
+    for (long long i = 0; i < acc; i++) time += cfg.dt;  // repeated addition like ndrun.py:236
+    if (cfg.mtd_enabled) {
+      long long dep = 0;
+      CU(cudaMemcpy(&dep, d_mc_dep + walker, sizeof dep, cudaMemcpyDeviceToHost));
+      n_hills = dep; dep_count = dep;
+    }
     return 0;
   }
 
@@ -1080,6 +1096,7 @@ struct Engine : nds_engine {
               double* Fb) override {
     CU(cudaSetDevice(cfg.device));
     if (n <= 0) return 0;
+    if (mc_sync_walker(0)) return 1;  // MC: walker 0's table
     if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
       return fail(this, "path colvar: call nds_set_path() before nds_eval_at()");
     const size_t sn = (size_t)n;
@@ -1112,6 +1129,7 @@ struct Engine : nds_engine {
 
   int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) override {
     CU(cudaSetDevice(cfg.device));
+    if (mc_sync_walker(walker)) return 1;
     if (!cfg.mtd_enabled) return fail(this, "nds_get_hill_sigma2: metadynamics is not enabled");
     if (n_hills == 0 || !sigma2) return 0;
     if (cap < n_hills) return fail(this, "nds_get_hill_sigma2: capacity %lld < %lld hills", (long long)cap, (long long)n_hills);
@@ -1153,6 +1171,7 @@ struct Engine : nds_engine {
 
   int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) override {
     CU(cudaSetDevice(cfg.device));
+    if (mc_sync_walker(walker)) return 1;
     if (n) *n = n_hills;
     if (!cfg.mtd_enabled || n_hills == 0 || (!centers && !heights)) return 0;
     if (cap < n_hills) return fail(this, "nds_get_hills: capacity %lld < %lld hills", (long long)cap, (long long)n_hills);
@@ -1273,6 +1292,7 @@ struct Engine : nds_engine {
                double* grid) override {
     CU(cudaSetDevice(cfg.device));
     if (!cfg.mtd_enabled) return fail(this, "nds_fes_grid: metadynamics is not enabled");
+    if (mc_sync_walker(walker)) return 1;
     if (cd > 2) return fail(this, "nds_fes_grid: colvardim %d > 2", cd);
     if (cd == 1) ny = 1;
     const int64_t np = nx * ny;
@@ -1411,7 +1431,10 @@ int nds_get_state_f32(nds_engine* e, float* x, float* v, float* f, float* fixf, 
   return e->get_state_f32(x, v, f, fixf, colv, thermo);
 }
 int64_t nds_step(const nds_engine* e) { return e->step; }
-double nds_time(const nds_engine* e) { return e->time; }
+double nds_time(const nds_engine* e) {
+  const_cast<nds_engine*>(e)->mc_sync_walker(0);  // MC: NDRun.time of walker 0 = accepted moves * dt
+  return e->time;
+}
 int nds_eval_at(nds_engine* e, const double* x, int64_t n, double* V, double* F, double* colv, double* J,
                 double* Vb, double* Fb) {
   return e->eval_at(x, n, V, F, colv, J, Vb, Fb);
@@ -1476,7 +1499,10 @@ int nds_open_peer_tables(nds_engine* e, const void* handles, int nranks, int ran
   return e->set_peer_tables(ptrs.data(), nranks, rank, true);
 }
 void* nds_stream(nds_engine* e) { return (void*)e->stream; }
-int64_t nds_n_hills(const nds_engine* e, int64_t) { return e->n_hills; }
+int64_t nds_n_hills(const nds_engine* e, int64_t walker) {
+  const_cast<nds_engine*>(e)->mc_sync_walker(walker);  // MC: every walker has its own count
+  return e->n_hills;
+}
 int64_t nds_launch_count(const nds_engine* e) { return e->launches; }
 double nds_last_run_ms(nds_engine* e) { return e->last_run_ms(); }
 const char* nds_kernel_name(const nds_engine* e) { return e->kernel_name; }

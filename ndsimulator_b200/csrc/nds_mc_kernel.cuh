@@ -37,7 +37,10 @@ NDS_DEV float u01(uint32_t w, float) { return ((float)(w >> 8) + 0.5f) * 5.96046
 template <typename R, int ND>
 __global__ void __launch_bounds__(NDS_BLOCK)
 mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<R> A, long long* accepted,
-         R* wl_hE /* [NDS_WL_GRID][M] per-walker histograms, Wang-Landau only */) {
+         R* wl_hE /* [NDS_WL_GRID][M] per-walker histograms, Wang-Landau only */,
+         double* mc_time /* [M] NDRun.time of each walker: advances on ACCEPTED moves only (ndrun.py:234-237) */,
+         long long* mc_dep /* [M] Gaussian._dep_count of each walker's own table */,
+         R* hills_rw /* per-walker hill tables, written by the in-kernel deposition */) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long M = A.M;
   if (w >= M) return;
@@ -57,22 +60,54 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     for (int k = 0; k < ND; k++)
       if (k < cd) { wb.k[k] = A.umb_k[k * M + w]; wb.r0[k] = A.umb_r0[k * M + w]; }
   }
-  const long long hstride = K.mtd_shared ? 1 : M;
-  const R* hills = K.mtd_shared ? A.hills : (A.hills ? A.hills + w : nullptr);
-  // MC.begin (mc.py:34-40): energies at the current point.  After a deposition this is the refresh of
-  // Gaussian.update (gaus.py:138-146): pe, forces, fixf, biase with the new hill, VR, totale.
+  // Metadynamics under MC: NDRun.time only advances on accepted moves (ndrun.py:234-237), so fix.update
+  // (gaus.py:130-146) follows a clock of the walker's own: every walker keeps its own table (mtd_shared = 0,
+  // checked by nds_create), deposits inside this kernel and sees dep hills.
+  const bool mtd = (bias_mask & BIAS_MTD) != 0;
+  const long long hstride = M;
+  const R* hills = (mtd && hills_rw) ? hills_rw + w : nullptr;
+  double tw = mtd ? mc_time[w] : 0.0;
+  long long dep = mtd ? mc_dep[w] : 0;
+  R vr = mtd ? A.vr[w] : (R)0;
+  // MC.begin (mc.py:34-40): energies at the current point
   Eval<R, ND> cur;
-  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, cur);
-  if (A.refresh_vr && (bias_mask & BIAS_MTD)) {
-    A.vr[w] = cur.vm;
-#pragma unroll
-    for (int d = 0; d < ND; d++) { A.f[d * M + w] = cur.fp[d]; A.fixf[d * M + w] = cur.fb[d]; }
-    A.thermo[4 * M + w] = A.thermo[2 * M + w] + cur.pe + cur.be;
-  }
+  eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, hills, dep, hstride, cur);
   long long acc = accepted[w];
   const long long acc0 = acc;
 
+  bool deposited = false;
+  R ke = A.thermo[2 * M + w], tot = A.thermo[4 * M + w];  // atoms.ke / atoms.totale follow the last event
   for (long long s = A.step0; s < A.step0 + A.nsteps; s++) {
+    if (mtd && (long long)floor(tw / K.mtd_dep_freq64) + 1 > dep && dep < K.mtd_capacity) {
+      // Gaussian.update -> _deposite (gaus.py:130-213) at atoms.colv with the VR of the last refresh, then the
+      // refresh itself (pe, forces, fixf, biase with the new hill, VR, totale), gaus.py:138-146
+      const R h = dep == 0 ? K.mtd_w : K.mtd_w * nds_exp(-vr / K.mtd_kBdT);
+      const int rs = K.hill_stride;
+      R* rec = hills_rw + w;
+#pragma unroll
+      for (int q = 0; q < ND; q++)
+        if (q < cd) rec[(dep * rs + q) * M] = cur.cv.c[q];
+      rec[(dep * rs + K.hill_hidx) * M] = h;
+      if (K.mtd_adaptive) {  // gaus.py:162-165,189-192 (colvardim 1)
+        R g[ND], row[ND];
+#pragma unroll
+        for (int d = 0; d < ND; d++) g[d] = d == 0 ? (R)1 : (R)0;
+        cv_pullback<R, ND>(K.cv, K.rot, x, cur.cv, g, row);
+        R jj = (R)0;
+#pragma unroll
+        for (int d = 0; d < ND; d++) jj += row[d] * row[d];
+        const R s2 = dep == 0 ? jj : jj * K.mtd_sig2[0];
+        rec[(dep * rs + 2) * M] = (R)1.0 / s2;
+        rec[(dep * rs + 3) * M] = s2;
+      }
+      dep += 1;
+      eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, x, wb, hills, dep, hstride, cur);
+      vr = cur.vm;
+      deposited = true;
+#pragma unroll
+      for (int d = 0; d < ND; d++) { A.f[d * M + w] = cur.fp[d]; A.fixf[d * M + w] = cur.fb[d]; }
+      tot = ke + cur.pe + cur.be;  // gaus.py:146
+    }
     R u[ND + 1 > 3 ? ND + 1 : 3];  // "single": pick, displacement, acceptance; "all": ND displacements + acceptance
     if (ext) {
       const double* row = A.noise + ((s - A.noise_first) * nu) * M + w;
@@ -114,7 +149,7 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
       }
     }
     Eval<R, ND> tr;
-    eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, hills, A.n_hills, hstride, tr);
+    eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, bias_mask, xn, wb, hills, dep, hstride, tr);
     const R pe = cur.pe + cur.be, pe_new = tr.pe + tr.be;  // mc.py:64-76
     R pb = (pe_new > pe) ? nds_exp(-(pe_new - pe) / K.kBT) : (R)1.0;
     int eid1 = 0;
@@ -136,8 +171,11 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
       for (int d = 0; d < ND; d++) x[d] = xn[d];
       cur = tr;
       acc += 1;
+      tw += K.dt64;  // ndrun.py:235-237: time advances on accepted moves only
+      ke = (R)0; tot = cur.pe;  // mc.py:93-95
     }
   }
+  if (mtd) { mc_time[w] = tw; mc_dep[w] = dep; if (deposited) A.vr[w] = vr; }
 
 #pragma unroll
   for (int d = 0; d < ND; d++) A.x[d * M + w] = x[d];
@@ -146,10 +184,8 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
     if (q < cd) A.colv[q * M + w] = cur.cv.c[q];
   A.thermo[1 * M + w] = cur.pe;
   A.thermo[3 * M + w] = cur.be;
-  if (acc != acc0) {  // mc.py:93-94 on an accepted move: ke = 0, totale = pe
-    A.thermo[2 * M + w] = (R)0;
-    A.thermo[4 * M + w] = cur.pe;
-  }
+  A.thermo[2 * M + w] = ke;
+  A.thermo[4 * M + w] = tot;
   if (K.method == NDS_METHOD_WL && acc != acc0) {  // np.copyto(atoms.forces, forces_new), wang_landau.py:152
 #pragma unroll
     for (int d = 0; d < ND; d++) A.f[d * M + w] = cur.fp[d];
@@ -159,6 +195,6 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
 
 template <typename R>
 cudaError_t launch_mc_block(int nd, const Consts<R>& K, const BlockArgs<R>& A, long long* accepted,
-                            R* wl_hE, cudaStream_t st);
+                            R* wl_hE, double* mc_time, long long* mc_dep, R* hills_rw, cudaStream_t st);
 
 }  // namespace nds

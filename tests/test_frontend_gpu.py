@@ -113,7 +113,7 @@ def test_user_defined_python_colvar_is_rejected(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["c2-2d-mueller-langevin", "c3-2d-committor", "c4-5d-umbrella-windows",
-                                  "c5-5d-multiwalker-mtd"])
+                                  "c5-5d-multiwalker-mtd", "mc-2d-metropolis-mtd", "harmonic-quartic-5d"])
 def test_shipped_examples_run(name, tmp_path):
     """examples/*.yaml (the BASELINE configurations) through the CLI, shortened."""
     from ndsimulator_b200.scripts.run import main
@@ -128,3 +128,9 @@ def test_shipped_examples_run(name, tmp_path):
         assert np.abs(c - r0).mean() < 2.0          # walkers stay near their own window
     if name.startswith("c5"):
         assert sim.engine.n_hills() == 3 * 4096 and sim.engine.kernel_name.startswith("mtd_block")
+    if name.startswith("mc"):
+        assert sim.engine.kernel_name.startswith("mc_block")
+        n0 = sim.engine.n_hills(0)
+        assert 5 <= n0 <= 15                       # 300 moves, one hill per 20 ACCEPTED moves of walker 0
+        s2 = sim.engine.get_hill_sigma2(0)
+        assert len(s2) == n0 and s2[0] == 2.0 and np.allclose(s2[1:], 2.0 * 1.5 ** 2)

@@ -186,18 +186,24 @@ def test_gpu_wang_landau_philox_statistics():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shared", [True, False])
-def test_gpu_mc_metadynamics_matches_oracle(shared):
-    """Metadynamics under Metropolis MC: fix.update runs before every engine.update (ndrun.py:227-228), so
-    hills are deposited at atoms.colv every dep_freq / dt moves, tempered with the VR of the LAST deposition
-    refresh (MC passes col0 to fix.energy, which leaves VR alone, gaus.py:361-362).  Deterministic against
-    the oracle with caller-supplied uniforms: accept counts, positions, bias energies, VR and the hill
-    tables (shared and per-walker)."""
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_gpu_mc_metadynamics_matches_oracle(adaptive):
+    """Metadynamics under Metropolis MC.  NDRun.time advances on ACCEPTED moves only (ndrun.py:234-237), so
+    fix.update (gaus.py:130-146) follows each walker's own clock: walkers deposit at different moves into their
+    own tables, inside the kernel.  VR is refreshed by the deposition only (MC passes col0 to fix.energy,
+    gaus.py:361-362).  Deterministic against the oracle with caller-supplied uniforms: accept counts, clocks,
+    per-walker hill counts and tables (with per-hill variances for adapsig_geo), positions, energies, VR."""
     from ndsimulator_b200.engine import Engine
-    M, n = 32, 400
-    cfg = dict(M2, dt=0.5, biases=["mtd"], mtd_w=0.02, mtd_sigma=[1.5, 1.5], mtd_dep_freq=10, mtd_biasf=8.0,
-               mtd_shared=shared, steps=n)
+    M, n = 32, 600
+    cfg = dict(M2, dt=0.5, biases=["mtd"], mtd_w=0.02, mtd_dep_freq=10, mtd_biasf=8.0, steps=n)
+    if adaptive:
+        cfg.update(colvar_name="XmY", mtd_sigma=1.5, mtd_adapsig=True, mtd_adapsig_geo=True)
+    else:
+        cfg.update(mtd_sigma=[1.5, 1.5])
     spec = spec_from(cfg, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    assert spec.mtd_shared is False
+    with pytest.raises(ValueError):
+        config.parse(dict(cfg, mtd_shared=True))
     st = spec.to_struct()
     eng, orc = Engine(st), oracle.OracleSim(st, seeds=np.arange(M))
     assert eng.kernel_name.startswith("mc_block")
@@ -208,15 +214,25 @@ def test_gpu_mc_metadynamics_matches_oracle(shared):
         sim.set_noise(u)
         sim.begin()
         sim.run(n)
-    assert eng.time == orc.time == n * 0.5
-    assert np.array_equal(eng.get_mc(), orc.get_mc())
+    acc = eng.get_mc()
+    assert np.array_equal(acc, orc.get_mc())
+    assert eng.time == orc.time == acc[0] * 0.5                       # walker 0's clock
     a, b = eng.get_state(), orc.get_state()
-    for k in ("x", "colv", "pe", "biase", "f", "fixf", "totale"):
+    for k in ("x", "colv", "pe", "biase", "f", "fixf", "ke", "totale"):
         assert scaled_err(a[k], b[k]) < 1e-10, k
     assert scaled_err(eng.get_vr(), orc.get_vr()) < 1e-10
-    for wk in ((0,) if shared else (0, M - 1)):
+    counts = []
+    for wk in (0, 7, M - 1):
         (cg, hg), (co, ho) = eng.get_hills(wk), orc.get_hills(wk)
-        assert len(hg) == len(ho) == (20 * M if shared else 20)      # one deposition per 20 moves of dt 0.5
+        # the walker's own clock: one deposition per dep_freq / dt = 20 ACCEPTED moves
+        assert len(hg) == len(ho) == eng.n_hills(wk)
+        lo_n, hi_n = int(np.floor(max(acc[wk] - 1, 0) * 0.5 / 10)) + 1, int(np.floor(acc[wk] * 0.5 / 10)) + 1
+        assert lo_n <= len(hg) <= hi_n
+        counts.append(len(hg))
         assert scaled_err(cg, co) < 1e-10 and scaled_err(hg, ho) < 1e-10
-        assert hg.min() < 0.9 * 0.02                                   # the tempering is active
+        assert hg.min() < 0.9 * 0.02                                  # the tempering is active
+        if adaptive:
+            sg, so = eng.get_hill_sigma2(wk), orc.get_hill_sigma2(wk)
+            assert np.array_equal(sg, so) and sg[0] == 2.0 and np.all(sg[1:] == 2.0 * 1.5 ** 2)
+    assert len(set(int(c) for c in np.floor(np.maximum(acc - 1, 0) * 0.5 / 10))) > 1   # clocks really differ
     assert b["biase"].max() > 0.01
