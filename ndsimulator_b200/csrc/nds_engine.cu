@@ -334,8 +334,8 @@ static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dump
 // shared-hill metadynamics: pick the mtd_block variant with the best SM fill for M walkers
 static const MtdVariant* pick_mtd_variant(const nds_config& c, int bias_mask, int n_sm) {
   typedef const MtdVariant* (*table_fn)(int*);
-  static const table_fn tables[] = {mtd_variants_f32_nd2, mtd_variants_f32_nd5, mtd_variants_f64_nd2,
-                                    mtd_variants_f64_nd5};
+  static const table_fn tables[] = {mtd_variants_f32_nd1, mtd_variants_f64_nd1, mtd_variants_f32_nd2,
+                                    mtd_variants_f32_nd5, mtd_variants_f64_nd2, mtd_variants_f64_nd5};
   const int want[10] = {c.precision, c.ndim, c.potential, c.colvar, c.true_colvar, c.integrator,
                         bias_mask, c.method, c.noise_mode, 0};
   const MtdVariant* best = nullptr;

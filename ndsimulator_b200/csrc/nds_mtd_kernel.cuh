@@ -254,7 +254,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
 #pragma unroll
     for (int q = 0; q < W; q++) {
       c0[q] = __shfl_sync(0xffffffffu, e.cv.c[0], q);
-      c1[q] = cd > 1 ? __shfl_sync(0xffffffffu, e.cv.c[1], q) : (R)0;
+      c1[q] = cd > 1 ? __shfl_sync(0xffffffffu, e.cv.c[ND > 1 ? 1 : 0], q) : (R)0;
     }
     R Vm, g[ND];
 #pragma unroll
@@ -370,7 +370,7 @@ mtd_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant
       v2 += v[d] * v[d];
     }
     A.colv[0 * M + w] = e.cv.c[0];
-    if (cd > 1) A.colv[1 * M + w] = e.cv.c[1];
+    if (cd > 1) A.colv[1 * M + w] = e.cv.c[ND > 1 ? 1 : 0];
     const R ke = v2 * K.m / (R)2.0;
     A.thermo[0 * M + w] = A.begin_mode ? ke / (R)ND * (R)2.0 / K.kB : ke / (R)ND / K.kB * (R)2.0;
     A.thermo[1 * M + w] = e.pe;

@@ -48,6 +48,8 @@ struct MtdVariant {
   const char* name;
   void* launch;
 };
+const MtdVariant* mtd_variants_f32_nd1(int* n);
+const MtdVariant* mtd_variants_f64_nd1(int* n);
 const MtdVariant* mtd_variants_f32_nd2(int* n);
 const MtdVariant* mtd_variants_f32_nd5(int* n);
 const MtdVariant* mtd_variants_f64_nd2(int* n);

@@ -486,7 +486,7 @@ def test_mtd_block_many_tiles(integrate):
     assert np.allclose(eng.get_vr(), orc.get_vr(), rtol=1e-9)
 
 
-@pytest.mark.parametrize("case", ["XmY_2d", "Proj5dto1d_umb"])
+@pytest.mark.parametrize("case", ["XmY_2d", "Proj5dto1d_umb", "DoubleWell1d"])
 def test_mtd_block_one_dimensional_colvar(case):
     """Shared hill table over a 1-D colvar: the records become (c, 0, w, log2 w) and the TMA-tiled 2-D hill pass
     runs with c1 = 0 and 1/sigma_1^2 = 0.  Against the oracle with external noise (fp64), plus fp32 vs fp64 of the
@@ -496,6 +496,8 @@ def test_mtd_block_one_dimensional_colvar(case):
                 mtd_dep_freq=10, mtd_biasf=10.0, steps=nsteps, mtd_shared=True)
     if case == "XmY_2d":
         cfg = dict(base, ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], biases=["mtd"])
+    elif case == "DoubleWell1d":   # 1-D system: multiple-walker metadynamics across the double-well barrier
+        cfg = dict(base, ndim=1, potential="DoubleWell1d", x0=30.0, biases=["mtd"], temperature=1000)
     else:
         cfg = dict(base, ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
                    x0=[12.0] * 5, biases=["umb", "mtd"], umb_k=0.02, umb_r0=[15.0])
