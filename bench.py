@@ -20,7 +20,14 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to its workers.  With that setting libgomp runs the CPU arm's
+# `parallel for num_threads(n)` regions at single-core speed (measured here and on the GPU box: 9.8e6 instead of
+# 1.1e8 walker-steps/s), which would flatter the GPU/CPU ratio at N > 1.  The CPU baseline must see the same
+# OpenMP environment as in the N = 1 run, so the variable is dropped before libgomp is loaded (by numpy / torch).
+if os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ.pop("OMP_NUM_THREADS")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -134,11 +141,20 @@ def initial_state(name, spec, M, rank_offset):
     return x0, extra
 
 
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would time
+    the CPU arm on one core: the oracle gets an explicit thread count instead (num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(name, threads, target_seconds=12.0):
     """The oracle (scalar fp64 C port of the reference path) timed on the host cores of this box."""
     from oracle import oracle
     from ndsimulator_b200 import config
-    threads = threads or oracle.max_threads()
+    threads = threads or host_threads()
     M = 256 * threads
     spec = config.parse(workload_cfg(name, M, "f64"))
     x0, extra = initial_state(name, spec, M, 0)
@@ -172,7 +188,7 @@ def reference_arm(args):
     from oracle import oracle
     from ndsimulator_b200 import config
     name = args.workload
-    threads = oracle.max_threads()
+    threads = host_threads()
     M = 64 * threads
     md_steps = 1000 if name != "c5" else 100
     spec = config.parse(workload_cfg(name, M, "f64"))
