@@ -868,3 +868,25 @@ def test_checkpoint_resume_is_bit_exact(case):
     if case == "mtd":
         assert np.array_equal(c.get_hills()[1], a.get_hills()[1])
     assert c.count_nonfinite() == 0
+
+
+def test_walker_results_do_not_depend_on_ensemble_size():
+    """Tail handling of every launch shape: walker w follows the same Philox stream whatever M is (odd M runs the
+    scalar kernel, even M the packed one; partial CTAs, a single thread, M = 1)."""
+    cfg = dict(MD2D, integrate="langevin", gamma=0.1, seed=31)
+    ref = None
+    for M in (1024, 1, 2, 3, 127, 128, 129, 130, 257, 1022):
+        spec = spec_from(cfg, n_walkers=M, precision="f32", n_walkers_global=1024)
+        eng = Engine(spec.to_struct())
+        rng = np.random.RandomState(0)
+        x0 = np.stack([rng.uniform(18, 30, 1024), rng.uniform(12, 32, 1024)])[:, :M]
+        eng.set_state(x0)
+        eng.begin()
+        eng.run(20)
+        st = eng.get_state()
+        assert eng.count_nonfinite() == 0
+        if ref is None:
+            ref = st
+            continue
+        for k in ("x", "v", "pe", "T"):
+            assert scaled_err(st[k], ref[k][..., :M]) < 2e-5, (M, k)
