@@ -146,3 +146,22 @@ def test_library_exports_every_declared_symbol():
         from ndsimulator_b200 import Engine, NdsError
         with pytest.raises(NdsError):
             Engine(st)
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under ndsimulator_b200/ (Python or CUDA / C++ sources) may import,
+    link or mention it, and the engine wrapper must fail loudly when the CUDA library is missing."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ndsimulator_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(d, fn), errors="ignore").read()
+                if re.search(r"\boracle\b", text):
+                    offenders.append(os.path.join(d, fn))
+    assert not offenders, offenders
+    src = open(os.path.join(pkg, "_abi.py")).read()
+    assert "raise" in src and "libndsb200.so" in src  # load() raises when the library is missing: no fallback
