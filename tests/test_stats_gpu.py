@@ -256,7 +256,8 @@ def test_mtd_fes_matches_oracle_ensemble():
     assert rms < max(0.1 * kT, 3 * np.sqrt(2) * sem), (rms / kT, sem / kT)
 
 
-def test_six_normals_of_one_call_are_independent_standard_normals():
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_six_normals_of_one_call_are_independent_standard_normals(precision):
     """All six lanes of the 21-bit Box-Muller layout over 2^16 walkers: on a flat 1-D potential six Langevin steps
     consume exactly one Philox call per walker and the normals can be solved from the velocities.  Each lane is
     N(0,1) (KS, variance, kurtosis), lanes are uncorrelated (also in their squares), nothing exceeds the 5.40 sigma
@@ -264,7 +265,7 @@ def test_six_normals_of_one_call_are_independent_standard_normals():
     M = 1 << 16
     cfg = dict(ndim=1, potential="Flat1d", x0=0.0, integrate="langevin", mass=1.0, method="md", temperature=300,
                dt=1.0, gamma=0.1, seed=2718)
-    spec = spec_from(cfg, n_walkers=M)
+    spec = spec_from(cfg, n_walkers=M, precision=precision)
     eng = Engine(spec.to_struct())
     eng.set_state(np.zeros((1, M)), np.zeros((1, M)))
     eng.begin()
@@ -282,6 +283,6 @@ def test_six_normals_of_one_call_are_independent_standard_normals():
     c2m = np.corrcoef(z ** 2)
     off = ~np.eye(6, dtype=bool)
     assert np.abs(cc[off]).max() < 5 / np.sqrt(M) and np.abs(c2m[off]).max() < 5 / np.sqrt(M)
-    assert np.abs(z).max() <= np.sqrt(2 * np.log(2.0 ** 21)) + 1e-9
+    assert np.abs(z).max() <= np.sqrt(2 * np.log(2.0 ** 21)) + (1e-9 if precision == "f64" else 1e-3)
     # walkers are independent too: neighbouring walkers (the two lanes of a packed thread)
     assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5 / np.sqrt(3 * M)
