@@ -299,6 +299,9 @@ NDS_API int64_t nds_count_alive(nds_engine* e);
 NDS_API int nds_get_mc(nds_engine* e, int64_t* accepted);
 /* Wang-Landau: the energy histogram hE[NDS_WL_GRID] of one walker (WangLandau.hE[0]) */
 NDS_API int nds_get_wl_histogram(nds_engine* e, int64_t walker, double* hE);
+/* WangLandau.copy_hE (wang_landau.py:24-34, one basin): install a saved histogram; walker < 0: every walker.
+ * nds_begin() clears the histograms, so call it afterwards.                                          */
+NDS_API int nds_set_wl_histogram(nds_engine* e, int64_t walker, const double* hE);
 
 /* frames recorded since the last drain (io/dump.py:76-102 content for walkers [0, dump_walkers)).
  * Row layout per frame and walker: step, time, x[ndim], v[ndim], f[ndim], colv[cd],

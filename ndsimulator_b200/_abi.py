@@ -125,6 +125,7 @@ _PROTOTYPES = {
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
     "nds_get_mc": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "nds_get_wl_histogram": (C.c_int, [C.c_void_p, C.c_int64, _dp]),
+    "nds_set_wl_histogram": (C.c_int, [C.c_void_p, C.c_int64, _dp]),
     "nds_get_clock": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nds_set_clock": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_int64]),

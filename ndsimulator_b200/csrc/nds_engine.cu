@@ -48,6 +48,7 @@ struct nds_engine {
   virtual int get_mc(int64_t* accepted) = 0;
   virtual int mc_sync_walker(int64_t walker) = 0;
   virtual int get_wl_histogram(int64_t walker, double* hE) = 0;
+  virtual int set_wl_histogram(int64_t walker, const double* hE) = 0;
   virtual int get_clock(int64_t* step, double* time, int64_t* dep, int64_t* resc) const = 0;
   virtual int set_clock(int64_t step, double time, int64_t dep, int64_t resc) = 0;
   virtual int set_vr(const double* vr) = 0;
@@ -957,6 +958,21 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  int set_wl_histogram(int64_t walker, const double* hE) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_WL) return fail(this, "nds_set_wl_histogram: method is not wl-mc");
+    if (walker >= M) return fail(this, "nds_set_wl_histogram: bad walker");
+    CU(cudaStreamSynchronize(stream));
+    std::vector<R> h((size_t)NDS_WL_GRID * (size_t)M);
+    CU(cudaMemcpy(h.data(), d_wl, sizeof(R) * h.size(), cudaMemcpyDeviceToHost));
+    for (int64_t w = 0; w < M; w++) {
+      if (walker >= 0 && w != walker) continue;
+      for (int i = 0; i < NDS_WL_GRID; i++) h[(size_t)i * (size_t)M + (size_t)w] = (R)hE[i];
+    }
+    CU(cudaMemcpy(d_wl, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
+    return 0;
+  }
+
   int get_clock(int64_t* s, double* t, int64_t* dep, int64_t* resc) const override {
     if (s) *s = step;
     if (t) *t = time;
@@ -1460,6 +1476,7 @@ int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e
 int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
 int nds_get_mc(nds_engine* e, int64_t* accepted) { return e->get_mc(accepted); }
 int nds_get_wl_histogram(nds_engine* e, int64_t walker, double* hE) { return e->get_wl_histogram(walker, hE); }
+int nds_set_wl_histogram(nds_engine* e, int64_t walker, const double* hE) { return e->set_wl_histogram(walker, hE); }
 int nds_get_clock(const nds_engine* e, int64_t* step, double* time, int64_t* dep, int64_t* resc) {
   return e->get_clock(step, time, dep, resc);
 }

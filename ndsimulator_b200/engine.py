@@ -265,6 +265,11 @@ class Engine:
         self._check(self.lib.nds_get_wl_histogram(self.h, int(walker), _p(h)))
         return h
 
+    def set_wl_histogram(self, hE, walker=-1):
+        """WangLandau.copy_hE with one basin (engines/wang_landau.py:24-34); after begin()."""
+        h = _f64(hE, (_abi.NDS_WL_GRID,))
+        self._check(self.lib.nds_set_wl_histogram(self.h, int(walker), _p(h)))
+
     def count_alive(self):
         return int(self.lib.nds_count_alive(self.h))
 

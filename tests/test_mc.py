@@ -166,6 +166,34 @@ def test_gpu_wang_landau_external_uniforms_match_oracle():
 
 
 @pytest.mark.gpu
+def test_gpu_wang_landau_histogram_roundtrip_continues_the_run():
+    """dump_hE / copy_hE with one basin (wang_landau.py:24-47): a run that is stopped, whose histogram and
+    positions are installed on a fresh engine, continues exactly like the uninterrupted run."""
+    from ndsimulator_b200.engine import Engine
+    M, n, cut = 16, 600, 250
+    spec = spec_from(WL, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=100)
+    st = spec.to_struct()
+    u = np.random.RandomState(12).uniform(size=(n, 3, M))
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    full = Engine(st)
+    full.set_state(x0); full.set_noise(u); full.begin(); full.run(n)
+    first = Engine(st)
+    first.set_state(x0); first.set_noise(u); first.begin(); first.run(cut)
+    hists = [first.get_wl_histogram(w) for w in range(M)]
+    second = Engine(st)
+    second.set_state(first.get_state()["x"])
+    second.set_noise(u[cut:])
+    second.begin()
+    for w in range(M):
+        second.set_wl_histogram(hists[w], walker=w)
+    second.run(n - cut)
+    for w in (0, 5, M - 1):
+        assert np.array_equal(second.get_wl_histogram(w), full.get_wl_histogram(w))
+    assert np.array_equal(second.get_state()["x"], full.get_state()["x"])
+    assert np.array_equal(first.get_mc() + second.get_mc(), full.get_mc())
+
+
+@pytest.mark.gpu
 def test_gpu_wang_landau_philox_statistics():
     """Philox-driven WL walkers explore like the oracle's: distribution of visited-bin counts (KS)."""
     from ndsimulator_b200.engine import Engine
