@@ -263,6 +263,12 @@ NDS_API int nds_get_hills(nds_engine* e, int64_t walker, int64_t* n, double* cen
  * fixed-sigma table, first colvar).  nds_set_hill_sigma2 follows nds_set_hills when a table is restored. */
 NDS_API int nds_get_hill_sigma2(nds_engine* e, int64_t walker, double* sigma2, int64_t cap);
 NDS_API int nds_set_hill_sigma2(nds_engine* e, int64_t walker, int64_t n, const double* sigma2);
+/* whole hill storage in engine layout, as doubles (checkpoints of per-walker tables): n_hills * hill_stride
+ * values for a shared table, n_hills * hill_stride * M otherwise (field j of record i of walker w at
+ * (i * hill_stride + j) * M + w).  nds_set_hill_table_raw installs n records (n <= mtd_capacity).           */
+NDS_API int64_t nds_hill_table_size(const nds_engine* e, int64_t n);
+NDS_API int nds_get_hill_table_raw(nds_engine* e, double* out, int64_t cap);
+NDS_API int nds_set_hill_table_raw(nds_engine* e, int64_t n, const double* in);
 NDS_API int nds_set_hills(nds_engine* e, int64_t walker, int64_t n, const double* centers,
                   const double* heights);
 /* stale bias energy per walker used by the well-tempered height (fix.VR): [M] */

@@ -114,6 +114,9 @@ _PROTOTYPES = {
     "nds_eval_at": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
     "nds_get_hills": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), _dp, _dp, C.c_int64]),
     "nds_set_hills": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]),
+    "nds_hill_table_size": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "nds_get_hill_table_raw": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
+    "nds_set_hill_table_raw": (C.c_int, [C.c_void_p, C.c_int64, _dp]),
     "nds_get_hill_sigma2": (C.c_int, [C.c_void_p, C.c_int64, _dp, C.c_int64]),
     "nds_set_hill_sigma2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
     "nds_get_vr": (C.c_int, [C.c_void_p, _dp]),

@@ -41,6 +41,9 @@ struct nds_engine {
                       double* Vb, double* Fb) = 0;
   virtual int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) = 0;
   virtual int set_hills(int64_t walker, int64_t n, const double* centers, const double* heights) = 0;
+  virtual int64_t hill_table_size(int64_t n) const = 0;
+  virtual int get_hill_table_raw(double* out, int64_t cap) = 0;
+  virtual int set_hill_table_raw(int64_t n, const double* in) = 0;
   virtual int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) = 0;
   virtual int set_hill_sigma2(int64_t walker, int64_t n, const double* sigma2) = 0;
   virtual int get_vr(double* vr) = 0;
@@ -1143,6 +1146,27 @@ struct Engine : nds_engine {
     return rc;
   }
 
+  int64_t hill_table_size(int64_t n) const override {
+    return n * (int64_t)K.hill_stride * (cfg.mtd_shared ? 1 : M);
+  }
+  int get_hill_table_raw(double* out, int64_t cap) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!cfg.mtd_enabled) return fail(this, "nds_get_hill_table_raw: metadynamics is not enabled");
+    const int64_t n = hill_table_size(n_hills);
+    if (cap < n) return fail(this, "nds_get_hill_table_raw: capacity %lld < %lld", (long long)cap, (long long)n);
+    return n ? download(d_hills, out, n) : 0;
+  }
+  int set_hill_table_raw(int64_t n, const double* in) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!cfg.mtd_enabled) return fail(this, "nds_set_hill_table_raw: metadynamics is not enabled");
+    if (n < 0 || n > cfg.mtd_capacity) return fail(this, "nds_set_hill_table_raw: %lld records > capacity", (long long)n);
+    if (clear_hills()) return 1;
+    if (n && upload(in, d_hills, hill_table_size(n))) return 1;
+    n_hills = n;
+    need_refresh_vr = false;
+    return 0;
+  }
+
   int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) override {
     CU(cudaSetDevice(cfg.device));
     if (mc_sync_walker(walker)) return 1;
@@ -1467,6 +1491,9 @@ int nds_get_hill_sigma2(nds_engine* e, int64_t walker, double* sigma2, int64_t c
 int nds_set_hill_sigma2(nds_engine* e, int64_t walker, int64_t n, const double* sigma2) {
   return e->set_hill_sigma2(walker, n, sigma2);
 }
+int64_t nds_hill_table_size(const nds_engine* e, int64_t n) { return e->hill_table_size(n); }
+int nds_get_hill_table_raw(nds_engine* e, double* out, int64_t cap) { return e->get_hill_table_raw(out, cap); }
+int nds_set_hill_table_raw(nds_engine* e, int64_t n, const double* in) { return e->set_hill_table_raw(n, in); }
 int nds_get_vr(nds_engine* e, double* vr) { return e->get_vr(vr); }
 int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
   e->exchange = cb; e->exchange_user = user;

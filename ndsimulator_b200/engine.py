@@ -229,14 +229,21 @@ class Engine:
                 ck.update(hills_centers=c, hills_heights=h)
                 if self.cfg.mtd_adapsig_geo:
                     ck["hills_sigma2"] = self.get_hill_sigma2(0)
-            else:
-                raise NdsError("checkpoint of per-walker hill tables is not implemented")
+            else:  # per-walker tables: the raw storage (engine layout)
+                n = self.n_hills(0)
+                raw = np.empty(int(self.lib.nds_hill_table_size(self.h, n)))
+                self._check(self.lib.nds_get_hill_table_raw(self.h, _p(raw), raw.size))
+                ck.update(hills_raw=raw, hills_n=n)
             ck["vr"] = self.get_vr()
         return ck
 
     def restore(self, ck):
         self.set_state(ck["x"], ck["v"])
         self.begin()
+        if "hills_raw" in ck:
+            raw = _f64(ck["hills_raw"])
+            self._check(self.lib.nds_set_hill_table_raw(self.h, int(ck["hills_n"]), _p(raw)))
+            self.set_vr(ck["vr"])
         if "hills_heights" in ck:
             self.set_hills(ck["hills_centers"], ck["hills_heights"], sigma2=ck.get("hills_sigma2"))
             self.set_vr(ck["vr"])

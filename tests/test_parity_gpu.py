@@ -832,7 +832,7 @@ def test_f32_host_buffers_roundtrip(precision):
     assert np.allclose(b32["x"], b64["x"], rtol=1e-6) and np.allclose(b32["T"], b64["T"], rtol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["langevin", "mtd", "rescale"])
+@pytest.mark.parametrize("case", ["langevin", "mtd", "mtd_per_walker", "rescale"])
 def test_checkpoint_resume_is_bit_exact(case):
     """(x, v, clock, hills, VR) restored on a fresh engine continues the run bit for bit: Philox noise is a
     pure function of (seed, global walker id, global step)."""
@@ -844,7 +844,8 @@ def test_checkpoint_resume_is_bit_exact(case):
     else:
         cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d", true_colvar_name="Proj5dto2d",
                    x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0, temperature=300, biases=["mtd"],
-                   mtd_w=0.01, mtd_sigma=[2.0, 2.0], mtd_dep_freq=30, mtd_biasf=10.0, steps=400, seed=9)
+                   mtd_w=0.01, mtd_sigma=[2.0, 2.0], mtd_dep_freq=30, mtd_biasf=10.0, steps=400, seed=9,
+                   mtd_shared=(case == "mtd"))
     x0 = np.repeat(np.array(cfg["x0"], dtype=float).reshape(-1, 1), M, axis=1) + \
         np.random.RandomState(0).normal(scale=0.5, size=(len(cfg["x0"]), M))
     spec = spec_from(cfg, n_walkers=M, steps_per_launch=50)
@@ -865,8 +866,10 @@ def test_checkpoint_resume_is_bit_exact(case):
     assert c.step == 400 and c.time == a.time
     for k in ("x", "v", "pe", "biase"):
         assert np.array_equal(got[k], ref[k]), k
-    if case == "mtd":
-        assert np.array_equal(c.get_hills()[1], a.get_hills()[1])
+    if case.startswith("mtd"):
+        for wk in (0, M - 1):
+            assert np.array_equal(c.get_hills(wk)[1], a.get_hills(wk)[1])
+            assert np.array_equal(c.get_hills(wk)[0], a.get_hills(wk)[0])
     assert c.count_nonfinite() == 0
 
 
