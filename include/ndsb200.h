@@ -295,6 +295,10 @@ NDS_API int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, 
 /* committor outcome (engines/committor.py:103-111; ndrun.py:261-264): basin[M] (-1 = none),
  * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */
 NDS_API int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step);
+/* checkpoint / resume of a committor ensemble: alive[w] = 1 while walker w is still running.  nds_set_commit
+ * follows nds_begin() (which revives every walker) on the restoring engine.                               */
+NDS_API int nds_get_alive(nds_engine* e, uint8_t* alive);
+NDS_API int nds_set_commit(nds_engine* e, const int32_t* basin, const int64_t* exit_step, const uint8_t* alive);
 NDS_API int64_t nds_count_alive(nds_engine* e);
 
 /* Metropolis MC (engines/mc.py:42-101): accepted moves per walker [M] (MC.accept_rate); a walker's

@@ -125,6 +125,8 @@ _PROTOTYPES = {
     "nds_open_peer_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "nds_set_peer_tables": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "nds_get_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
+    "nds_set_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]),
     "nds_count_alive": (C.c_int64, [C.c_void_p]),
     "nds_get_mc": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "nds_get_wl_histogram": (C.c_int, [C.c_void_p, C.c_int64, _dp]),

@@ -48,6 +48,8 @@ struct nds_engine {
   virtual int set_hill_sigma2(int64_t walker, int64_t n, const double* sigma2) = 0;
   virtual int get_vr(double* vr) = 0;
   virtual int get_commit(int32_t* basin, int64_t* exit_step) = 0;
+  virtual int get_alive(uint8_t* alive) = 0;
+  virtual int set_commit(const int32_t* basin, const int64_t* exit_step, const uint8_t* alive) = 0;
   virtual int get_mc(int64_t* accepted) = 0;
   virtual int mc_sync_walker(int64_t walker) = 0;
   virtual int get_wl_histogram(int64_t walker, double* hE) = 0;
@@ -1296,6 +1298,28 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  int get_alive(uint8_t* alive) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_COMMITTOR) return fail(this, "nds_get_alive: method is not committor");
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpy(alive, d_alive, (size_t)M, cudaMemcpyDeviceToHost));
+    return unpermute_host<uint8_t>(alive, 1);
+  }
+
+  int set_commit(const int32_t* basin, const int64_t* exit_step, const uint8_t* alive) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_COMMITTOR) return fail(this, "nds_set_commit: method is not committor");
+    if (permuted && unpermute_device()) return 1;  // slots back to walker order
+    n_active = M;
+    std::vector<long long> ex((size_t)M);
+    for (int64_t w = 0; w < M; w++) ex[(size_t)w] = alive[w] ? 0 : exit_step[w];
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpy(d_basin, basin, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_exit, ex.data(), sizeof(long long) * (size_t)M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_alive, alive, (size_t)M, cudaMemcpyHostToDevice));
+    return 0;
+  }
+
   int64_t count_alive() override {
     if (cfg.method != NDS_METHOD_COMMITTOR) return M;
     // after compaction the live walkers are exactly the launched slots that have not stopped since
@@ -1500,6 +1524,10 @@ int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user) {
   return 0;
 }
 int nds_get_commit(nds_engine* e, int32_t* basin, int64_t* exit_step) { return e->get_commit(basin, exit_step); }
+int nds_get_alive(nds_engine* e, uint8_t* alive) { return e->get_alive(alive); }
+int nds_set_commit(nds_engine* e, const int32_t* basin, const int64_t* exit_step, const uint8_t* alive) {
+  return e->set_commit(basin, exit_step, alive);
+}
 int64_t nds_count_alive(nds_engine* e) { return e->count_alive(); }
 int nds_get_mc(nds_engine* e, int64_t* accepted) { return e->get_mc(accepted); }
 int nds_get_wl_histogram(nds_engine* e, int64_t walker, double* hE) { return e->get_wl_histogram(walker, hE); }

@@ -223,6 +223,11 @@ class Engine:
         """Everything needed to continue the run bit for bit on a fresh engine of the same config."""
         st = self.get_state(fields=("x", "v"))
         ck = dict(x=st["x"], v=st["v"], **self.get_clock())
+        if self.cfg.method == _abi.NDS_METHOD_COMMITTOR:
+            basin, exit_step = self.get_commit()
+            alive = np.empty(self.M, dtype=np.uint8)
+            self._check(self.lib.nds_get_alive(self.h, alive.ctypes.data_as(C.POINTER(C.c_uint8))))
+            ck.update(basin=basin, exit_step=exit_step, alive=alive)
         if self.cfg.mtd_enabled:
             if self.cfg.mtd_shared:
                 c, h = self.get_hills(0)
@@ -247,6 +252,13 @@ class Engine:
         if "hills_heights" in ck:
             self.set_hills(ck["hills_centers"], ck["hills_heights"], sigma2=ck.get("hills_sigma2"))
             self.set_vr(ck["vr"])
+        if "alive" in ck:
+            b = np.ascontiguousarray(ck["basin"], dtype=np.int32)
+            e = np.ascontiguousarray(ck["exit_step"], dtype=np.int64)
+            a = np.ascontiguousarray(ck["alive"], dtype=np.uint8)
+            self._check(self.lib.nds_set_commit(self.h, b.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                e.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                a.ctypes.data_as(C.POINTER(C.c_uint8))))
         self.set_clock(ck["step"], ck["time"], ck["dep_count"], ck["rescale_count"])
 
     def count_nonfinite(self):

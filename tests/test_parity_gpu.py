@@ -873,6 +873,32 @@ def test_checkpoint_resume_is_bit_exact(case):
     assert c.count_nonfinite() == 0
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_committor_checkpoint_resume(precision):
+    """A committor ensemble (alive flags, basins, exit steps, frozen states of stopped walkers; lane compaction
+    on both sides) restored on a fresh engine finishes exactly like the uninterrupted run."""
+    g = load_golden("committor.json")
+    cfg = dict(g["config"], steps=6000, seed=21)
+    M = 4096
+    spec = spec_from(cfg, n_walkers=M, precision=precision, steps_per_launch=500)
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    a = Engine(spec.to_struct())
+    a.set_state(x0); a.begin(); a.run(6000)
+    b = Engine(spec.to_struct())
+    b.set_state(x0); b.begin(); b.run(2500)
+    ck = b.checkpoint()
+    assert 0 < (ck["alive"] == 0).sum() < M
+    c = Engine(spec.to_struct())
+    c.restore(ck)
+    assert c.count_alive() == int(ck["alive"].sum())
+    c.run(3500)
+    (ba, ea), (bc, ec) = a.get_commit(), c.get_commit()
+    assert np.array_equal(ba, bc) and np.array_equal(ea, ec) and a.count_alive() == c.count_alive()
+    sa, sc = a.get_state(), c.get_state()
+    for k in ("x", "v", "colv", "pe"):
+        assert np.array_equal(sa[k], sc[k]), k
+
+
 def test_walker_results_do_not_depend_on_ensemble_size():
     """Tail handling of every launch shape: walker w follows the same Philox stream whatever M is (odd M runs the
     scalar kernel, even M the packed one; partial CTAs, a single thread, M = 1)."""
