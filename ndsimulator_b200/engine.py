@@ -221,6 +221,8 @@ class Engine:
 
     def checkpoint(self):
         """Everything needed to continue the run bit for bit on a fresh engine of the same config."""
+        if self.cfg.method in (_abi.NDS_METHOD_MC, _abi.NDS_METHOD_WL) and self.cfg.mtd_enabled:
+            raise NdsError("checkpoint of MC metadynamics (per-walker clocks and hill counts) is not implemented")
         st = self.get_state(fields=("x", "v"))
         ck = dict(x=st["x"], v=st["v"], **self.get_clock())
         if self.cfg.method == _abi.NDS_METHOD_COMMITTOR:
