@@ -417,8 +417,52 @@ def dump_files():
     dump("dump_files.json", out)
 
 
+# ------------------------------------------------------------------------------- Metropolis MC
+def mc_runs():
+    """Metropolis MC runs of the reference made reproducible by seeding the GLOBAL numpy RNG the engine proposes
+    with (mc.py:52-55).  The test rebuilds the same uniform numbers with numpy (RandomState(global_seed)
+    for randint / rand, RandomState(seed) for the acceptance draws after the ndim velocity draws of begin()), feeds
+    them to the oracle and the GPU as caller-supplied uniforms, and compares every recorded move."""
+    out = {}
+    base = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="mc", dt=0.5, mc_bounds=[1.5, 1.5],
+                mc_global_bounds=[48.0, 40.0], temperature=600, dump=False, screen=False, root=TMP, run_name="g",
+                steps=400, seed=4, plot_boundary=[[0.0, 48.0], [0.0, 40.0]])
+    cases = {
+        "single_2d": dict(base),
+        "all_2d_umb": dict(base, mc_propose_dim="all", biases=["umb"], umb_k=0.05, umb_r0=[25, 20]),
+        "single_2d_mtd": dict(base, biases=["mtd"], mtd_w=0.02, mtd_sigma=[1.5, 1.5], mtd_dep_freq=10, mtd_biasf=8.0),
+        "single_2d_mtd_adapsig_geo": dict(base, colvar_name="XmY", biases=["mtd"], mtd_w=0.02, mtd_sigma=1.5,
+                                          mtd_dep_freq=10, mtd_biasf=8.0, mtd_adapsig=True, mtd_adapsig_geo=True),
+    }
+    for name, cfg in cases.items():
+        global_seed = 1000 + len(out)
+        sim = unshadow(ref_stub.make_run(cfg))
+        np.random.seed(global_seed)
+        sim.begin()
+        a = sim.atoms
+        rec = dict(config={k: v for k, v in cfg.items() if k not in ("root", "run_name")}, global_seed=global_seed,
+                   x=[], pe=[], biase=[], accepted=[], time=[])
+        for k in range(cfg["steps"]):
+            sim.steps = k + 1
+            sim.run()
+            rec["x"].append(tolist(a.positions))
+            rec["pe"].append(float(a.pe))
+            rec["biase"].append(float(a.biase))
+            rec["accepted"].append(int(sim.engine.accept_rate))
+            rec["time"].append(float(sim.time))
+        for fix in sim.fixes:
+            if type(fix).__name__ == "Gaussian" and fix._history is not None:
+                rec["hills_centers"] = np.asarray(fix._history, dtype=float).tolist()
+                rec["hills_heights"] = tolist(fix._w)
+                rec["VR"] = float(fix.VR)
+                if fix.adapsig:
+                    rec["hills_sigma2"] = [float(np.asarray(m).reshape(-1)[0]) for m in fix._sigma_history]
+        out[name] = rec
+    dump("mc.json", out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor", "mc_runs"):
         globals()[sys.argv[1]]()
         sys.exit(0)
     eval_points()
@@ -428,3 +472,4 @@ if __name__ == "__main__":
     committor()
     dump_files()
     path_colvars()
+    mc_runs()

@@ -264,3 +264,88 @@ def test_gpu_mc_metadynamics_matches_oracle(adaptive):
             assert np.array_equal(sg, so) and sg[0] == 2.0 and np.all(sg[1:] == 2.0 * 1.5 ** 2)
     assert len(set(int(c) for c in np.floor(np.maximum(acc - 1, 0) * 0.5 / 10))) > 1   # clocks really differ
     assert b["biase"].max() > 0.01
+
+
+# ----------------------------------------------------- pinned to the reference's own (seeded) Metropolis runs
+MC_GOLD = None
+
+
+def _mc_gold():
+    global MC_GOLD
+    if MC_GOLD is None:
+        from tests.helpers import load_golden
+        MC_GOLD = load_golden("mc.json")
+    return MC_GOLD
+
+
+def _reference_uniforms(rec):
+    """The numbers the reference consumed (oracle/make_golden.py mc_runs): proposals from the GLOBAL numpy RNG
+    seeded with rec['global_seed'] (mc.py:52-55), acceptance draws from RandomState(seed) (mc.py:82) after the ndim
+    velocity draws of begin() (modify.py:44-54)."""
+    cfg = rec["config"]
+    nd, n = cfg["ndim"], cfg["steps"]
+    g = np.random.RandomState(rec["global_seed"])
+    rs = np.random.RandomState(cfg["seed"])
+    for _ in range(nd):
+        rs.normal(0, 1, 1)
+    allp = cfg.get("mc_propose_dim", "single") == "all"
+    u = np.zeros((n, nd + 1 if allp else 3, 1))
+    for k in range(n):
+        if allp:
+            u[k, :nd, 0] = g.rand(nd)
+            u[k, nd, 0] = rs.rand()
+        else:
+            dim = g.randint(nd)
+            u[k, 0, 0] = (dim + 0.5) / nd          # floor(u * ndim) == dim
+            u[k, 1, 0] = g.rand()
+            u[k, 2, 0] = rs.rand()
+    return u
+
+
+def _check_against_reference(sim, rec, every=1):
+    n = rec["config"]["steps"]
+    xs, pes, bes, accs = [], [], [], []
+    for k in range(0, n, every):
+        sim.run(every)
+        st = sim.get_state()
+        xs.append(st["x"][:, 0].copy()); pes.append(st["pe"][0]); bes.append(st["biase"][0])
+        accs.append(int(sim.get_mc()[0]))
+    idx = list(range(every - 1, n, every))
+    assert accs == [rec["accepted"][i] for i in idx]
+    assert scaled_err(np.array(xs), np.array(rec["x"])[idx]) < 1e-10
+    assert scaled_err(np.array(pes), np.array(rec["pe"])[idx]) < 1e-10
+    assert scaled_err(np.array(bes), np.array(rec["biase"])[idx]) < 1e-10
+    assert sim.time == rec["time"][-1]
+    if "hills_heights" in rec:
+        c, h = sim.get_hills(0)
+        assert len(h) == len(rec["hills_heights"])
+        assert scaled_err(c, np.array(rec["hills_centers"])) < 1e-10 and scaled_err(h, np.array(rec["hills_heights"])) < 1e-10
+        assert sim.get_vr()[0] == pytest.approx(rec["VR"], rel=1e-9)
+        if "hills_sigma2" in rec:
+            assert np.allclose(sim.get_hill_sigma2(0), rec["hills_sigma2"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo"])
+def test_oracle_mc_follows_the_seeded_reference(name):
+    """Every move of the reference's Metropolis run (accept / reject decisions, positions, energies, NDRun.time that
+    only advances on accepted moves, the hills deposited on that clock and their adapsig_geo variances)."""
+    rec = _mc_gold()[name]
+    spec = spec_from(rec["config"], n_walkers=1, noise_mode=_abi.NDS_NOISE_EXTERNAL)
+    o = oracle.OracleSim(spec.to_struct(), seeds=[rec["config"]["seed"]])
+    o.set_state(spec.x0.reshape(-1, 1))
+    o.set_noise(_reference_uniforms(rec))
+    o.begin()
+    _check_against_reference(o, rec, every=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo"])
+def test_gpu_mc_follows_the_seeded_reference(name):
+    from ndsimulator_b200.engine import Engine
+    rec = _mc_gold()[name]
+    spec = spec_from(rec["config"], n_walkers=1, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    eng = Engine(spec.to_struct())
+    eng.set_state(spec.x0.reshape(-1, 1))
+    eng.set_noise(_reference_uniforms(rec))
+    eng.begin()
+    _check_against_reference(eng, rec, every=40)
