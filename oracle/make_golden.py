@@ -434,6 +434,11 @@ def mc_runs():
         "single_2d_mtd_adapsig_geo": dict(base, colvar_name="XmY", biases=["mtd"], mtd_w=0.02, mtd_sigma=1.5,
                                           mtd_dep_freq=10, mtd_biasf=8.0, mtd_adapsig=True, mtd_adapsig_geo=True),
     }
+    # Wang-Landau (wang_landau.py:65-161, one basin): same random-number consumption as MC
+    cases["wl_single_2d"] = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 30.0], method="wl-mc",
+                                 bounds=[2.0, 2.0], global_bounds=[48.0, 40.0], temperature=300, dump=False,
+                                 screen=False, root=TMP, run_name="g", steps=400, seed=4,
+                                 plot_boundary=[[0.0, 48.0], [0.0, 40.0]])
     for name, cfg in cases.items():
         global_seed = 1000 + len(out)
         sim = unshadow(ref_stub.make_run(cfg))
@@ -457,6 +462,8 @@ def mc_runs():
                 rec["VR"] = float(fix.VR)
                 if fix.adapsig:
                     rec["hills_sigma2"] = [float(np.asarray(m).reshape(-1)[0]) for m in fix._sigma_history]
+        if cfg["method"] == "wl-mc":
+            rec["hE"] = tolist(sim.engine.hE[0])
         out[name] = rec
     dump("mc.json", out)
 

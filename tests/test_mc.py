@@ -288,7 +288,7 @@ def _reference_uniforms(rec):
     rs = np.random.RandomState(cfg["seed"])
     for _ in range(nd):
         rs.normal(0, 1, 1)
-    allp = cfg.get("mc_propose_dim", "single") == "all"
+    allp = cfg.get("mc_propose_dim", cfg.get("propose_dim", "single")) == "all"
     u = np.zeros((n, nd + 1 if allp else 3, 1))
     for k in range(n):
         if allp:
@@ -323,9 +323,14 @@ def _check_against_reference(sim, rec, every=1):
         assert sim.get_vr()[0] == pytest.approx(rec["VR"], rel=1e-9)
         if "hills_sigma2" in rec:
             assert np.allclose(sim.get_hill_sigma2(0), rec["hills_sigma2"], rtol=1e-12)
+    if "hE" in rec:  # Wang-Landau histogram (wang_landau.py:17,51-55)
+        assert np.array_equal(sim.get_wl_histogram(0), np.array(rec["hE"]))
 
 
-@pytest.mark.parametrize("name", ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo"])
+MC_CASES = ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo", "wl_single_2d"]
+
+
+@pytest.mark.parametrize("name", MC_CASES)
 def test_oracle_mc_follows_the_seeded_reference(name):
     """Every move of the reference's Metropolis run (accept / reject decisions, positions, energies, NDRun.time that
     only advances on accepted moves, the hills deposited on that clock and their adapsig_geo variances)."""
@@ -339,7 +344,7 @@ def test_oracle_mc_follows_the_seeded_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo"])
+@pytest.mark.parametrize("name", MC_CASES)
 def test_gpu_mc_follows_the_seeded_reference(name):
     from ndsimulator_b200.engine import Engine
     rec = _mc_gold()[name]
