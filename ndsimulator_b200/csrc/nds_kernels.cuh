@@ -436,11 +436,13 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   for (int k = 0; k < ND; k++)
     if (k < cd) A.colv[k * M + w] = o.cv.c[k];
   const R ke = v2 * K.m / (R)2.0;  // md.py:227
-  A.thermo[0 * M + w] = A.begin_mode ? ke / (R)ND * (R)2.0 / K.kB : ke / (R)ND / K.kB * (R)2.0;  // ndrun.py:195 / md.py:228
   A.thermo[1 * M + w] = o.pe;
-  A.thermo[2 * M + w] = ke;
   A.thermo[3 * M + w] = o.be;
-  A.thermo[4 * M + w] = A.begin_mode ? ke + o.pe : o.pe + ke + o.be;  // ndrun.py:196 / md.py:229
+  if (INTEG != NDS_INT_MINIMIZE || A.begin_mode) {  // Minimize never touches atoms.ke / T / totale (minimize.py:41-82)
+    A.thermo[0 * M + w] = A.begin_mode ? ke / (R)ND * (R)2.0 / K.kB : ke / (R)ND / K.kB * (R)2.0;  // ndrun.py:195 / md.py:228
+    A.thermo[2 * M + w] = ke;
+    A.thermo[4 * M + w] = A.begin_mode ? ke + o.pe : o.pe + ke + o.be;  // ndrun.py:196 / md.py:229
+  }
   if constexpr (PACK == 1) {
     if (committor) {
       if (!alive) { A.alive[w] = 0; A.exit_step[w] = exit_s; }

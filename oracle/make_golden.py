@@ -206,7 +206,7 @@ def run_traj(cfg, sample_every, v0=None):
         rec["x"].append(tolist(a.positions))
         rec["v"].append(tolist(a.velocities))
         rec["f"].append(tolist(a.forces))
-        rec["fixf"].append(tolist(a.fixf))
+        rec["fixf"].append(tolist(getattr(a, "fixf", np.zeros_like(a.positions))))  # Minimize never sets fixf
         rec["colv"].append(tolist(a.colv))
         for k in ("pe", "ke", "biase", "totale", "T"):
             rec[k].append(float(getattr(a, k)))
@@ -265,6 +265,9 @@ def trajectories():
     out["2d_doublewell_pe_seed6"] = run_traj(
         base_cfg(ndim=2, potential="DoubleWell", x0=[20.0, 12.0], gamma=0.05, seed=6, biases=["pe"],
                  pe_thred=-0.45, steps=1500), 150)
+    # method: minimize (engines/minimize.py:41-82): steepest descent with dt * 10.  Minimize.update returns None,
+    # so NDRun.run (ndrun.py:220,230) leaves its loop after ONE update per call: sampled after every call
+    out["2d_minimize"] = run_traj(dict(md2d, method="minimize", x0=[20.0, 20.0], seed=1, steps=60), 1)
     # adapsig_geo with 1-D colvars (the only case in which gaus.py:263-288 is finite): constant Jacobian
     # (XmY), position-dependent Jacobian (Proj5dto1d, note its 2.0*1e-7 term)
     adap = dict(integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05, mtd_sigma=2.0, mtd_dep_freq=50,

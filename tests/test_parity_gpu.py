@@ -113,7 +113,7 @@ def test_one_step_map_10k(integrate, gamma):
 # ------------------------------------------------------------------ golden deterministic trajectories
 TRAJ = load_golden("trajectories.json")
 DETERMINISTIC = ["2d_nve_seed7", "2d_langevin_gamma0_seed7", "2d_rescale_seed3",
-                 "1d_doublewell_nve_seed4", "2d_threehole_nve_seed5"]
+                 "1d_doublewell_nve_seed4", "2d_threehole_nve_seed5", "2d_minimize"]
 
 
 @pytest.mark.parametrize("name", DETERMINISTIC)
