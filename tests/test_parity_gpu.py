@@ -111,6 +111,7 @@ def test_one_step_map_10k(integrate, gamma):
 
 
 # ------------------------------------------------------------------ golden deterministic trajectories
+kB_ = 8.6173303e-5
 TRAJ = load_golden("trajectories.json")
 DETERMINISTIC = ["2d_nve_seed7", "2d_langevin_gamma0_seed7", "2d_rescale_seed3",
                  "1d_doublewell_nve_seed4", "2d_threehole_nve_seed5", "2d_minimize"]
@@ -141,6 +142,64 @@ def test_trajectories(name):
                           np.array(rec[k]).reshape(len(rec["steps"]), -1)) < TRAJ_TOL, k
     assert eng.step == rec["steps"][-1]
     assert eng.time == rec["final_time"]
+
+
+# ------------------------------------------ the reference's STOCHASTIC runs, given the reference's own Gaussians
+STOCHASTIC = ["2d_langevin_gamma0.1_seed0", "2d_md_yaml_as_shipped_seed0", "2d_langevin2_seed3", "5d_umb_seed0",
+              "2d_umb_seed1", "2d_mtd_seed0", "5d_mtd_seed2", "1d_doublewell_langevin_seed4",
+              "2d_doublewell_pe_seed6", "2d_mtd_adapsig_geo_XmY_seed2", "5d_mtd_adapsig_geo_Proj5dto1d_seed3"]
+
+
+def reference_normals(seed, ndim, nsteps, per_step):
+    """The numbers RandomState(seed) handed to the reference: ndim separate normal(0, 1, 1) draws for the initial
+    velocities (modify.py:44-54), then normal(0, 1, ndim) once (langevin) or twice (2nd-langevin) per step
+    (md.py:120,127-128).  numpy's legacy polar method caches every second Gaussian, so the call pattern matters."""
+    rs = np.random.RandomState(seed)
+    v = np.array([rs.normal(0, 1, 1)[0] for _ in range(ndim)])
+    table = np.zeros((nsteps, per_step, 1))
+    for k in range(nsteps):
+        for j in range(per_step // ndim):
+            table[k, j * ndim:(j + 1) * ndim, 0] = rs.normal(0, 1, ndim)
+    return v, table
+
+
+@pytest.mark.parametrize("name", STOCHASTIC)
+def test_stochastic_trajectories_with_the_references_own_noise(name):
+    """fp64 GPU against the fixtures of the reference's stochastic runs (Langevin 1st / 2nd order, umbrella,
+    metadynamics incl. adapsig_geo, PE bias): the Gaussian numbers are rebuilt with numpy exactly as the reference
+    drew them and supplied as external noise, so every sampled state must agree within the trajectory tolerance."""
+    rec = TRAJ[name]
+    cfg = rec["config"]
+    spec = spec_from(cfg, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=rec["sample_every"])
+    nd = spec.ndim
+    per_step = {"langevin": nd, "2nd-langevin": 2 * nd}[spec.integrate]
+    nsteps = rec["steps"][-1]
+    z0, table = reference_normals(cfg["seed"], nd, nsteps, per_step)
+    m = 104.23315626367025 * cfg["mass"]
+    t_init = cfg.get("initial_temperature", cfg["temperature"])
+    assert np.allclose(z0 * np.sqrt(kB_ * t_init / m), rec["v0"], rtol=1e-13)   # same stream position
+    eng = Engine(spec.to_struct())
+    eng.set_state(spec.x0.reshape(-1, 1), np.array(rec["v0"]).reshape(-1, 1))
+    eng.set_noise(table)
+    eng.begin()
+    got = {k: [] for k in ("x", "v", "f", "fixf", "colv", "pe", "ke", "biase", "totale", "T")}
+    prev = 0
+    for s_ in rec["steps"]:
+        eng.run(s_ - prev)
+        prev = s_
+        st = eng.get_state()
+        for k in got:
+            got[k].append(st[k][..., 0].copy())
+    for k in got:
+        assert scaled_err(np.array(got[k]).reshape(len(rec["steps"]), -1),
+                          np.array(rec[k]).reshape(len(rec["steps"]), -1)) < TRAJ_TOL, k
+    assert eng.time == rec["final_time"]
+    if "hills_heights" in rec:
+        c, h = eng.get_hills()
+        assert np.allclose(h, rec["hills_heights"], rtol=1e-9) and np.allclose(c, np.array(rec["hills_centers"]), rtol=1e-9)
+        assert eng.get_vr()[0] == pytest.approx(rec["VR"], rel=1e-8)
+    if "hills_sigma2" in rec:
+        assert np.allclose(eng.get_hill_sigma2(), rec["hills_sigma2"], rtol=1e-12)
 
 
 # -------------------------------------------------- every integrator / bias with externally given noise
