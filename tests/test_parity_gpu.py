@@ -382,20 +382,33 @@ def test_committor_external_noise():
     assert scaled_err(a["x"], b["x"]) < TRAJ_TOL
 
 
-def test_committor_golden_velocities():
-    """The reference's own shots (tests/golden/committor.json): same v0 but Philox noise cannot match
-    MT19937 -- so only gamma-independent facts are checked here: uncommitted walkers report the full
-    step count and basin -1."""
+def test_committor_shots_of_the_reference_with_its_own_noise():
+    """The reference's 24 committor shots (tests/golden/committor.json, one seed each) run as ONE 24-walker
+    ensemble: every walker gets the Gaussian numbers RandomState(seed) handed to its shot.  Basin ids, exit steps
+    and final positions must equal the reference's, and uncommitted shots report basin -1 / all steps."""
     g = load_golden("committor.json")
-    cfg = dict(g["config"], steps=200)
-    spec = spec_from(cfg, n_walkers=8)
+    shots = g["shots"]
+    cfg = dict(g["config"])
+    nsteps, M = cfg["steps"], len(shots)
+    spec = spec_from(cfg, n_walkers=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=1000)
+    table = np.zeros((nsteps, 2, M))
+    v0 = np.zeros((2, M))
+    for w, sh in enumerate(shots):
+        z0, t = reference_normals(sh["seed"], 2, nsteps, 2)
+        table[:, :, w] = t[:, :, 0]
+        v0[:, w] = sh["v0"]
+        assert np.allclose(z0 * np.sqrt(kB_ * cfg["temperature"] / (104.23315626367025 * cfg["mass"])), sh["v0"], rtol=1e-13)
     eng = Engine(spec.to_struct())
-    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), 8, axis=1))
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1), v0)
+    eng.set_noise(table)
     eng.begin()
-    eng.run(200)
+    eng.run(nsteps)
     basin, exit_step = eng.get_commit()
-    assert set(np.unique(basin)) <= {-1, 0, 1}
-    assert np.all(exit_step[basin < 0] == 200)
+    assert list(basin) == [sh["basin"] for sh in shots]
+    assert list(exit_step) == [sh["step"] for sh in shots]
+    assert len(set(basin)) == 3                      # both basins and uncommitted shots occur
+    x = eng.get_state()["x"]
+    assert scaled_err(x.T, np.array([sh["x"] for sh in shots])) < 1e-8
 
 
 def test_umbrella_windows_per_walker():
