@@ -394,6 +394,10 @@ def dump_files():
         "2d_xmy_nve": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
                            integrate="nve", colvar_name="XmY", temperature=300, dt=1.0, seed=7, steps=20,
                            dump=True, dump_freq=10, screen=False),
+        # examples/2d-md.yaml as shipped (Langevin), shortened: the stochastic default user path
+        "2d_md_yaml_langevin_dump10": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md",
+                                           integration="langevin", temperature=300, dt=1.0, seed=0, steps=60,
+                                           dump=True, dump_freq=10, screen=False),
         # adaptive variances are listed in fix0.dat instead of sigma (gaus.py:455-456); "[c]" colvar tokens (A28)
         "2d_mtd_adapsig_geo_xmy_gamma0": dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 30.0],
                                                method="md", integrate="langevin", gamma=0.0, temperature=300,

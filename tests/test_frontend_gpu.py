@@ -31,14 +31,24 @@ def assert_same_text(got, want, rtol=1e-9, what=""):
 
 
 @pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve",
-                                  "2d_mtd_adapsig_geo_xmy_gamma0"])
+                                  "2d_mtd_adapsig_geo_xmy_gamma0", "2d_md_yaml_langevin_dump10"])
 def test_dump_files_match_reference(name, tmp_path):
-    """pos/force/velocity/colvar/thermo/fix*.dat of deterministic runs against the files the Python
-    reference wrote (tests/golden/dump_files.json), including the lagged thermo row (A16)."""
+    """pos/force/velocity/colvar/thermo/fix*.dat against the files the Python reference wrote
+    (tests/golden/dump_files.json), including the lagged thermo row (A16).  The stochastic case (examples/2d-md.yaml
+    as shipped: Langevin) is fed the Gaussian numbers RandomState(seed) handed to the reference."""
     rec = load_golden("dump_files.json")[name]
     cfg = dict(rec["config"], root=str(tmp_path), run_name="r", screen=False, precision="f64")
+    stochastic = name == "2d_md_yaml_langevin_dump10"
+    if stochastic:
+        from ndsimulator_b200 import _abi
+        cfg["noise_mode"] = _abi.NDS_NOISE_EXTERNAL
     sim = NDRun(**cfg)
     sim.modify.set_velocity(v=np.array(rec["v0"]))
+    if stochastic:
+        rs = np.random.RandomState(cfg["seed"])
+        for _ in range(2):
+            rs.normal(0, 1, 1)                                  # the velocity draws of begin() (modify.py:44-54)
+        sim.engine.set_noise(np.array([rs.normal(0, 1, 2) for _ in range(cfg["steps"])]).reshape(-1, 2, 1))
     sim.begin()
     sim.run()
     sim.end()
