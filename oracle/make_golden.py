@@ -292,6 +292,16 @@ def committor():
         out["shots"].append(dict(seed=seed, v0=v0, basin=int(sim.commit_basin), step=int(sim.step),
                                  x=tolist(sim.atoms.positions)))
         print(seed, sim.commit_basin, sim.step)
+    # diffusion_time (committor.py:100-101): started INSIDE basin 0, a shot may only commit from NDRun.step 37 on
+    dcfg = dict(cm, x0=[22.5, 32.5], engine_diffusion_time=37, steps=2000)
+    out["diffusion"] = dict(config={k: v for k, v in dcfg.items() if k not in ("root", "run_name")}, shots=[])
+    for seed in range(8):
+        sim = ref_stub.make_run(dict(dcfg, seed=seed))
+        sim.begin()
+        v0 = tolist(sim.atoms.velocities)
+        sim.run()
+        out["diffusion"]["shots"].append(dict(seed=seed, v0=v0, basin=int(sim.commit_basin), step=int(sim.step),
+                                              x=tolist(sim.atoms.positions)))
     dump("committor.json", out)
     # temperature 0: the inner engine is Minimize (engines/__init__.py:22-23) -- deterministic relaxation
     t0 = dict(config={k: v for k, v in dict(cm, temperature=0, seed=0, steps=3000).items()

@@ -121,8 +121,14 @@ def test_mtd_first_hill_heights():
     assert np.allclose(w, [0.05, 0.04033116, 0.03563761, 0.03074257, 0.03092146, 0.03591853], atol=5e-9)
 
 
-def test_committor_shots():
+@pytest.mark.parametrize("which", ["shots", "diffusion"])
+def test_committor_shots(which):
+    """24 shots of examples/2d-committor.yaml; 8 shots started inside basin 0 with diffusion_time = 37
+    (committor.py:100-101: the first tested update is the one made at NDRun.step 37, so they exit at step 38)."""
     g = load_golden("committor.json")
+    if which == "diffusion":
+        g = g["diffusion"]
+        assert all(s["step"] == 38 and s["basin"] == 0 for s in g["shots"])
     cfg = g["config"]
     shots = g["shots"]
     spec = spec_from(cfg, n_walkers=len(shots))

@@ -382,11 +382,14 @@ def test_committor_external_noise():
     assert scaled_err(a["x"], b["x"]) < TRAJ_TOL
 
 
-def test_committor_shots_of_the_reference_with_its_own_noise():
+@pytest.mark.parametrize("which", ["shots", "diffusion"])
+def test_committor_shots_of_the_reference_with_its_own_noise(which):
     """The reference's 24 committor shots (tests/golden/committor.json, one seed each) run as ONE 24-walker
     ensemble: every walker gets the Gaussian numbers RandomState(seed) handed to its shot.  Basin ids, exit steps
     and final positions must equal the reference's, and uncommitted shots report basin -1 / all steps."""
     g = load_golden("committor.json")
+    if which == "diffusion":   # started inside basin 0 with diffusion_time = 37: exit at step 38 (committor.py:100)
+        g = g["diffusion"]
     shots = g["shots"]
     cfg = dict(g["config"])
     nsteps, M = cfg["steps"], len(shots)
@@ -406,7 +409,8 @@ def test_committor_shots_of_the_reference_with_its_own_noise():
     basin, exit_step = eng.get_commit()
     assert list(basin) == [sh["basin"] for sh in shots]
     assert list(exit_step) == [sh["step"] for sh in shots]
-    assert len(set(basin)) == 3                      # both basins and uncommitted shots occur
+    if which == "shots":
+        assert len(set(basin)) == 3                  # both basins and uncommitted shots occur
     x = eng.get_state()["x"]
     assert scaled_err(x.T, np.array([sh["x"] for sh in shots])) < 1e-8
 
