@@ -26,7 +26,7 @@ extern "C" {
 #define NDS_API
 #endif
 
-#define NDS_ABI_VERSION 2
+#define NDS_ABI_VERSION 3
 #define NDS_MAX_DIM 5     /* ndim of the built-in potentials is 1, 2 or 5                       */
 #define NDS_MAX_CV 5      /* colvardim <= ndim for every built-in colvar                         */
 #define NDS_MAX_UMB 4     /* harmonic restraints acting on one walker (umb_n, bias/__init__.py:31) */
@@ -172,6 +172,23 @@ typedef struct nds_config {
   double mc_global_bounds[NDS_MAX_DIM]; /* periodic box ("global_bounds") */
   int32_t mc_propose_all;               /* propose_dim: 0 = "single" (one random coordinate), 1 = "all" */
   int32_t mc_periodic;                  /* bound_cond == "periodic" (mc.py:57-62) */
+
+  /* grid-accumulated metadynamics bias (new key mtd_grid; the reference's own incremental trick for its FES plot,
+   * bias/gaus.py:380-393 `_dep_projection`, promoted to the step loop): every deposition adds the footprint of the
+   * new hills to a regular grid of (V, dV/dc0, dV/dc1, d2V/dc0dc1) over [lo, hi] per colvar; the step kernel
+   * evaluates the bias by bicubic Hermite interpolation from a shared-memory copy of the grid, so a step costs the
+   * same whatever the number of hills.  Shared table, fixed sigma, colvardim 1 or 2.  The exact hill sum
+   * (mtd_grid = 0) stays the parity path.                                                                        */
+  int32_t mtd_grid;                     /* 0: exact hill sum; 1: grid-accumulated bias */
+  int32_t mtd_grid_n[2];                /* grid points per colvar (n[1] = 1 for colvardim 1); spacing (hi-lo)/(n-1) */
+  int32_t reserved4;
+  double mtd_grid_lo[2], mtd_grid_hi[2];
+
+  /* history-based adaptive sigma (gaus.py:166-183 `adapsig` without `adapsig_geo`): the variance of a new hill is
+   * Var(colvar) over the last mtd_hist_window stat samples of the walker (Stat.colv history, io/stat.py:57-74);
+   * colvardim 1, per-hill variance records like mtd_adapsig_geo.                                                 */
+  int32_t mtd_adapsig_hist;
+  int32_t reserved5;
 } nds_config;
 
 typedef struct nds_engine nds_engine;
@@ -278,6 +295,9 @@ NDS_API int nds_get_vr(nds_engine* e, double* vr);
  * into its slot of the table and then calls  cb(user, dev_ptr_table_segment, bytes_per_rank)  on
  * the engine's stream-ordered host path; the callback performs the allgather IN PLACE over the
  * segment [n_hills, n_hills + n_walkers_global) (e.g. torch.distributed / NCCL).               */
+/* Calls made through the callback: (segment, bytes_per_rank > 0, rank_offset_bytes >= 0) = allgather in place;
+ * (NULL, 0, 0) = barrier (peer-memory exchange); (buffer, bytes, -1) = all-reduce (sum) in place of
+ * bytes / sizeof(real) reals of the engine's precision (grid increment of mtd_grid).                  */
 typedef int (*nds_exchange_fn)(void* user, void* dev_segment, int64_t bytes_per_rank,
                                int64_t rank_offset_bytes);
 NDS_API int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
@@ -291,6 +311,45 @@ NDS_API int nds_set_exchange(nds_engine* e, nds_exchange_fn cb, void* user);
 NDS_API int nds_hills_ipc_handle(nds_engine* e, void* handle);
 NDS_API int nds_open_peer_tables(nds_engine* e, const void* handles, int nranks, int rank);
 NDS_API int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, int rank);
+
+/* device-side barrier of the peer-memory exchange: one warp per rank signals its arrival into every peer's
+ * window and waits for theirs (no host round trip, no callback).  ONLY for one rank per GPU: ranks that share
+ * a GPU must keep the callback barrier (their waiting kernels are not guaranteed to be co-resident).  A rank
+ * that does not arrive within 10 s makes nds_sync() / nds_wait() fail instead of hanging the GPU.        */
+NDS_API int nds_set_peer_barrier(nds_engine* e, int on_device);
+
+/* native NCCL exchange (SURVEY.md section 8b `nds_set_comm`): a C caller gets the multi-GPU hill exchange
+ * without Python.  Either pass a ready ncclComm_t (nccl_comm != NULL; the caller keeps ownership), or the
+ * 128-byte ncclUniqueId produced once by nds_nccl_unique_id() on one rank and handed to every rank by the
+ * launcher (MPI_Bcast, torch.distributed.broadcast_object_list, a file...): the engine then creates and owns
+ * its communicator.  Afterwards each deposition runs ONE in-place ncclAllGather of the new table segment
+ * (exact hill sum) or ONE ncclAllReduce of the grid increment (mtd_grid) on the engine's stream; nds_run()
+ * no longer synchronises with the host.  NCCL is resolved with dlopen("libnccl.so.2") at the first call
+ * (the copy already loaded in the process wins; NDS_NCCL_LIB overrides the name).                     */
+NDS_API int nds_nccl_unique_id(void* id128);
+NDS_API int nds_set_comm(nds_engine* e, const void* unique_id, void* nccl_comm, int rank, int nranks);
+
+/* device time spent in the exchange steps so far (CUDA events around every allgather / all-reduce /
+ * peer-store + barrier) and their number                                                               */
+NDS_API int nds_exchange_info(nds_engine* e, double* exchange_ms, int64_t* n_exchanges);
+/* position-weighted 64-bit checksum of hill records [first, first + n) of this rank's table, computed on
+ * the device: after an exchange every rank must report the same value for the same segment.           */
+NDS_API int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum);
+
+/* mtd_grid: the accumulated bias grid, [ny][nx][4] doubles = (V, h0 dV/dc0, h1 dV/dc1, h0 h1 d2V/dc0dc1) at
+ * the point lo + (i, j) * h (checkpoints, FES output); nds_mtd_grid_outside() = evaluations that fell
+ * outside [lo, hi] so far (they see no bias: the box must cover the reachable colvar range).          */
+NDS_API int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap);
+NDS_API int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n);
+NDS_API int64_t nds_mtd_grid_outside(nds_engine* e);
+
+/* asynchronous host path, one block per direction: host_xv = [2 ndim][M] (x rows, then v rows) and host_xvt =
+ * [2 ndim + 5][M] (x, v, thermo) in the ENGINE's precision (float for NDS_F32), ideally pinned; either may be
+ * NULL.  Enqueues H2D -> nsteps steps -> D2H and returns; nds_wait() completes the pass (the buffers must stay
+ * untouched until then).  chunks > 1 pipelines the pass over walker chunks on separate copy / compute streams
+ * (independent walkers only: no metadynamics, no committor compaction, nsteps <= steps_per_launch).     */
+NDS_API int nds_submit(nds_engine* e, const void* host_xv, int64_t nsteps, void* host_xvt, int32_t chunks);
+NDS_API int nds_wait(nds_engine* e);
 
 /* committor outcome (engines/committor.py:103-111; ndrun.py:261-264): basin[M] (-1 = none),
  * exit_step[M] (value of NDRun.step when the walker stopped; == steps run when uncommitted).    */

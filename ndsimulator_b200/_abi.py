@@ -6,7 +6,7 @@ There is no CPU fallback: :func:`load_library` raises if ``libndsb200.so`` has n
 import ctypes as C
 import os
 
-NDS_ABI_VERSION = 2
+NDS_ABI_VERSION = 3
 NDS_MAX_DIM = 5
 NDS_MAX_CV = 5
 NDS_MAX_UMB = 4
@@ -83,6 +83,9 @@ class NdsConfig(C.Structure):
         ("emin", C.c_double), ("min_gtol", C.c_double), ("min_maxiter", C.c_int64),
         ("mc_bounds", C.c_double * NDS_MAX_DIM), ("mc_global_bounds", C.c_double * NDS_MAX_DIM),
         ("mc_propose_all", C.c_int32), ("mc_periodic", C.c_int32),
+        ("mtd_grid", C.c_int32), ("mtd_grid_n", C.c_int32 * 2), ("reserved4", C.c_int32),
+        ("mtd_grid_lo", C.c_double * 2), ("mtd_grid_hi", C.c_double * 2),
+        ("mtd_adapsig_hist", C.c_int32), ("reserved5", C.c_int32),
     ]
 
 
@@ -124,6 +127,16 @@ _PROTOTYPES = {
     "nds_hills_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nds_open_peer_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "nds_set_peer_tables": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "nds_set_peer_barrier": (C.c_int, [C.c_void_p, C.c_int]),
+    "nds_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "nds_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nds_exchange_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "nds_table_checksum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
+    "nds_get_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
+    "nds_set_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
+    "nds_mtd_grid_outside": (C.c_int64, [C.c_void_p]),
+    "nds_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "nds_wait": (C.c_int, [C.c_void_p]),
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nds_get_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
     "nds_set_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]),

@@ -91,6 +91,11 @@ class RunSpec:
     mtd_shared: bool = True
     mtd_capacity: int = 0
     mtd_adapsig_geo: bool = False
+    mtd_adapsig_hist: bool = False
+    mtd_grid: bool = False
+    mtd_grid_lo: Optional[np.ndarray] = None
+    mtd_grid_hi: Optional[np.ndarray] = None
+    mtd_grid_n: Optional[np.ndarray] = None
     pe_thred: float = 0.0
     n_basins: int = 0
     criteria: Optional[np.ndarray] = None
@@ -169,6 +174,15 @@ class RunSpec:
             c.mtd_biasf = float(self.mtd_biasf)
             c.mtd_capacity = int(self.mtd_capacity)
             c.mtd_adapsig_geo = int(self.mtd_adapsig_geo)
+            c.mtd_adapsig_hist = int(self.mtd_adapsig_hist)
+            c.mtd_grid = int(self.mtd_grid)
+            if self.mtd_grid:
+                for k in range(self.colvardim):
+                    c.mtd_grid_lo[k] = float(self.mtd_grid_lo[k])
+                    c.mtd_grid_hi[k] = float(self.mtd_grid_hi[k])
+                    c.mtd_grid_n[k] = int(self.mtd_grid_n[k])
+                if self.colvardim == 1:
+                    c.mtd_grid_n[1] = 1
         c.pe_enabled = int("pe" in self.biases)
         c.pe_thred = float(self.pe_thred)
         c.n_basins = int(self.n_basins)
@@ -413,6 +427,28 @@ def parse(config: dict) -> RunSpec:
     if "mtd" in biases and method == "mc" and spec.mtd_shared:
         raise ValueError("metadynamics under method: mc needs mtd_shared: false (per-walker deposition clocks)")
     spec.umb_per_walker = bool(cfg.get("umb_per_walker", False))
+    if "mtd" in biases and cfg.get("mtd_grid", False):
+        # grid-accumulated bias (new keys): box [mtd_grid_lo, mtd_grid_hi] per colvar -- default: the reference's
+        # `boundary` / `plot_boundary` key (plot.py:42-46) -- and spacing mtd_grid_spacing (default sigma / 4)
+        if spec.mtd_adapsig_geo or not spec.mtd_shared or cd > 2:
+            raise ValueError("mtd_grid needs a shared table, a fixed sigma and colvardim <= 2")
+        box = cfg.get("mtd_grid_box", cfg.get("plot_boundary", cfg.get("boundary", None)))
+        lo, hi = cfg.get("mtd_grid_lo", None), cfg.get("mtd_grid_hi", None)
+        if lo is None or hi is None:
+            if box is None:
+                raise TypeError("mtd_grid needs mtd_grid_lo / mtd_grid_hi (or boundary)")
+            box = np.asarray(box, dtype=float).reshape(-1, 2)
+            lo, hi = box[:cd, 0], box[:cd, 1]
+        spec.mtd_grid_lo = np.asarray(lo, dtype=float).reshape(-1)[:cd]
+        spec.mtd_grid_hi = np.asarray(hi, dtype=float).reshape(-1)[:cd]
+        if len(spec.mtd_grid_lo) != cd or len(spec.mtd_grid_hi) != cd:
+            raise ValueError("mtd_grid_lo / mtd_grid_hi need colvardim entries")
+        n = cfg.get("mtd_grid_n", None)
+        if n is None:
+            h = np.broadcast_to(np.asarray(cfg.get("mtd_grid_spacing", spec.mtd_sigma / 4.0), dtype=float), (cd,))
+            n = np.ceil((spec.mtd_grid_hi - spec.mtd_grid_lo) / h).astype(int) + 1
+        spec.mtd_grid_n = np.broadcast_to(np.asarray(n, dtype=int), (cd,)).copy()
+        spec.mtd_grid = True
     if "mtd" in biases:
         cap = cfg.get("mtd_capacity", None)
         if cap is None:

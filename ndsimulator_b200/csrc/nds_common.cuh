@@ -19,6 +19,7 @@ constexpr int BIAS_UMB = 1;         // >= 1 harmonic restraint (bias/umb.py)
 constexpr int BIAS_MTD = 2;         // metadynamics hill sum (bias/gaus.py)
 constexpr int BIAS_PE = 4;          // potential-energy bias (bias/pe.py)
 constexpr int BIAS_UMB_WALKER = 8;  // restraint 0 takes (k, r0) per walker
+constexpr int BIAS_MTD_GRID = 16;   // metadynamics bias interpolated from the accumulated grid (mtd_grid)
 
 template <typename R_, int ND_, int POT_ = DYN, int CV_ = DYN, int TCV_ = DYN, int INTEG_ = DYN,
           int BIAS_ = DYN, int METHOD_ = DYN, int NOISE_ = DYN, int DUMP_ = DYN, int NBASIN_ = DYN>
@@ -71,6 +72,9 @@ struct Consts {
   R mtd_sig2[NDS_MAX_CV];                      // sigma^2 (gaus.py:90)
   double mtd_dep_freq64; long long mtd_capacity;  // in-kernel deposition of the MC engine (per-walker clocks)
   R mtd_pre[NDS_MAX_CV];  // fp32 fast form: sqrt(log2(e) / 2) / sigma
+  // grid-accumulated bias (mtd_grid): point (i, j) at lo + (i, j) * h holds (V, h0 dV/dc0, h1 dV/dc1, h0 h1 d2V/dc0dc1)
+  int grid_nx, grid_ny;
+  R grid_lo[2], grid_h[2], grid_invh[2];
   R pe_thred;
   R crit[NDS_MAX_BASINS][NDS_MAX_CV][2];
   long long diffusion_time;
@@ -90,6 +94,7 @@ template <typename R>
 struct BlockArgs {
   long long M;             // local walkers = stride of the SoA arrays
   long long n_active;      // slots [0, n_active) are launched (0 = all M); committor compaction shrinks it
+  long long slot0;         // first slot of this launch (walker chunks of the pipelined host path; 0 otherwise)
   const long long* ids;    // slot -> local walker index after compaction (null = identity)
   long long walker_offset; // global id of local walker 0
   long long step0;         // NDRun.step before the first step of this launch
@@ -102,6 +107,9 @@ struct BlockArgs {
   unsigned char* alive; int* basin; long long* exit_step;  // committor
   // hills
   const R* hills; long long n_hills;
+  // accumulated bias grid (mtd_grid): 4 reals per point, row-major [ny][nx]; grid_smem = 1: the launch carries
+  // dynamic shared memory for a copy of the whole grid
+  const R* grid; int grid_smem; unsigned long long* grid_outside;
   int refresh_vr;          // 1: the launch follows a deposition (or begin): store V_mtd into vr[]
   int need_init_v;         // 1: draw Maxwell-Boltzmann velocities first (modify.py:44-54)
   int begin_mode;          // 1: NDRun.begin semantics: totale = ke + pe, bias omitted (ndrun.py:196)

@@ -12,10 +12,13 @@
 #include <type_traits>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "nds_variants.h"
 #include "nds_mc_kernel.cuh"
+#include "nds_grid_kernels.cuh"
 
 namespace nds { constexpr int MTD_TILE_HOST = 2048; }  // >= mtd_tile_records<R>() of nds_mtd_kernel.cuh
 
@@ -68,6 +71,14 @@ struct nds_engine {
   virtual int hills_ipc_handle(void* handle) = 0;
   virtual int set_peer_tables(void* const* tables, int nranks, int rank, bool opened_by_ipc) = 0;
   virtual double last_run_ms() = 0;
+  virtual int set_comm(const void* unique_id, void* comm, int rank, int nranks) = 0;
+  virtual int set_peer_barrier(int on_device) = 0;
+  virtual int get_mtd_grid(double* out, int64_t cap) = 0;
+  virtual int set_mtd_grid(const double* in, int64_t n) = 0;
+  virtual int64_t mtd_grid_outside() = 0;
+  virtual int submit(const void* host_in, int64_t nsteps, void* host_out, int chunks) = 0;
+  virtual int exchange_info(double* exchange_ms, int64_t* n_exchanges) = 0;
+  virtual int table_checksum(uint64_t* sum, int64_t first, int64_t n) = 0;
 
   nds_config cfg;
   int cd = 0, tcd = 0;
@@ -101,6 +112,50 @@ static int fail(nds_engine* e, const char* fmt, ...) {
       return fail(this, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, \
                   __LINE__, #call);                                                       \
   } while (0)
+
+
+// ------------------------------------------------------------------------------- NCCL (dlopen)
+// The library does not link against NCCL: the few entry points it needs are resolved at run time from the
+// libnccl.so.2 already loaded in the process (torch's bundled copy) or found by the dynamic loader
+// (NDS_NCCL_LIB overrides the name).  Types are restated from nccl.h (stable ABI: ncclUniqueId is 128 bytes,
+// ncclChar = 0, ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0).
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  struct unique_id { char internal[128]; };
+  int (*GetUniqueId)(unique_id*) = nullptr;
+  int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* handle = nullptr;
+  std::string why;
+  bool ok = false;
+};
+
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {getenv("NDS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm) continue;
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD);  // the copy that is already mapped (torch's), if any
+    if (!api.handle) api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) { api.why = "libnccl.so.2 not found (set NDS_NCCL_LIB)"; return api; }
+  auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) api.why = std::string("missing symbol ") + n; return p; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce && api.GetErrorString;
+  return api;
+}
 
 // ------------------------------------------------------------------------------ validation
 static const int kPotNdim[NDS_POT_COUNT] = {2, 5, 5, 1, 2, 2, 5, 2, 2, 1, 2, 0};  // 0: any supported ndim
@@ -166,7 +221,24 @@ static int validate(const nds_config* c) {
     if (c->mtd_adapsig_geo && nds_colvar_dim(c->colvar, c->ndim) != 1)
       return fail(nullptr, "mtd_adapsig_geo needs a 1-D colvar: for colvardim > 1 the reference takes the "
                            "element-wise reciprocal of J.J^T (gaus.py:268-275), which is inf / NaN");
+    if (c->mtd_grid) {
+      const int gcd_ = nds_colvar_dim(c->colvar, c->ndim);
+      if (!c->mtd_shared) return fail(nullptr, "mtd_grid needs the shared hill table (mtd_shared = 1)");
+      if (c->mtd_adapsig_geo || c->mtd_adapsig_hist) return fail(nullptr, "mtd_grid needs a fixed sigma (no adapsig)");
+      if (gcd_ > 2) return fail(nullptr, "mtd_grid: colvardim %d > 2", gcd_);
+      if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR) return fail(nullptr, "mtd_grid needs method md / committor");
+      if (c->n_walkers_global % c->n_walkers != 0 || c->walker_offset % c->n_walkers != 0)
+        return fail(nullptr, "mtd_grid needs the same number of walkers on every rank");
+      if (c->n_walkers_global / c->n_walkers > nds::NDS_MAX_RANKS) return fail(nullptr, "mtd_grid: more than %d ranks", nds::NDS_MAX_RANKS);
+      for (int k = 0; k < gcd_; k++) {
+        if (c->mtd_grid_n[k] < 2) return fail(nullptr, "mtd_grid_n[%d] must be >= 2", k);
+        if (!(c->mtd_grid_hi[k] > c->mtd_grid_lo[k])) return fail(nullptr, "mtd_grid_hi[%d] must exceed mtd_grid_lo[%d]", k, k);
+      }
+      const long long pts = (long long)c->mtd_grid_n[0] * (gcd_ > 1 ? c->mtd_grid_n[1] : 1);
+      if (pts > (1 << 24)) return fail(nullptr, "mtd_grid: %lld grid points > 2^24", pts);
+    }
   }
+  if (c->mtd_adapsig_hist) return fail(nullptr, "mtd_adapsig (history-based variance, gaus.py:166-183) is not built into this library");
   if (c->method == NDS_METHOD_COMMITTOR) {
     if (c->n_basins < 1 || c->n_basins > NDS_MAX_BASINS) return fail(nullptr, "n_basins out of range");
     if (c->temperature == 0 && c->integrator != NDS_INT_MINIMIZE)  // engines/__init__.py:22-23
@@ -286,6 +358,16 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
     }
     for (int k = K.cd; k < NDS_MAX_CV; k++) { K.mtd_invsig2[k] = (R)0; K.mtd_pre[k] = (R)1; }  // unused components
     K.mtd_kBdT = (R)(kB_ * ((c.mtd_biasf - 1) * c.temperature));  // gaus.py:102-103
+    if (c.mtd_grid) {
+      K.bias_mask |= BIAS_MTD_GRID;
+      K.grid_nx = c.mtd_grid_n[0];
+      K.grid_ny = K.cd > 1 ? c.mtd_grid_n[1] : 1;
+      for (int k = 0; k < 2; k++) {
+        const int n = k == 0 ? K.grid_nx : K.grid_ny;
+        const double h = n > 1 ? (c.mtd_grid_hi[k] - c.mtd_grid_lo[k]) / (n - 1) : 1.0;
+        K.grid_lo[k] = (R)c.mtd_grid_lo[k]; K.grid_h[k] = (R)h; K.grid_invh[k] = (R)(1.0 / h);
+      }
+    }
   }
   K.pe_thred = (R)c.pe_thred;
   for (int bb = 0; bb < NDS_MAX_BASINS; bb++)
@@ -309,7 +391,7 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
 // -------------------------------------------------------------------------- variant lookup
 static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dumping, int prec_override = -1) {
   typedef const Variant* (*table_fn)(int*);
-  static const table_fn tables[] = {variants_hot,
+  static const table_fn tables[] = {variants_hot, variants_grid,
                                     variants_generic_f32_nd1, variants_generic_f32_nd2,
                                     variants_generic_f32_nd5, variants_generic_f64_nd1,
                                     variants_generic_f64_nd2, variants_generic_f64_nd5};
@@ -423,6 +505,22 @@ static __global__ void count_alive_kernel(long long M, const unsigned char* aliv
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+// out[row * M + w] = in[row] for every walker w (install one hill list into all per-walker tables)
+template <typename R>
+static __global__ void broadcast_rows_kernel(long long total, long long M, const R* __restrict__ in, R* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = in[i / M];
+}
+
+// position-weighted 64-bit checksum of a word array: sum_i (i + 1) * 0x9E3779B97F4A7C15 * (word_i + 1)  (mod 2^64)
+static __global__ void checksum_kernel(const uint32_t* __restrict__ words, long long n, unsigned long long* out) {
+  unsigned long long local = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    local += (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull * ((unsigned long long)words[i] + 1ull);
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, local);
+}
+
 // ----------------------------------------------------------------------------------- engine
 template <typename R>
 struct Engine : nds_engine {
@@ -462,15 +560,52 @@ struct Engine : nds_engine {
   // peer-memory exchange: device array of every rank's hill table (own included)
   R** d_peer_tables = nullptr;
   std::vector<void*> ipc_opened;
-  int n_peers = 0;
+  int n_peers = 0, peer_rank = 0;
+  // one device slab holds x | v | thermo | f | fixf | colv | vr: (x, v) and (x, v, thermo) are contiguous, so the
+  // asynchronous host path moves each direction with ONE copy (nds_submit)
+  R* d_slab = nullptr;
+  // exchange window behind the hill table (same allocation, hence the same IPC handle): barrier flags + grid slots
+  int nranks_cfg = 1;
+  int64_t xwin_off = 0;                    // bytes from d_hills to the window
+  unsigned long long* d_flags_own = nullptr;  // [NDS_MAX_RANKS] arrival epochs written by the peers, then the error word
+  unsigned long long** d_peer_flags = nullptr;
+  unsigned long long barrier_epoch = 0;
+  bool device_barrier = false;
+  // grid-accumulated bias
+  bool grid_mode = false, grid_in_smem = false, variant_wide = false;
+  int64_t grid_elems = 0;                  // 4 * nx * ny
+  R* d_grid = nullptr;
+  R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
+  R** d_slot_dst = nullptr;                // [nranks] slot of THIS rank on every peer, parity 0 then parity 1
+  R** d_slot_src = nullptr;                // [nranks] slots of every rank in THIS rank's window, parity 0 then 1
+  R** d_ginc_list = nullptr;               // {d_ginc}
+  unsigned long long* d_grid_outside = nullptr;
+  // native NCCL communicator (nds_set_comm)
+  NcclApi::comm_t comm = nullptr;
+  bool comm_owned = false;
+  int comm_rank = 0, comm_nranks = 1;
+  cudaEvent_t xev0 = nullptr, xev1 = nullptr;
+  double exchange_ms_total = 0.0;
+  int64_t n_exchanges = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xev_pending;
+  // asynchronous host path (nds_submit): copy streams + events
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_alt = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
+  // scratch of nds_eval_at, grown on demand
+  R* d_eval = nullptr;
+  size_t eval_elems = 0;
+  std::vector<long long> ids_host;  // slot -> walker of the current permutation (downloaded once per change)
+  bool ids_host_valid = false;
   int64_t dep_count = 0, rescale_count = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 
   ~Engine() override {
     cudaSetDevice(cfg.device);
-    for (void* p : {(void*)d_x, (void*)d_v, (void*)d_f, (void*)d_fixf, (void*)d_colv, (void*)d_thermo,
-                    (void*)d_vr, (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
+    if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+                    (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
+                    (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
                     (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_mc_time, (void*)d_mc_dep, (void*)d_wl, (void*)d_ids, (void*)d_flags, (void*)d_scan,
                     (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
@@ -480,13 +615,23 @@ struct Engine : nds_engine {
     if (d_peer_tables) cudaFree(d_peer_tables);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (auto& pr : xev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t ev : pipe_events) cudaEventDestroy(ev);
+    for (cudaStream_t st : {s_h2d, s_d2h, s_alt}) if (st) cudaStreamDestroy(st);
     if (stream) cudaStreamDestroy(stream);
   }
 
   double step_dt() const { return cfg.integrator == NDS_INT_MINIMIZE ? cfg.dt * 10 : cfg.dt; }
 
+  // records one deposition appends to this rank's table, and the records the table can hold.  mtd_grid keeps only
+  // the LOCAL hills (for fix.dat listings / checkpoints): the bias the walkers feel lives in the grid.
+  int64_t table_add() const { return !cfg.mtd_shared ? 1 : (grid_mode ? M : cfg.n_walkers_global); }
+  int64_t table_cap() const {
+    return (grid_mode && cfg.mtd_shared) ? (cfg.mtd_capacity + nranks_cfg - 1) / nranks_cfg : cfg.mtd_capacity;
+  }
   int64_t hill_elems() const {
     if (!cfg.mtd_shared) return cfg.mtd_capacity * (int64_t)K.hill_stride * M;
+    if (grid_mode) return (table_cap() + 1) * (int64_t)K.hill_stride;
     // shared table: padded with zero-height records to whole TMA tiles (mtd_block reads full tiles)
     const int64_t cap = (cfg.mtd_capacity + MTD_TILE_HOST - 1) / MTD_TILE_HOST * MTD_TILE_HOST + MTD_TILE_HOST;
     return cap * (int64_t)K.hill_stride;
@@ -515,10 +660,13 @@ struct Engine : nds_engine {
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     const bool dumping = K.dump_freq > 0;
+    grid_mode = c.mtd_enabled && c.mtd_grid;
+    nranks_cfg = (int)((c.n_walkers_global + c.n_walkers - 1) / c.n_walkers);
     const Variant* var = pick_variant(c, K.bias_mask, dumping);
     if (!var) return fail(this, "no compiled md_block variant matches this configuration");
     launch_block = (BlockLaunchFn<R>)var->launch;
     kernel_name = var->name;
+    variant_wide = var->wide;
     if (std::is_same<R, float>::value && M % 2 == 0 && !getenv("NDS_NO_PACKED")) {
       const Variant* pv = pick_variant(c, K.bias_mask, dumping, PREC_F32_PACKED);
       if (pv) {
@@ -528,23 +676,17 @@ struct Engine : nds_engine {
         kernel_name = pv->name;
       }
     }
-    if (c.mtd_enabled && c.mtd_shared && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping) {
+    if (c.mtd_enabled && c.mtd_shared && !grid_mode && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping) {
       cudaDeviceProp prop;
       CU(cudaGetDeviceProperties(&prop, c.device));
       const MtdVariant* mv = pick_mtd_variant(c, K.bias_mask, prop.multiProcessorCount);
       if (mv) { launch_block = (BlockLaunchFn<R>)mv->launch; kernel_name = mv->name; }
     }
     const size_t sM = (size_t)M;
-    CU(cudaMalloc(&d_x, sizeof(R) * nd * sM));
-    CU(cudaMalloc(&d_v, sizeof(R) * nd * sM));
-    CU(cudaMalloc(&d_f, sizeof(R) * nd * sM));
-    CU(cudaMalloc(&d_fixf, sizeof(R) * nd * sM));
-    CU(cudaMalloc(&d_colv, sizeof(R) * cd * sM));
-    CU(cudaMalloc(&d_thermo, sizeof(R) * 5 * sM));
-    CU(cudaMalloc(&d_vr, sizeof(R) * sM));
-    CU(cudaMemsetAsync(d_x, 0, sizeof(R) * nd * sM, stream));
-    CU(cudaMemsetAsync(d_v, 0, sizeof(R) * nd * sM, stream));
-    CU(cudaMemsetAsync(d_vr, 0, sizeof(R) * sM, stream));
+    CU(cudaMalloc(&d_slab, sizeof(R) * (size_t)(4 * nd + cd + 6) * sM));
+    d_x = d_slab; d_v = d_x + nd * sM; d_thermo = d_v + nd * sM; d_f = d_thermo + 5 * sM;
+    d_fixf = d_f + nd * sM; d_colv = d_fixf + nd * sM; d_vr = d_colv + cd * sM;
+    CU(cudaMemsetAsync(d_slab, 0, sizeof(R) * (size_t)(4 * nd + cd + 6) * sM, stream));
     if (K.bias_mask & BIAS_UMB_WALKER) {
       CU(cudaMalloc(&d_umb_k, sizeof(R) * cd * sM));
       CU(cudaMalloc(&d_umb_r0, sizeof(R) * cd * sM));
@@ -555,8 +697,30 @@ struct Engine : nds_engine {
       if (upload(r0.data(), d_umb_r0, (int64_t)cd * M)) return 1;
     }
     if (c.mtd_enabled) {
-      CU(cudaMalloc(&d_hills, sizeof(R) * (size_t)hill_elems()));
+      // hill table, then (same allocation => same IPC handle) the exchange window: barrier flags + grid slots
+      grid_elems = grid_mode ? 4 * (int64_t)K.grid_nx * K.grid_ny : 0;
+      xwin_off = ((int64_t)sizeof(R) * hill_elems() + 255) / 256 * 256;
+      const int64_t flag_bytes = 256;  // NDS_MAX_RANKS arrival words + the error word
+      const int64_t slot_bytes = (int64_t)sizeof(R) * grid_elems;
+      const int64_t total = xwin_off + flag_bytes + (c.mtd_shared ? 2 * nranks_cfg * slot_bytes : 0);
+      CU(cudaMalloc(&d_hills, (size_t)total));
+      CU(cudaMemsetAsync(d_hills, 0, (size_t)total, stream));
+      d_flags_own = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_hills) + xwin_off);
       if (clear_hills()) return 1;
+      if (grid_mode) {
+        CU(cudaMalloc(&d_grid, sizeof(R) * (size_t)grid_elems));
+        CU(cudaMalloc(&d_ginc, sizeof(R) * (size_t)grid_elems));
+        CU(cudaMemsetAsync(d_grid, 0, sizeof(R) * (size_t)grid_elems, stream));
+        CU(cudaMemsetAsync(d_ginc, 0, sizeof(R) * (size_t)grid_elems, stream));
+        CU(cudaMalloc(&d_ginc_list, sizeof(R*)));
+        CU(cudaMemcpyAsync(d_ginc_list, &d_ginc, sizeof(R*), cudaMemcpyHostToDevice, stream));
+        CU(cudaMalloc(&d_grid_outside, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(d_grid_outside, 0, sizeof(unsigned long long), stream));
+        // the whole grid rides in shared memory when the wide variant was picked and it fits beside the static part
+        int dev_smem = 0;
+        CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+        grid_in_smem = variant_wide && (int64_t)sizeof(R) * grid_elems <= (int64_t)dev_smem - 1024 && !getenv("NDS_GRID_NO_SMEM");
+      }
     }
     if (c.method == NDS_METHOD_COMMITTOR) {
       CU(cudaMalloc(&d_alive, sM));
@@ -765,6 +929,7 @@ struct Engine : nds_engine {
     A.alive = d_alive; A.basin = d_basin; A.exit_step = d_exit;
     A.n_active = n_active; A.ids = permuted ? d_ids : nullptr;
     A.hills = d_hills; A.n_hills = n_hills;
+    A.grid = d_grid; A.grid_smem = grid_in_smem ? 1 : 0; A.grid_outside = d_grid_outside;
     A.noise = d_noise; A.noise_first = noise_first;
     A.frames = d_frames; A.frame_base = frames_written; A.frame_cap = cfg.dump_capacity;
     A.frame_width = frame_width;
@@ -775,10 +940,13 @@ struct Engine : nds_engine {
     CU(cudaSetDevice(cfg.device));
     if ((cfg.colvar == NDS_CV_PATH || cfg.colvar == NDS_CV_PATH5DTO2D) && !d_path_ref)
       return fail(this, "path colvar: call nds_set_path() before nds_begin()");
-    step = 0; time = 0.0; dep_count = 0; rescale_count = 0; frames_written = 0;
+    // Gaussian._dep_count and _history survive a second NDRun.begin() in the reference (only step / time restart,
+    // ndrun.py:199-200): neither the deposition count nor the hills are reset here; MC keeps its per-walker
+    // clocks on the device and restarts both below.
+    step = 0; time = 0.0; rescale_count = 0; frames_written = 0;
     if (d_mc_accepted) CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * (size_t)M, stream));
     if (d_mc_time) CU(cudaMemsetAsync(d_mc_time, 0, sizeof(double) * (size_t)M, stream));
-    if (d_mc_dep) { CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (size_t)M, stream)); n_hills = 0; }
+    if (d_mc_dep) { CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (size_t)M, stream)); n_hills = 0; dep_count = 0; }
     if (d_wl) CU(cudaMemsetAsync(d_wl, 0, sizeof(R) * NDS_WL_GRID * (size_t)M, stream));
     if (cfg.method == NDS_METHOD_COMMITTOR) {
       if (permuted && unpermute_device()) return 1;
@@ -799,50 +967,163 @@ struct Engine : nds_engine {
     return 0;
   }
 
-  int deposit() {  // Gaussian.update -> _deposite (gaus.py:130-213), all live walkers together
-    const int64_t add = cfg.mtd_shared ? cfg.n_walkers_global : 1;
-    if (n_hills + add > cfg.mtd_capacity)
-      return fail(this, "hill table full: %lld + %lld > mtd_capacity %lld", (long long)n_hills,
-                  (long long)add, (long long)cfg.mtd_capacity);
-    if (cfg.mtd_shared && d_peer_tables && cfg.n_walkers_global > M && !K.mtd_adaptive) {
-      // fused deposition + exchange: records go straight into every rank's table over NVLink
-      deposit_p2p_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
-          K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_peer_tables, n_peers, n_hills,
-          dep_count == 0 ? 1 : 0);
+  // ---- exchange plumbing shared by the exact and the grid path
+  // events around every exchange (deposit kernel excluded): nds_exchange_info() reports their sum
+  void exchange_mark(bool begin_) {
+    if (begin_) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      cudaEventRecord(a, stream);
+      xev_pending.push_back({a, b});
+    } else if (!xev_pending.empty()) {
+      cudaEventRecord(xev_pending.back().second, stream);
+      if (xev_pending.size() > 1024) exchange_collect();
+    }
+  }
+  void exchange_collect() {
+    for (auto& pr : xev_pending) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        exchange_ms_total += ms;
+        n_exchanges += 1;
+      }
+      cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    xev_pending.clear();
+  }
+  int exchange_info(double* ms, int64_t* n) override {
+    CU(cudaSetDevice(cfg.device));
+    exchange_collect();
+    if (ms) *ms = exchange_ms_total;
+    if (n) *n = n_exchanges;
+    return 0;
+  }
+
+  // all ranks have finished their peer stores: device-side flag barrier (one GPU per rank) or the host callback
+  int peer_barrier() {
+    if (device_barrier) {
+      barrier_epoch += 1;
+      peer_barrier_kernel<<<1, 32, 0, stream>>>(d_peer_flags, peer_rank, n_peers, barrier_epoch,
+                                                10000000000ull, d_flags_own + NDS_MAX_RANKS);
       CU(cudaGetLastError());
       launches++;
-      CU(cudaStreamSynchronize(stream));
-      if (!exchange) return fail(this, "peer tables need a barrier callback (nds_set_exchange)");
-      const int rc = exchange(exchange_user, nullptr, 0, 0);  // bytes == 0: barrier only
-      if (rc) return fail(this, "barrier callback failed (%d)", rc);
+      return 0;
+    }
+    CU(cudaStreamSynchronize(stream));
+    if (!exchange) return fail(this, "peer tables need a barrier: nds_set_peer_barrier(e, 1) or a callback (nds_set_exchange)");
+    const int rc = exchange(exchange_user, nullptr, 0, 0);  // bytes == 0: barrier only
+    if (rc) return fail(this, "barrier callback failed (%d)", rc);
+    return 0;
+  }
+
+  int nccl_check(int rc, const char* what) {
+    if (rc == 0) return 0;
+    return fail(this, "%s failed: %s", what, nccl_api().GetErrorString(rc));
+  }
+
+  int deposit() {  // Gaussian.update -> _deposite (gaus.py:130-213), all live walkers together
+    const int64_t add = table_add();
+    if (n_hills + add > table_cap())
+      return fail(this, "hill table full: %lld + %lld > mtd_capacity %lld", (long long)n_hills,
+                  (long long)add, (long long)table_cap());
+    const bool multi = cfg.mtd_shared && cfg.n_walkers_global > M;
+    const int first = dep_count == 0 ? 1 : 0;
+    const unsigned g = (unsigned)((M + 127) / 128);
+    if (grid_mode) {
+      // the new records of this rank (local table), then their footprint on the grid
+      deposit_kernel<R><<<g, 128, 0, stream>>>(K, M, 0, d_colv, d_vr, d_alive, d_hills, n_hills, first);
+      CU(cudaGetLastError());
+      const R* rec = d_hills + n_hills * K.hill_stride;
+      const unsigned tiles = (unsigned)(((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY));
+      const unsigned ga = (unsigned)((grid_elems + 255) / 256);
+      launches += 2;
+      if (!multi) {
+        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, nullptr, 0, d_grid, 1);
+        CU(cudaGetLastError());
+      } else if (d_slot_dst) {
+        // fused with the exchange: the increment goes straight into this rank's slot on EVERY peer over NVLink;
+        // after the barrier each rank adds the slots in rank order (bit-identical grids everywhere)
+        const int par = (int)(dep_count & 1);
+        exchange_mark(true);
+        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_slot_dst + par * n_peers, n_peers, nullptr, 0);
+        CU(cudaGetLastError());
+        if (peer_barrier()) return 1;
+        grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
+        CU(cudaGetLastError());
+        exchange_mark(false);
+        launches++;
+      } else if (comm) {
+        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_ginc_list, 1, nullptr, 0);
+        CU(cudaGetLastError());
+        exchange_mark(true);
+        if (nccl_check(nccl_api().AllReduce(d_ginc, d_ginc, (size_t)grid_elems, sizeof(R) == 4 ? 7 : 8, 0, comm, stream), "ncclAllReduce")) return 1;
+        exchange_mark(false);
+        grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_ginc_list, 1);
+        CU(cudaGetLastError());
+        launches++;
+      } else if (exchange) {
+        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_ginc_list, 1, nullptr, 0);
+        CU(cudaGetLastError());
+        exchange_mark(true);
+        CU(cudaStreamSynchronize(stream));
+        // rank_offset_bytes == -1: all-reduce (sum) of bytes / sizeof(real) reals of the engine's precision, in place
+        const int rc = exchange(exchange_user, (void*)d_ginc, grid_elems * (int64_t)sizeof(R), -1);
+        if (rc) return fail(this, "grid exchange callback failed (%d)", rc);
+        exchange_mark(false);
+        grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_ginc_list, 1);
+        CU(cudaGetLastError());
+        launches++;
+      } else {
+        return fail(this, "shared hills over several ranks need nds_set_comm(), nds_open_peer_tables() or nds_set_exchange()");
+      }
       n_hills += add;
       dep_count += 1;
       need_refresh_vr = true;
       return 0;
     }
-    deposit_kernel<R><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
-        K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, dep_count == 0 ? 1 : 0);
+    if (multi && d_peer_tables && !K.mtd_adaptive) {
+      // fused deposition + exchange: records go straight into every rank's table over NVLink
+      exchange_mark(true);
+      deposit_p2p_kernel<R><<<g, 128, 0, stream>>>(
+          K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_peer_tables, n_peers, n_hills, first);
+      CU(cudaGetLastError());
+      launches++;
+      if (peer_barrier()) return 1;
+      exchange_mark(false);
+      n_hills += add;
+      dep_count += 1;
+      need_refresh_vr = true;
+      return 0;
+    }
+    deposit_kernel<R><<<g, 128, 0, stream>>>(
+        K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, first);
     CU(cudaGetLastError());
     launches++;
     if (K.mtd_adaptive) {  // per-hill variance J.J^T (* sigma^2) at the deposition point
-      const unsigned g = (unsigned)((M + 127) / 128);
-      const int first = dep_count == 0 ? 1 : 0;
       if (nd == 1) hill_variance_kernel<R, 1><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
       else if (nd == 2) hill_variance_kernel<R, 2><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
       else hill_variance_kernel<R, 5><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
       CU(cudaGetLastError());
       launches++;
     }
-    if (cfg.mtd_shared && exchange && cfg.n_walkers_global > M) {
-      // multi-GPU: complete the segment [n_hills, n_hills + n_walkers_global) with every rank's
-      // records.  The callback runs an in-place allgather on its own stream.
-      CU(cudaStreamSynchronize(stream));
+    if (multi) {
+      // multi-GPU: complete the segment [n_hills, n_hills + n_walkers_global) with every rank's records
+      // (SURVEY 8e): ONE in-place allgather, on the engine's stream (native NCCL) or through the callback
       const int64_t rec = (int64_t)K.hill_stride * (int64_t)sizeof(R);
-      const int rc = exchange(exchange_user, (void*)(d_hills + n_hills * K.hill_stride), M * rec,
-                              cfg.walker_offset * rec);
-      if (rc) return fail(this, "hill exchange callback failed (%d)", rc);
-    } else if (cfg.mtd_shared && cfg.n_walkers_global > M) {
-      return fail(this, "shared hills over several ranks need nds_set_exchange()");
+      R* seg = d_hills + n_hills * K.hill_stride;
+      exchange_mark(true);
+      if (comm) {
+        if (cfg.walker_offset != (int64_t)comm_rank * M)
+          return fail(this, "nds_set_comm: walker_offset %lld != rank %d * n_walkers", (long long)cfg.walker_offset, comm_rank);
+        if (nccl_check(nccl_api().AllGather((const char*)seg + cfg.walker_offset * rec, seg, (size_t)(M * rec), 0, comm, stream), "ncclAllGather")) return 1;
+      } else if (exchange) {
+        CU(cudaStreamSynchronize(stream));
+        const int rc = exchange(exchange_user, (void*)seg, M * rec, cfg.walker_offset * rec);
+        if (rc) return fail(this, "hill exchange callback failed (%d)", rc);
+      } else {
+        return fail(this, "shared hills over several ranks need nds_set_comm(), nds_open_peer_tables() or nds_set_exchange()");
+      }
+      exchange_mark(false);
     }
     n_hills += add;
     dep_count += 1;
@@ -875,6 +1156,7 @@ struct Engine : nds_engine {
       CU(cudaGetLastError());
       launches += 4;
       permuted = true;
+      ids_host_valid = false;
     }
     n_active = n_alive;
     return 0;
@@ -884,9 +1166,13 @@ struct Engine : nds_engine {
   template <typename T>
   int unpermute_host(T* buf, int rows) {
     if (!permuted) return 0;
-    std::vector<long long> ids((size_t)M);
-    CU(cudaMemcpyAsync(ids.data(), d_ids, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    if (!ids_host_valid) {  // one download per permutation, shared by all arrays of a nds_get_state call
+      ids_host.resize((size_t)M);
+      CU(cudaMemcpyAsync(ids_host.data(), d_ids, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      ids_host_valid = true;
+    }
+    const std::vector<long long>& ids = ids_host;
     std::vector<T> tmp((size_t)M);
     for (int r = 0; r < rows; r++) {
       T* row = buf + (size_t)r * M;
@@ -968,13 +1254,24 @@ struct Engine : nds_engine {
     if (cfg.method != NDS_METHOD_WL) return fail(this, "nds_set_wl_histogram: method is not wl-mc");
     if (walker >= M) return fail(this, "nds_set_wl_histogram: bad walker");
     CU(cudaStreamSynchronize(stream));
-    std::vector<R> h((size_t)NDS_WL_GRID * (size_t)M);
-    CU(cudaMemcpy(h.data(), d_wl, sizeof(R) * h.size(), cudaMemcpyDeviceToHost));
-    for (int64_t w = 0; w < M; w++) {
-      if (walker >= 0 && w != walker) continue;
-      for (int i = 0; i < NDS_WL_GRID; i++) h[(size_t)i * (size_t)M + (size_t)w] = (R)hE[i];
+    std::vector<R> h((size_t)NDS_WL_GRID);
+    for (int i = 0; i < NDS_WL_GRID; i++) h[(size_t)i] = (R)hE[i];
+    if (walker >= 0) {  // one column of the [NDS_WL_GRID][M] storage
+      CU(cudaMemcpy2D(d_wl + walker, sizeof(R) * (size_t)M, h.data(), sizeof(R), sizeof(R), NDS_WL_GRID, cudaMemcpyHostToDevice));
+      return 0;
     }
-    CU(cudaMemcpy(d_wl, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
+    R* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, sizeof(R) * NDS_WL_GRID));
+    cudaError_t err = cudaMemcpy(d_tmp, h.data(), sizeof(R) * NDS_WL_GRID, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+      const long long tot = (long long)NDS_WL_GRID * M;
+      broadcast_rows_kernel<R><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(tot, M, d_tmp, d_wl);
+      err = cudaGetLastError();
+      launches++;
+    }
+    cudaStreamSynchronize(stream);
+    cudaFree(d_tmp);
+    if (err != cudaSuccess) return fail(this, "nds_set_wl_histogram: %s", cudaGetErrorString(err));
     return 0;
   }
 
@@ -1014,6 +1311,103 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  // one fused launch of k steps over slots [slot0, slot0 + nslots) (nslots == 0: every launched slot) on stream st
+  cudaError_t launch_steps(int64_t k, int64_t slot0, int64_t nslots, cudaStream_t st) {
+    BlockArgs<R> A = make_args(k);
+    A.refresh_vr = need_refresh_vr ? 1 : 0;
+    if (nslots > 0) { A.slot0 = slot0; A.n_active = slot0 + nslots; }
+    if (launch_packed) {
+      // same buffers, read as pairs: SoA float[d][M] == f2[d][M/2]
+      BlockArgs<f2> P;
+      memset(&P, 0, sizeof P);
+      P.M = M / 2; P.walker_offset = A.walker_offset; P.step0 = A.step0; P.nsteps = A.nsteps;
+      P.time0 = A.time0; P.rescale_count = A.rescale_count;
+      P.x = (f2*)A.x; P.v = (f2*)A.v; P.f = (f2*)A.f; P.fixf = (f2*)A.fixf; P.colv = (f2*)A.colv;
+      P.thermo = (f2*)A.thermo; P.vr = (f2*)A.vr;
+      P.umb_k = (const f2*)A.umb_k; P.umb_r0 = (const f2*)A.umb_r0;
+      // committor: a thread owns slots 2t and 2t+1 of the (compacted) slot order
+      P.alive = A.alive; P.basin = A.basin; P.exit_step = A.exit_step; P.ids = A.ids;
+      P.n_active = A.n_active > 0 ? (A.n_active + 1) / 2 : 0;
+      P.slot0 = A.slot0 / 2;
+      return launch_packed(K2, P, st);
+    }
+    return launch_block(K, A, st);
+  }
+
+  // asynchronous host path: ONE pinned block per direction.  host_in = [2 ndim][M] (x rows, then v rows), host_out =
+  // [2 ndim + 5][M] (x, v, thermo), both in the engine's precision; either may be NULL.  chunks > 1 pipelines the
+  // pass over walker chunks (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c on their own
+  // streams): legal because the walkers of these ensembles are independent.  Returns after enqueueing;
+  // nds_wait() (= nds_sync) completes the pass.
+  int submit(const void* host_in, int64_t nsteps, void* host_out, int chunks) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!begun) return fail(this, "nds_submit before nds_begin");
+    if (permuted || compactable) return fail(this, "nds_submit: committor ensembles with lane compaction use nds_set_state / nds_run / nds_get_state");
+    const size_t row = sizeof(R) * (size_t)M;
+    const bool can_chunk = chunks > 1 && !cfg.mtd_enabled && cfg.method == NDS_METHOD_MD && K.dump_freq == 0 &&
+                           nsteps <= cfg.steps_per_launch && cfg.integrator != NDS_INT_RESCALE &&
+                           (cfg.noise_mode == NDS_NOISE_PHILOX || normals_per_step(cfg.integrator, nd) == 0);
+    if (!can_chunk) {
+      if (host_in) { CU(cudaMemcpyAsync(d_x, host_in, row * 2 * nd, cudaMemcpyHostToDevice, stream)); have_v = true; }
+      if (run(nsteps)) return 1;
+      if (host_out) CU(cudaMemcpyAsync(host_out, d_x, row * (2 * nd + 5), cudaMemcpyDeviceToHost, stream));
+      return 0;
+    }
+    if (!s_h2d) {
+      CU(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&s_alt, cudaStreamNonBlocking));
+    }
+    // chunk = whole CTAs of the step kernel (128 threads, two walkers per thread when packed)
+    const int64_t unit = 128 * (launch_packed ? 2 : 1);
+    int64_t per = ((M + chunks - 1) / chunks + unit - 1) / unit * unit;
+    const int nch = (int)((M + per - 1) / per);
+    while ((int)pipe_events.size() < 2 * nch + 2) {
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      pipe_events.push_back(ev);
+    }
+    cudaEvent_t ev_start = pipe_events[(size_t)(2 * nch)], ev_end = pipe_events[(size_t)(2 * nch + 1)];
+    CU(cudaEventRecord(ev0, stream));
+    CU(cudaEventRecord(ev_start, stream));  // everything queued so far (previous pass) precedes the new copies
+    CU(cudaStreamWaitEvent(s_h2d, ev_start, 0));
+    CU(cudaStreamWaitEvent(s_alt, ev_start, 0));
+    CU(cudaStreamWaitEvent(s_d2h, ev_start, 0));
+    if (host_in) have_v = true;
+    for (int c = 0; c < nch; c++) {
+      const int64_t w0 = c * per, wn = (w0 + per <= M ? per : M - w0);
+      cudaStream_t cs = (c & 1) ? s_alt : stream;
+      cudaEvent_t e_in = pipe_events[(size_t)(2 * c)], e_k = pipe_events[(size_t)(2 * c + 1)];
+      if (host_in) {
+        CU(cudaMemcpy2DAsync(d_x + w0, row, (const R*)host_in + w0, row, sizeof(R) * (size_t)wn, (size_t)(2 * nd),
+                             cudaMemcpyHostToDevice, s_h2d));
+        CU(cudaEventRecord(e_in, s_h2d));
+        CU(cudaStreamWaitEvent(cs, e_in, 0));
+      }
+      const int64_t pk = launch_packed ? 2 : 1;
+      cudaError_t err = launch_steps(nsteps, w0 / pk * pk, wn, cs);
+      if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
+      launches++;
+      if (host_out) {
+        CU(cudaEventRecord(e_k, cs));
+        CU(cudaStreamWaitEvent(s_d2h, e_k, 0));
+        CU(cudaMemcpy2DAsync((R*)host_out + w0, row, d_x + w0, row, sizeof(R) * (size_t)wn, (size_t)(2 * nd + 5),
+                             cudaMemcpyDeviceToHost, s_d2h));
+      }
+    }
+    // join: the engine stream completes when every chunk has
+    CU(cudaEventRecord(ev_end, s_alt));
+    CU(cudaStreamWaitEvent(stream, ev_end, 0));
+    CU(cudaEventRecord(ev_end, s_d2h));
+    CU(cudaStreamWaitEvent(stream, ev_end, 0));
+    CU(cudaEventRecord(ev1, stream));
+    timed = true;
+    need_refresh_vr = false;
+    for (int64_t j = 0; j < nsteps; j++) time += step_dt();  // ndrun.py:240
+    step += nsteps;
+    return 0;
+  }
+
   int run(int64_t nsteps) override {  // the NDRun.run loop (ndrun.py:214-251)
     CU(cudaSetDevice(cfg.device));
     if (!begun) return fail(this, "nds_run before nds_begin");
@@ -1048,25 +1442,7 @@ struct Engine : nds_engine {
           return fail(this, "frame ring full (%lld frames pending, capacity %lld): call nds_drain_frames",
                       (long long)frames_written, (long long)cfg.dump_capacity);
       }
-      BlockArgs<R> A = make_args(k);
-      A.refresh_vr = need_refresh_vr ? 1 : 0;
-      cudaError_t err;
-      if (launch_packed) {
-        // same buffers, read as pairs: SoA float[d][M] == f2[d][M/2]
-        BlockArgs<f2> P;
-        memset(&P, 0, sizeof P);
-        P.M = M / 2; P.walker_offset = A.walker_offset; P.step0 = A.step0; P.nsteps = A.nsteps;
-        P.time0 = A.time0; P.rescale_count = A.rescale_count;
-        P.x = (f2*)A.x; P.v = (f2*)A.v; P.f = (f2*)A.f; P.fixf = (f2*)A.fixf; P.colv = (f2*)A.colv;
-        P.thermo = (f2*)A.thermo; P.vr = (f2*)A.vr;
-        P.umb_k = (const f2*)A.umb_k; P.umb_r0 = (const f2*)A.umb_r0;
-        // committor: a thread owns slots 2t and 2t+1 of the (compacted) slot order
-        P.alive = A.alive; P.basin = A.basin; P.exit_step = A.exit_step; P.ids = A.ids;
-        P.n_active = A.n_active > 0 ? (A.n_active + 1) / 2 : 0;
-        err = launch_packed(K2, P, stream);
-      } else {
-        err = launch_block(K, A, stream);
-      }
+      cudaError_t err = launch_steps(k, 0, 0, stream);
       if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
       launches++;
       need_refresh_vr = false;
@@ -1090,6 +1466,11 @@ struct Engine : nds_engine {
   int sync() override {
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamSynchronize(stream));
+    if (device_barrier && barrier_epoch > 0) {
+      unsigned long long bad = 0;
+      CU(cudaMemcpy(&bad, d_flags_own + NDS_MAX_RANKS, sizeof bad, cudaMemcpyDeviceToHost));
+      if (bad) return fail(this, "peer barrier %llu timed out: a rank did not arrive within 10 s", bad);
+    }
     return 0;
   }
 
@@ -1122,17 +1503,22 @@ struct Engine : nds_engine {
       return fail(this, "path colvar: call nds_set_path() before nds_eval_at()");
     const size_t sn = (size_t)n;
     const size_t total = sn * (size_t)(nd + 1 + nd + cd + cd * nd + 1 + nd);
-    R* buf = nullptr;
-    CU(cudaMalloc(&buf, sizeof(R) * total));
+    if (total > eval_elems) {  // scratch grows on demand and is kept
+      if (d_eval) CU(cudaFree(d_eval));
+      d_eval = nullptr; eval_elems = 0;
+      CU(cudaMalloc(&d_eval, sizeof(R) * total));
+      eval_elems = total;
+    }
+    R* buf = d_eval;
     R* dx = buf; R* dV = dx + nd * sn; R* dF = dV + sn; R* dc = dF + nd * sn; R* dJ = dc + cd * sn;
     R* dVb = dJ + (size_t)cd * nd * sn; R* dFb = dVb + sn;
     int rc = upload(x, dx, (int64_t)nd * n);
     if (!rc) {
       const unsigned grid = (unsigned)((n + NDS_BLOCK - 1) / NDS_BLOCK);
       const long long es = cfg.mtd_shared ? 1 : M;
-      if (nd == 1) eval_at_kernel<R, 1><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
-      else if (nd == 2) eval_at_kernel<R, 2><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
-      else eval_at_kernel<R, 5><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb);
+      if (nd == 1) eval_at_kernel<R, 1><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb, d_grid);
+      else if (nd == 2) eval_at_kernel<R, 2><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb, d_grid);
+      else eval_at_kernel<R, 5><<<grid, NDS_BLOCK, 0, stream>>>(K, n, dx, d_hills, n_hills, es, dV, dF, dc, dJ, dVb, dFb, d_grid);
       cudaError_t err = cudaGetLastError();
       if (err != cudaSuccess) rc = fail(this, "eval_at launch failed: %s", cudaGetErrorString(err));
       launches++;
@@ -1144,7 +1530,6 @@ struct Engine : nds_engine {
     if (!rc && Vb) rc = download(dVb, Vb, n);
     if (!rc && Fb) rc = download(dFb, Fb, (int64_t)nd * n);
     cudaStreamSynchronize(stream);
-    cudaFree(buf);
     return rc;
   }
 
@@ -1169,6 +1554,51 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  // first n records of one table as doubles, record-major [n][hill_stride].  Per-walker tables live
+  // field-interleaved over the walkers (field j of record i of walker w at (i * stride + j) * M + w): a strided
+  // 2-D copy moves exactly the n * stride values of that walker.
+  int download_table(int64_t walker, int64_t n, std::vector<double>& out) {
+    const int rs = K.hill_stride;
+    out.assign((size_t)(n * rs), 0.0);
+    if (n <= 0) return 0;
+    if (cfg.mtd_shared) return download(d_hills, out.data(), n * rs);
+    if (walker < 0 || walker >= M) return fail(this, "hill table: bad walker");
+    std::vector<R> tmp((size_t)(n * rs));
+    CU(cudaMemcpy2DAsync(tmp.data(), sizeof(R), d_hills + walker, sizeof(R) * (size_t)M, sizeof(R), (size_t)(n * rs),
+                         cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < tmp.size(); i++) out[i] = (double)tmp[i];
+    return 0;
+  }
+  // install n records (record-major doubles) into one walker's table, or into every walker's (walker < 0)
+  int upload_table(int64_t walker, int64_t n, const std::vector<double>& in) {
+    const int rs = K.hill_stride;
+    if (n <= 0) return 0;
+    if (cfg.mtd_shared) return upload(in.data(), d_hills, n * rs);
+    std::vector<R> tmp((size_t)(n * rs));
+    for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (R)in[i];
+    if (walker >= 0) {
+      CU(cudaMemcpy2DAsync(d_hills + walker, sizeof(R) * (size_t)M, tmp.data(), sizeof(R), sizeof(R), (size_t)(n * rs),
+                           cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+      return 0;
+    }
+    // every walker: upload the n * stride values once, broadcast on the device
+    R* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, sizeof(R) * tmp.size()));
+    cudaError_t err = cudaMemcpyAsync(d_tmp, tmp.data(), sizeof(R) * tmp.size(), cudaMemcpyHostToDevice, stream);
+    if (err == cudaSuccess) {
+      const long long tot = (long long)tmp.size() * M;
+      broadcast_rows_kernel<R><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(tot, M, d_tmp, d_hills);
+      err = cudaGetLastError();
+      launches++;
+    }
+    cudaStreamSynchronize(stream);
+    cudaFree(d_tmp);
+    if (err != cudaSuccess) return fail(this, "hill table upload: %s", cudaGetErrorString(err));
+    return 0;
+  }
+
   int get_hill_sigma2(int64_t walker, double* sigma2, int64_t cap) override {
     CU(cudaSetDevice(cfg.device));
     if (mc_sync_walker(walker)) return 1;
@@ -1181,12 +1611,9 @@ struct Engine : nds_engine {
       return 0;
     }
     const int rs = K.hill_stride;
-    const int64_t es = cfg.mtd_shared ? 1 : M;
-    const int64_t span = cfg.mtd_shared ? n_hills * rs : n_hills * rs * M;
-    std::vector<double> h((size_t)span);
-    if (download(d_hills, h.data(), span)) return 1;
-    const int64_t off = cfg.mtd_shared ? 0 : walker;
-    for (int64_t i = 0; i < n_hills; i++) sigma2[i] = h[(size_t)((i * rs + 3) * es + off)];
+    std::vector<double> h;
+    if (download_table(walker, n_hills, h)) return 1;
+    for (int64_t i = 0; i < n_hills; i++) sigma2[i] = h[(size_t)(i * rs + 3)];
     return 0;
   }
 
@@ -1197,18 +1624,11 @@ struct Engine : nds_engine {
     if (n != n_hills) return fail(this, "nds_set_hill_sigma2: %lld values for %lld hills", (long long)n, (long long)n_hills);
     if (n == 0) return 0;
     const int rs = K.hill_stride;
-    const int64_t es = cfg.mtd_shared ? 1 : M;
-    const int64_t span = cfg.mtd_shared ? n * rs : n * rs * M;
-    std::vector<double> h((size_t)span);
-    if (download(d_hills, h.data(), span)) return 1;
-    for (int64_t w = 0; w < (cfg.mtd_shared ? 1 : M); w++) {
-      if (!cfg.mtd_shared && walker >= 0 && w != walker) continue;
-      for (int64_t i = 0; i < n; i++) {
-        h[(size_t)((i * rs + 2) * es + w)] = 1.0 / sigma2[i];
-        h[(size_t)((i * rs + 3) * es + w)] = sigma2[i];
-      }
-    }
-    return upload(h.data(), d_hills, span);
+    // fields 2, 3 of every record: 1/s and s; one walker's table, or (walker < 0) the same values for all of them
+    std::vector<double> h;
+    if (download_table(walker < 0 ? 0 : walker, n, h)) return 1;
+    for (int64_t i = 0; i < n; i++) { h[(size_t)(i * rs + 2)] = 1.0 / sigma2[i]; h[(size_t)(i * rs + 3)] = sigma2[i]; }
+    return upload_table(walker, n, h);
   }
 
   int get_hills(int64_t walker, int64_t* n, double* centers, double* heights, int64_t cap) override {
@@ -1219,15 +1639,12 @@ struct Engine : nds_engine {
     if (cap < n_hills) return fail(this, "nds_get_hills: capacity %lld < %lld hills", (long long)cap, (long long)n_hills);
     if (!cfg.mtd_shared && (walker < 0 || walker >= M)) return fail(this, "nds_get_hills: bad walker");
     const int rs = K.hill_stride;
-    const int64_t es = cfg.mtd_shared ? 1 : M;
-    const int64_t span = cfg.mtd_shared ? n_hills * rs : n_hills * rs * M;
-    std::vector<double> h((size_t)span);
-    if (download(d_hills, h.data(), span)) return 1;
-    const int64_t off = cfg.mtd_shared ? 0 : walker;
+    std::vector<double> h;
+    if (download_table(walker, n_hills, h)) return 1;
     for (int64_t i = 0; i < n_hills; i++) {
       for (int k = 0; k < cd; k++)
-        if (centers) centers[i * cd + k] = h[(size_t)((i * rs + k) * es + off)];
-      if (heights) heights[i] = h[(size_t)((i * rs + K.hill_hidx) * es + off)];
+        if (centers) centers[i * cd + k] = h[(size_t)(i * rs + k)];
+      if (heights) heights[i] = h[(size_t)(i * rs + K.hill_hidx)];
     }
     return 0;
   }
@@ -1248,24 +1665,23 @@ struct Engine : nds_engine {
           h[(size_t)(i * rs + 3)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
         }
       }
+      if (n > table_cap()) return fail(this, "nds_set_hills: %lld hills > capacity %lld of this rank's table", (long long)n, (long long)table_cap());
       if (clear_hills()) return 1;  // padding records stay (0, 0, 0, -inf)
       if (n && upload(h.data(), d_hills, n * rs)) return 1;
+      if (grid_mode && rebuild_grid(n)) return 1;
     } else {
       // per-walker tables: the given hills are installed for EVERY walker (walker < 0) or one walker
-      std::vector<double> h((size_t)(cfg.mtd_capacity * rs * M));
-      if (download(d_hills, h.data(), (int64_t)h.size())) return 1;
-      for (int64_t w = 0; w < M; w++) {
-        if (walker >= 0 && w != walker) continue;
-        for (int64_t i = 0; i < n; i++) {
-          for (int k = 0; k < cd; k++) h[(size_t)((i * rs + k) * M + w)] = centers[i * cd + k];
-          h[(size_t)((i * rs + K.hill_hidx) * M + w)] = heights[i];
-          if (K.mtd_adaptive) {
-            h[(size_t)((i * rs + 2) * M + w)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
-            h[(size_t)((i * rs + 3) * M + w)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
-          }
+      if (walker >= M) return fail(this, "nds_set_hills: bad walker");
+      std::vector<double> h((size_t)(n * rs), 0.0);
+      for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < cd; k++) h[(size_t)(i * rs + k)] = centers[i * cd + k];
+        h[(size_t)(i * rs + K.hill_hidx)] = heights[i];
+        if (K.mtd_adaptive) {
+          h[(size_t)(i * rs + 2)] = 1.0 / (cfg.mtd_sigma[0] * cfg.mtd_sigma[0]);
+          h[(size_t)(i * rs + 3)] = cfg.mtd_sigma[0] * cfg.mtd_sigma[0];
         }
       }
-      if (upload(h.data(), d_hills, (int64_t)h.size())) return 1;
+      if (n && upload_table(walker, n, h)) return 1;
     }
     n_hills = n;
     need_refresh_vr = false;
@@ -1360,15 +1776,18 @@ struct Engine : nds_engine {
     if (cd > 2) return fail(this, "nds_fes_grid: colvardim %d > 2", cd);
     if (cd == 1) ny = 1;
     const int64_t np = nx * ny;
-    double* d_grid = nullptr;
-    CU(cudaMalloc(&d_grid, sizeof(double) * (size_t)np));
+    double* d_out = nullptr;
+    CU(cudaMalloc(&d_out, sizeof(double) * (size_t)np));
     const R* base = cfg.mtd_shared ? d_hills : d_hills + walker;
-    fes_grid_kernel<R><<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(
-        K, base, n_hills, cfg.mtd_shared ? 1 : M, x0, dx, nx, y0, dy, ny, d_grid);
+    if (grid_mode)  // the accumulated grid IS the sum of all ranks' hills: sample its interpolant
+      grid_sample_kernel<R><<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(K, d_grid, x0, dx, nx, y0, dy, ny, d_out);
+    else
+      fes_grid_kernel<R><<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(
+          K, base, n_hills, cfg.mtd_shared ? 1 : M, x0, dx, nx, y0, dy, ny, d_out);
     launches++;
-    cudaError_t err = cudaMemcpyAsync(grid, d_grid, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, stream);
+    cudaError_t err = cudaMemcpyAsync(grid, d_out, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
-    cudaFree(d_grid);
+    cudaFree(d_out);
     if (err != cudaSuccess) return fail(this, "nds_fes_grid: %s", cudaGetErrorString(err));
     return 0;
   }
@@ -1406,16 +1825,121 @@ struct Engine : nds_engine {
     CU(cudaSetDevice(cfg.device));
     if (!d_hills || !cfg.mtd_shared) return fail(this, "peer tables need a shared hill table");
     if (K.mtd_adaptive) return fail(this, "peer tables do not carry per-hill variances (mtd_adapsig_geo): use the allgather exchange");
-    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(this, "bad rank / nranks");
+    if (nranks < 1 || rank < 0 || rank >= nranks || nranks > NDS_MAX_RANKS) return fail(this, "bad rank / nranks");
+    if (grid_mode && nranks != nranks_cfg) return fail(this, "peer tables: %d ranks, config says %d", nranks, nranks_cfg);
     std::vector<R*> t((size_t)nranks);
     for (int r = 0; r < nranks; r++) t[(size_t)r] = (r == rank) ? d_hills : (R*)tables[r];
     if (d_peer_tables) CU(cudaFree(d_peer_tables));
     CU(cudaMalloc(&d_peer_tables, sizeof(R*) * (size_t)nranks));
     CU(cudaMemcpy(d_peer_tables, t.data(), sizeof(R*) * (size_t)nranks, cudaMemcpyHostToDevice));
-    n_peers = nranks;
+    n_peers = nranks; peer_rank = rank;
+    // the exchange window sits at the same offset behind every rank's table
+    std::vector<unsigned long long*> fl((size_t)nranks);
+    for (int r = 0; r < nranks; r++) fl[(size_t)r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(t[(size_t)r]) + xwin_off);
+    if (d_peer_flags) CU(cudaFree(d_peer_flags));
+    CU(cudaMalloc(&d_peer_flags, sizeof(void*) * (size_t)nranks));
+    CU(cudaMemcpy(d_peer_flags, fl.data(), sizeof(void*) * (size_t)nranks, cudaMemcpyHostToDevice));
+    if (grid_mode) {
+      auto slot = [&](int owner, int par, int writer) {
+        char* base = reinterpret_cast<char*>(t[(size_t)owner]) + xwin_off + 256;
+        return reinterpret_cast<R*>(base + (int64_t)sizeof(R) * grid_elems * (par * nranks + writer));
+      };
+      std::vector<R*> dst((size_t)(2 * nranks)), src((size_t)(2 * nranks));
+      for (int par = 0; par < 2; par++)
+        for (int r = 0; r < nranks; r++) {
+          dst[(size_t)(par * nranks + r)] = slot(r, par, rank);   // my slot on peer r
+          src[(size_t)(par * nranks + r)] = slot(rank, par, r);   // rank r's slot in my window
+        }
+      if (d_slot_dst) { CU(cudaFree(d_slot_dst)); CU(cudaFree(d_slot_src)); }
+      CU(cudaMalloc(&d_slot_dst, sizeof(R*) * dst.size()));
+      CU(cudaMalloc(&d_slot_src, sizeof(R*) * src.size()));
+      CU(cudaMemcpy(d_slot_dst, dst.data(), sizeof(R*) * dst.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_slot_src, src.data(), sizeof(R*) * src.size(), cudaMemcpyHostToDevice));
+    }
     if (opened_by_ipc)
       for (int r = 0; r < nranks; r++)
         if (r != rank) ipc_opened.push_back(tables[r]);
+    return 0;
+  }
+
+  int set_peer_barrier(int on_device) override {
+    if (on_device && !d_peer_flags) return fail(this, "nds_set_peer_barrier: open the peer tables first");
+    device_barrier = on_device != 0;
+    return 0;
+  }
+
+  // native NCCL communicator for the hill / grid exchange: a ready ncclComm_t of the caller, or the 128-byte
+  // unique id from nds_nccl_unique_id() (broadcast by the caller's launcher), from which the engine builds its own
+  int set_comm(const void* unique_id, void* existing, int rank, int nranks) override {
+    CU(cudaSetDevice(cfg.device));
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(this, "nds_set_comm: NCCL is not available (%s)", api.why.c_str());
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(this, "nds_set_comm: bad rank / nranks");
+    if (comm && comm_owned) api.CommDestroy(comm);
+    comm = nullptr; comm_owned = false;
+    if (existing) {
+      comm = (NcclApi::comm_t)existing;
+    } else {
+      if (!unique_id) return fail(this, "nds_set_comm: neither a communicator nor a unique id");
+      NcclApi::unique_id id;
+      memcpy(&id, unique_id, sizeof id);
+      if (nccl_check(api.CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank")) return 1;
+      comm_owned = true;
+    }
+    comm_rank = rank; comm_nranks = nranks;
+    return 0;
+  }
+
+  int get_mtd_grid(double* out, int64_t cap) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!grid_mode) return fail(this, "nds_get_mtd_grid: mtd_grid is off");
+    if (cap < grid_elems) return fail(this, "nds_get_mtd_grid: capacity %lld < %lld", (long long)cap, (long long)grid_elems);
+    return download(d_grid, out, grid_elems);
+  }
+  int set_mtd_grid(const double* in, int64_t n) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!grid_mode) return fail(this, "nds_set_mtd_grid: mtd_grid is off");
+    if (n != grid_elems) return fail(this, "nds_set_mtd_grid: %lld values, the grid has %lld", (long long)n, (long long)grid_elems);
+    need_refresh_vr = false;
+    return upload(in, d_grid, grid_elems);
+  }
+  int64_t mtd_grid_outside() override {
+    if (!grid_mode) return 0;
+    cudaSetDevice(cfg.device);
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, d_grid_outside, sizeof h, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    return (int64_t)h;
+  }
+
+  // grid <- footprint of the first n records of the (local) hill table
+  int rebuild_grid(int64_t n) {
+    CU(cudaMemsetAsync(d_grid, 0, sizeof(R) * (size_t)grid_elems, stream));
+    if (n > 0) {
+      const unsigned tiles = (unsigned)(((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY));
+      grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, d_hills, n, nullptr, 0, d_grid, 1);
+      CU(cudaGetLastError());
+      launches++;
+    }
+    return 0;
+  }
+
+  // order-independent checksum of hill records [first, first + n) of this rank's table (multi-rank exchange checks)
+  int table_checksum(uint64_t* sum, int64_t first, int64_t n) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_hills || !cfg.mtd_shared) return fail(this, "nds_table_checksum: no shared hill table");
+    if (first < 0 || n < 0 || first + n > n_hills) return fail(this, "nds_table_checksum: records [%lld, %lld) of %lld", (long long)first, (long long)(first + n), (long long)n_hills);
+    CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+    const long long words = n * K.hill_stride * (long long)(sizeof(R) / 4);
+    if (words > 0) {
+      checksum_kernel<<<296, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_hills + first * K.hill_stride), words, d_counter);
+      CU(cudaGetLastError());
+      launches++;
+    }
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d_counter, sizeof h, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    *sum = h;
     return 0;
   }
 
@@ -1570,6 +2094,28 @@ int nds_open_peer_tables(nds_engine* e, const void* handles, int nranks, int ran
   }
   return e->set_peer_tables(ptrs.data(), nranks, rank, true);
 }
+int nds_set_peer_barrier(nds_engine* e, int on_device) { return e->set_peer_barrier(on_device); }
+int nds_nccl_unique_id(void* id128) {
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(nullptr, "nds_nccl_unique_id: NCCL is not available (%s)", api.why.c_str());
+  NcclApi::unique_id id;
+  const int rc = api.GetUniqueId(&id);
+  if (rc) return fail(nullptr, "ncclGetUniqueId failed: %s", api.GetErrorString(rc));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+int nds_set_comm(nds_engine* e, const void* unique_id, void* nccl_comm, int rank, int nranks) {
+  return e->set_comm(unique_id, nccl_comm, rank, nranks);
+}
+int nds_exchange_info(nds_engine* e, double* exchange_ms, int64_t* n_exchanges) { return e->exchange_info(exchange_ms, n_exchanges); }
+int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum) { return e->table_checksum(sum, first, n); }
+int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap) { return e->get_mtd_grid(out, cap); }
+int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n) { return e->set_mtd_grid(in, n); }
+int64_t nds_mtd_grid_outside(nds_engine* e) { return e->mtd_grid_outside(); }
+int nds_submit(nds_engine* e, const void* host_xv, int64_t nsteps, void* host_xvt, int32_t chunks) {
+  return e->submit(host_xv, nsteps, host_xvt, chunks);
+}
+int nds_wait(nds_engine* e) { return e->sync(); }
 void* nds_stream(nds_engine* e) { return (void*)e->stream; }
 int64_t nds_n_hills(const nds_engine* e, int64_t walker) {
   const_cast<nds_engine*>(e)->mc_sync_walker(walker);  // MC: every walker has its own count

@@ -15,6 +15,55 @@
 namespace nds {
 
 constexpr int NDS_BLOCK = 128;
+constexpr int NDS_BLOCK_WIDE = 512;  // md_block_wide (grid-accumulated bias: one CTA per SM holds the grid)
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk; SASS: UBLKCP + SYNCS), shared by mtd_block and the grid loader
+NDS_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+NDS_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+NDS_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NDS_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA: global -> shared bulk copy that completes on an mbarrier (SASS: UBLKCP)
+NDS_DEV void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Whole bias grid -> dynamic shared memory of this CTA (mtd_grid): thread 0 issues the bulk copies, everybody waits on
+// the mbarrier.  bytes is a multiple of 16 and below the 2^20 - 1 transaction-count limit of one mbarrier phase.
+NDS_DEV void grid_to_smem(unsigned char* smem, const void* grid, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes);
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < bytes; off += CHUNK)
+      tma_load_1d(smem + off, (const unsigned char*)grid + off, bytes - off < CHUNK ? bytes - off : CHUNK, bar);
+  }
+  mbar_wait(bar, 0);
+}
 
 // NDS_INT_NVE, NDS_INT_RESCALE and NDS_INT_MINIMIZE draw no noise
 __host__ __device__ constexpr int normals_per_step(int integ, int nd) {
@@ -55,14 +104,14 @@ struct Eval {
 template <typename R, int ND, bool ENERGY>
 NDS_DEV void eval_all(const Consts<R>& K, int pot, int cv, int tcv, int cd, int bias_mask,
                       const R (&x)[ND], const WalkerBias<R, ND>& wb, const R* hills, long long n_hills,
-                      long long elem_stride, Eval<R, ND>& e) {
+                      long long elem_stride, Eval<R, ND>& e, const GridView<R> gv = GridView<R>{nullptr, 0, nullptr}) {
   cv_eval<R, ND>(K, cv, K.rot, x, e.cv);
   // PE bias needs the potential energy even when the caller does not
   if (ENERGY || (bias_mask & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
   else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
   if (bias_mask != 0)
     bias_eval<R, ND>(K, bias_mask, cv, cd, x, e.cv, wb, hills, n_hills, elem_stride, e.pe, e.fp, e.be,
-                     e.fb, e.vm);
+                     e.fb, e.vm, gv);
   else {
     e.be = (R)0; e.vm = (R)0;
 #pragma unroll
@@ -109,8 +158,7 @@ constexpr int md_block_min_ctas() {
 }
 
 template <class S>
-__global__ void __launch_bounds__(NDS_BLOCK, md_block_min_ctas<S>())
-md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
+NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A) {
   using R = typename S::R;
   constexpr int ND = S::ND;
   constexpr int INTEG = S::INTEG;  // always compile-time
@@ -126,8 +174,19 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   // generated already multiplied by c2 and xi[] below holds c2 * xi
   constexpr bool PRESCALED = is_f32<R>::value && INTEG == NDS_INT_LANGEVIN;
 
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
+  const long long w = A.slot0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
+  // mtd_grid: every CTA first copies the whole bias grid into its shared memory (1-D TMA bulk copies)
+  GridView<R> gv{A.grid, 0, A.grid_outside};
+  if constexpr (PACK == 1 && (S::BIAS < 0 || (S::BIAS & BIAS_MTD_GRID) != 0)) {
+    if (A.grid_smem) {
+      extern __shared__ __align__(128) unsigned char md_smem[];
+      __shared__ uint64_t grid_bar;
+      grid_to_smem(md_smem, A.grid, (uint32_t)(4u * sizeof(R)) * (uint32_t)(K.grid_nx * K.grid_ny), &grid_bar);
+      gv.grid = reinterpret_cast<const R*>(md_smem);
+      gv.smem = 1;
+    }
+  }
   if (w >= (A.n_active > 0 ? A.n_active : M)) return;
   // local walker index of this slot (Philox stream, noise row); a packed thread owns slots 2w and 2w+1
   const long long lw = A.ids ? A.ids[w * PACK] : w * PACK;
@@ -182,7 +241,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   // ---- forces at the current positions: MD.begin (md.py:101-110) / refresh after a deposition
   //      (gaus.py:138-146).  Identical to the values the previous launch ended with.
   Eval<R, ND> e;
-  eval_all<R, ND, INTEG == NDS_INT_MINIMIZE>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+  eval_all<R, ND, INTEG == NDS_INT_MINIMIZE>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
   if (A.refresh_vr && (bias_mask & BIAS_MTD)) A.vr[w] = e.vm;  // Gaussian.VR, gaus.py:292-293
   R f[ND];
 #pragma unroll
@@ -267,7 +326,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           R n2 = (R)0, xold[ND];
 #pragma unroll
           for (int d = 0; d < ND; d++) { n2 += f[d] * f[d]; xold[d] = x[d]; x[d] += f[d] / K.m * K.dt * K.dt; }
-          eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+          eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
 #pragma unroll
           for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];
           const R dE = e.pe + e.be - pe_prev;
@@ -314,7 +373,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           x[d] = x[d] + dx;
         }
         // ---- colvar, potential and biases at the new positions, md.py:179-188
-        eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e);
+        eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
 #pragma unroll
         for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];
         // ---- second half kick, md.py:190-198
@@ -376,7 +435,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
           if (dumping && event) {
             // io/dump.py:76-102: full observables of this walker at NDRun.step == s
             Eval<R, ND> o;
-            eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+            eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o, gv);
             write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
           }
           }
@@ -422,7 +481,7 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   }
   Eval<R, ND> o;
   if constexpr (INTEG == NDS_INT_MINIMIZE) o = e;  // pe / forces / colv of the last (trial) point, minimize.py:61-67
-  else eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o);
+  else eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o, gv);
   R v2 = (R)0;
 #pragma unroll
   for (int d = 0; d < ND; d++) {
@@ -464,13 +523,27 @@ md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant_
   }
 }
 
+template <class S>
+__global__ void __launch_bounds__(NDS_BLOCK, md_block_min_ctas<S>())
+md_block(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
+  md_body<S>(K, A);
+}
+
+// same body, CTAs of up to 512 threads: with mtd_grid the shared-memory copy of the grid leaves room for one CTA
+// per SM, so large ensembles need wide CTAs to keep the SM busy
+template <class S>
+__global__ void __launch_bounds__(NDS_BLOCK_WIDE, 1)
+md_block_wide(const __grid_constant__ Consts<typename S::R> K, const __grid_constant__ BlockArgs<typename S::R> A) {
+  md_body<S>(K, A);
+}
+
 // ---------------------------------------------------------------------------------- eval_at
 // potential.compute(x), colvar.compute/jacobian(x), sum of fix.compute(x0, col0) at n configurations.
 template <typename R, int ND>
 __global__ void __launch_bounds__(NDS_BLOCK)
 eval_at_kernel(const __grid_constant__ Consts<R> K, long long n, const R* __restrict__ xin,
                const R* hills, long long n_hills, long long elem_stride, R* V, R* F, R* colv, R* J,
-               R* Vb, R* Fb) {
+               R* Vb, R* Fb, const R* grid = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   R x[ND];
@@ -482,7 +555,7 @@ eval_at_kernel(const __grid_constant__ Consts<R> K, long long n, const R* __rest
   Eval<R, ND> e;
   const int cd = K.cd;
   eval_all<R, ND, true>(K, K.pot, K.cv, K.tcv, cd, K.bias_mask & ~BIAS_UMB_WALKER, x, wb, hills,
-                        n_hills, elem_stride, e);
+                        n_hills, elem_stride, e, GridView<R>{grid, 0, nullptr});
   if (V) V[i] = e.pe;
   if (Vb) Vb[i] = e.be;
 #pragma unroll

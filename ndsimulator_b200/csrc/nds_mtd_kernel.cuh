@@ -23,36 +23,6 @@ constexpr int MTD_TILE_BYTES = 32768;  // one shared-memory tile: 2048 fp32 reco
 constexpr int MTD_NBUF = 3;            // tiles in flight
 template <typename R> __host__ __device__ constexpr int mtd_tile_records() { return MTD_TILE_BYTES / (4 * (int)sizeof(R)); }
 
-NDS_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-NDS_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-NDS_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-NDS_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// 1-D TMA: global -> shared bulk copy that completes on an mbarrier (SASS: UBLKCP)
-NDS_DEV void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
 template <typename R> struct HillRec;
 template <> struct HillRec<float> { float4 v; NDS_DEV float h0() const { return v.x; } NDS_DEV float h1() const { return v.y; } NDS_DEV float w() const { return v.z; } NDS_DEV float lw() const { return v.w; } };
 template <> struct HillRec<double> { double4 v; NDS_DEV double h0() const { return v.x; } NDS_DEV double h1() const { return v.y; } NDS_DEV double w() const { return v.z; } };

@@ -467,6 +467,115 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
   V = v;
 }
 
+// ---------------------------------------------------------------------------- grid-accumulated bias
+// mtd_grid: the metadynamics bias is kept as a regular grid of (V, h0 V_0, h1 V_1, h0 h1 V_01) (value, first
+// derivatives and the cross derivative, pre-multiplied by the spacings), accumulated hill by hill at deposition
+// time (grid_accumulate_kernel) -- the reference's own incremental trick for its FES plot (gaus.py:380-393).  The
+// step evaluates V and g = -dV/dc by bicubic Hermite interpolation: 4 vector loads + ~60 FMAs whatever the
+// number of hills.  The interpolant is C1 and its gradient is the exact derivative of the interpolated energy, so
+// the bias force stays conservative.  Error for a Gaussian of width sigma at spacing h: (h/sigma)^4 * 3/384 of the
+// hill height in V (3e-5 at h = sigma/4).
+// A point outside [lo, hi] sees no bias (V = 0, g = 0) and is counted in *outside.
+template <typename R> struct Real4;
+template <> struct Real4<float> { using type = float4; };
+template <> struct Real4<double> { using type = double4; };
+
+template <typename R, bool SMEM>
+NDS_DEV typename Real4<R>::type grid_load(const R* grid, int idx) {
+  using V4 = typename Real4<R>::type;
+  if constexpr (SMEM && sizeof(R) == 4) {
+    float4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(grid) + (unsigned)idx * 16u;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+  } else if constexpr (SMEM) {
+    return reinterpret_cast<const V4*>(grid)[idx];
+  } else {
+    if constexpr (sizeof(R) == 4) return __ldg(reinterpret_cast<const float4*>(grid) + idx);
+    else {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(grid) + 2 * idx);
+      const double2 b = __ldg(reinterpret_cast<const double2*>(grid) + 2 * idx + 1);
+      return double4{a.x, a.y, b.x, b.y};
+    }
+  }
+}
+
+// cubic Hermite basis on [0, 1]: a0 = h00, a1 = h01 (values), b0 = h10, b1 = h11 (slopes), and derivatives
+template <typename R>
+NDS_DEV void hermite_basis(R t, R (&a)[2], R (&b)[2], R (&da)[2], R (&db)[2]) {
+  const R u = (R)1 - t;
+  a[0] = ((R)1 + (R)2 * t) * (u * u);
+  a[1] = (t * t) * ((R)3 - (R)2 * t);
+  b[0] = t * (u * u);
+  b[1] = -((t * t) * u);
+  da[1] = (R)6 * (t * u);
+  da[0] = -da[1];
+  db[0] = u * ((R)1 - (R)3 * t);
+  db[1] = t * ((R)3 * t - (R)2);
+}
+
+template <typename R, int ND, bool SMEM>
+NDS_DEV void grid_interp(const Consts<R>& K, int cd, const R* grid, const R (&c)[ND], R& V, R (&g)[ND],
+                         unsigned long long* outside) {
+  V = (R)0;
+#pragma unroll
+  for (int k = 0; k < ND; k++) g[k] = (R)0;
+  if constexpr (pack_of<R>::value == 1) {
+    const int nx = K.grid_nx, ny = K.grid_ny;
+    const R u = (c[0] - K.grid_lo[0]) * K.grid_invh[0];
+    R w = (R)0;
+    if (cd > 1) w = (c[ND > 1 ? 1 : 0] - K.grid_lo[1]) * K.grid_invh[1];
+    // !(a >= b) forms: a NaN colvar counts as outside
+    bool out = !(u >= (R)0) || !(u <= (R)(nx - 1));
+    if (cd > 1) out = out || !(w >= (R)0) || !(w <= (R)(ny - 1));
+    if (out) {
+      if (outside) atomicAdd(outside, 1ull);
+      return;
+    }
+    int i = (int)u;
+    if (i > nx - 2) i = nx - 2;
+    const R t = u - (R)i;
+    R a[2], b[2], da[2], db[2];
+    hermite_basis<R>(t, a, b, da, db);
+    if (cd == 1) {
+      const auto G0 = grid_load<R, SMEM>(grid, i), G1 = grid_load<R, SMEM>(grid, i + 1);
+      V = a[0] * G0.x + b[0] * G0.y + a[1] * G1.x + b[1] * G1.y;
+      const R dt = da[0] * G0.x + db[0] * G0.y + da[1] * G1.x + db[1] * G1.y;
+      g[0] = -(dt * K.grid_invh[0]);
+      return;
+    }
+    int j = (int)w;
+    if (j > ny - 2) j = ny - 2;
+    const R s = w - (R)j;
+    R as[2], bs[2], das[2], dbs[2];
+    hermite_basis<R>(s, as, bs, das, dbs);
+    R Vt = (R)0, dVt = (R)0, dVs = (R)0;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const auto G0 = grid_load<R, SMEM>(grid, j * nx + i + p);
+      const auto G1 = grid_load<R, SMEM>(grid, (j + 1) * nx + i + p);
+      // contraction along s at column i + p: value, t-slope, and their s-derivatives
+      const R vp = as[0] * G0.x + bs[0] * G0.z + as[1] * G1.x + bs[1] * G1.z;
+      const R yp = as[0] * G0.y + bs[0] * G0.w + as[1] * G1.y + bs[1] * G1.w;
+      const R vps = das[0] * G0.x + dbs[0] * G0.z + das[1] * G1.x + dbs[1] * G1.z;
+      const R yps = das[0] * G0.y + dbs[0] * G0.w + das[1] * G1.y + dbs[1] * G1.w;
+      Vt += a[p] * vp + b[p] * yp;
+      dVt += da[p] * vp + db[p] * yp;
+      dVs += a[p] * vps + b[p] * yps;
+    }
+    V = Vt;
+    g[0] = -(dVt * K.grid_invh[0]);
+    if constexpr (ND > 1) g[1] = -(dVs * K.grid_invh[1]);
+  }
+}
+
+template <typename R>
+struct GridView {  // accumulated bias grid seen by one evaluation (mtd_grid)
+  const R* grid;   // 4 reals per point: shared-memory copy (smem = 1) or the global array
+  int smem;
+  unsigned long long* outside;
+};
+
 struct HillView {
   const void* base;      // hill table (engine precision)
   long long n;           // hills visible to this evaluation
@@ -480,7 +589,7 @@ template <typename R, int ND>
 NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const R (&x)[ND],
                        const CvOut<R, ND>& o, const WalkerBias<R, ND>& wb, const R* hills,
                        long long n_hills, long long elem_stride, R pe, const R (&fpot)[ND], R& Vb,
-                       R (&fb)[ND], R& Vm) {
+                       R (&fb)[ND], R& Vm, const GridView<R> gv = GridView<R>{nullptr, 0, nullptr}) {
   Vb = (R)0;
   Vm = (R)0;
 #pragma unroll
@@ -511,8 +620,13 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
   }
   if (bias_mask & BIAS_MTD) {
     R g[ND], f[ND];
-    hill_sum<R, ND>(K, cd, hills, n_hills, elem_stride, o.c, Vm, g);
-    if (n_hills > 0) {
+    if (bias_mask & BIAS_MTD_GRID) {
+      if (gv.smem) grid_interp<R, ND, true>(K, cd, gv.grid, o.c, Vm, g, gv.outside);
+      else grid_interp<R, ND, false>(K, cd, gv.grid, o.c, Vm, g, gv.outside);
+    } else {
+      hill_sum<R, ND>(K, cd, hills, n_hills, elem_stride, o.c, Vm, g);
+    }
+    if (n_hills > 0 || (bias_mask & BIAS_MTD_GRID)) {
       cv_pullback<R, ND>(cv, K.rot, x, o, g, f);
 #pragma unroll
       for (int d = 0; d < ND; d++) fb[d] += f[d];

@@ -15,6 +15,7 @@ struct Variant {
   VariantKey key;
   const char* name;
   void* launch;  // BlockLaunchFn<R>
+  bool wide;     // md_block_wide: may carry the bias grid in shared memory
 };
 
 template <typename R>
@@ -23,9 +24,27 @@ using BlockLaunchFn = cudaError_t (*)(const Consts<R>&, const BlockArgs<R>&, cud
 template <class S>
 cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
                             cudaStream_t st) {
-  const long long n = A.n_active > 0 ? A.n_active : A.M;
+  const long long n = (A.n_active > 0 ? A.n_active : A.M) - A.slot0;
   const unsigned grid = (unsigned)((n + NDS_BLOCK - 1) / NDS_BLOCK);
   md_block<S><<<grid, NDS_BLOCK, 0, st>>>(K, A);
+  return cudaGetLastError();
+}
+
+// wide CTAs (md_block_wide): used by the mtd_grid variants, whose launch carries the shared-memory copy of the grid
+template <class S>
+cudaError_t launch_md_block_wide(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
+                                 cudaStream_t st) {
+  using R = typename S::R;
+  const long long n = (A.n_active > 0 ? A.n_active : A.M) - A.slot0;
+  const size_t smem = A.grid_smem ? sizeof(R) * 4 * (size_t)K.grid_nx * (size_t)K.grid_ny : 0;
+  // few walkers: many small CTAs (latency-bound, one warp per scheduler); many walkers: one wide CTA per SM
+  const int threads = n >= 148LL * 512 ? 512 : (n >= 148LL * 256 ? 256 : 128);
+  if (smem > 48 * 1024) {  // per device, cheap: set on every launch that needs the opt-in
+    cudaError_t e = cudaFuncSetAttribute(md_block_wide<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned grid = (unsigned)((n + threads - 1) / threads);
+  md_block_wide<S><<<grid, threads, smem, st>>>(K, A);
   return cudaGetLastError();
 }
 
@@ -38,7 +57,14 @@ template <class S>
 Variant make_variant(const char* name) {
   return Variant{VariantKey{prec_of<typename S::R>::value, S::ND, S::POT, S::CV, S::TCV, S::INTEG,
                             S::BIAS, S::METHOD, S::NOISE, S::DUMP, S::NBASIN},
-                 name, (void*)&launch_md_block<S>};
+                 name, (void*)&launch_md_block<S>, false};
+}
+
+template <class S>
+Variant make_variant_wide(const char* name) {
+  return Variant{VariantKey{prec_of<typename S::R>::value, S::ND, S::POT, S::CV, S::TCV, S::INTEG,
+                            S::BIAS, S::METHOD, S::NOISE, S::DUMP, S::NBASIN},
+                 name, (void*)&launch_md_block_wide<S>, true};
 }
 
 // shared-hill metadynamics kernels (nds_mtd_kernel.cuh): W walkers per warp, NW warps per CTA
@@ -63,5 +89,6 @@ const Variant* variants_generic_f64_nd1(int* n);
 const Variant* variants_generic_f64_nd2(int* n);
 const Variant* variants_generic_f64_nd5(int* n);
 const Variant* variants_hot(int* n);
+const Variant* variants_grid(int* n);
 
 }  // namespace nds

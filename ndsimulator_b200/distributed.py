@@ -49,10 +49,16 @@ def attach_hill_exchange(engine, group=None):
     import torch
     import torch.distributed as dist
 
+    real = torch.float32 if engine.cfg.precision == 0 else torch.float64
+
     def exchange(ptr, bytes_per_rank, rank_offset_bytes):
         world = dist.get_world_size(group)
-        seg = torch.as_tensor(_DevSegment(ptr, bytes_per_rank * world), device="cuda")
-        exchange_segment(seg, bytes_per_rank, rank_offset_bytes, group)
+        if rank_offset_bytes < 0:  # mtd_grid: sum the grid increments of all ranks in place
+            buf = torch.as_tensor(_DevSegment(ptr, bytes_per_rank), device="cuda").view(real)
+            dist.all_reduce(buf, group=group)
+        else:
+            seg = torch.as_tensor(_DevSegment(ptr, bytes_per_rank * world), device="cuda")
+            exchange_segment(seg, bytes_per_rank, rank_offset_bytes, group)
         torch.cuda.current_stream().synchronize()
         return 0
 
@@ -60,10 +66,24 @@ def attach_hill_exchange(engine, group=None):
     return engine
 
 
-def attach_peer_hill_exchange(engine, group=None):
-    """NVLink peer-memory exchange: every rank maps every other rank's hill table (CUDA IPC) and the
-    deposition kernel stores new records straight into all of them; the only host-side step left per
-    deposition stride is a barrier (a 1-element NCCL all-reduce)."""
+def attach_native_hill_exchange(engine, group=None):
+    """Native NCCL exchange (``nds_set_comm``): rank 0 creates an ncclUniqueId, torch.distributed only carries
+    its 128 bytes to the other ranks; from then on the engine runs its allgather / all-reduce itself, on its
+    own stream, with no host synchronisation and no Python in the deposition path."""
+    import torch.distributed as dist
+    from .engine import nccl_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.set_comm(unique_id=box[0], rank=rank, nranks=world)
+    return engine
+
+
+def attach_peer_hill_exchange(engine, group=None, device_barrier=None):
+    """NVLink peer-memory exchange: every rank maps every other rank's hill table + exchange window (CUDA IPC)
+    and the deposition kernel stores new records (or, with mtd_grid, its grid increment) straight into all of
+    them.  The barrier between the ranks runs on the device (one warp signalling / polling flags in peer memory)
+    when every rank has a GPU of its own; ranks sharing a GPU fall back to a 1-element all-reduce on the host."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -71,6 +91,15 @@ def attach_peer_hill_exchange(engine, group=None):
     dist.all_gather_object(handles, engine.hills_ipc_handle(), group=group)
     engine.open_peer_tables(handles, rank)
     token = torch.zeros(1, device="cuda")
+    if device_barrier is None:
+        ids = [None] * world
+        props = torch.cuda.get_device_properties(torch.cuda.current_device())
+        dist.all_gather_object(ids, (os.uname().nodename, str(getattr(props, "uuid", torch.cuda.current_device()))), group=group)
+        device_barrier = len(set(ids)) == world and os.environ.get("NDS_HOST_BARRIER") != "1"
+    if device_barrier:
+        dist.barrier(group=group)  # every rank has mapped every window before the first flag is written
+        engine.set_peer_barrier(True)
+        return engine
 
     def barrier(ptr, bytes_per_rank, rank_offset_bytes):
         assert bytes_per_rank == 0

@@ -194,6 +194,52 @@ class Engine:
         arr = (C.c_void_p * len(pointers))(*pointers)
         self._check(self.lib.nds_set_peer_tables(self.h, arr, len(pointers), int(rank)))
 
+    # ---- native exchange / grid-accumulated bias
+    def set_comm(self, unique_id: bytes = None, comm_ptr: int = None, rank=0, nranks=1):
+        """Native NCCL exchange on the engine's stream (``nds_set_comm``): pass the 128-byte unique id of
+        :func:`nccl_unique_id` (same on every rank) or a raw ``ncclComm_t``."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._check(self.lib.nds_set_comm(self.h, buf, C.c_void_p(comm_ptr) if comm_ptr else None, int(rank), int(nranks)))
+
+    def set_peer_barrier(self, on_device=True):
+        self._check(self.lib.nds_set_peer_barrier(self.h, int(bool(on_device))))
+
+    def exchange_info(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.nds_exchange_info(self.h, C.byref(ms), C.byref(n)))
+        return dict(exchange_ms=ms.value, n_exchanges=n.value)
+
+    def table_checksum(self, first=0, n=None):
+        n = self.n_hills() - first if n is None else n
+        out = C.c_uint64()
+        self._check(self.lib.nds_table_checksum(self.h, int(first), int(n), C.byref(out)))
+        return int(out.value)
+
+    def grid_shape(self):
+        return (int(self.cfg.mtd_grid_n[1]) if self.cd > 1 else 1, int(self.cfg.mtd_grid_n[0]), 4)
+
+    def get_mtd_grid(self):
+        """Accumulated bias grid ``[ny][nx][4]`` = (V, h0 dV/dc0, h1 dV/dc1, h0 h1 d2V/dc0dc1)."""
+        g = np.empty(self.grid_shape())
+        self._check(self.lib.nds_get_mtd_grid(self.h, _p(g), g.size))
+        return g
+
+    def set_mtd_grid(self, g):
+        g = _f64(g, self.grid_shape())
+        self._check(self.lib.nds_set_mtd_grid(self.h, _p(g), g.size))
+
+    def mtd_grid_outside(self):
+        return int(self.lib.nds_mtd_grid_outside(self.h))
+
+    def submit(self, host_in, nsteps, host_out, chunks=1):
+        """Asynchronous pass: ``host_in`` / ``host_out`` are raw addresses (ints) of pinned blocks in the engine's
+        precision, ``[2 ndim][M]`` and ``[2 ndim + 5][M]``; complete with :meth:`wait`."""
+        self._check(self.lib.nds_submit(self.h, C.c_void_p(host_in) if host_in else None, int(nsteps),
+                                        C.c_void_p(host_out) if host_out else None, int(chunks)))
+
+    def wait(self):
+        self._check(self.lib.nds_wait(self.h))
+
     def fes_grid(self, x0, dx, nx, y0=0.0, dy=1.0, ny=1, walker=0):
         g = np.empty((ny, nx))
         self._check(self.lib.nds_fes_grid(self.h, walker, x0, dx, nx, y0, dy, ny, _p(g)))
@@ -236,6 +282,8 @@ class Engine:
                 ck.update(hills_centers=c, hills_heights=h)
                 if self.cfg.mtd_adapsig_geo:
                     ck["hills_sigma2"] = self.get_hill_sigma2(0)
+                if self.cfg.mtd_grid:  # the grid holds every rank's hills; the table only this rank's
+                    ck["mtd_grid"] = self.get_mtd_grid()
             else:  # per-walker tables: the raw storage (engine layout)
                 n = self.n_hills(0)
                 raw = np.empty(int(self.lib.nds_hill_table_size(self.h, n)))
@@ -253,6 +301,8 @@ class Engine:
             self.set_vr(ck["vr"])
         if "hills_heights" in ck:
             self.set_hills(ck["hills_centers"], ck["hills_heights"], sigma2=ck.get("hills_sigma2"))
+            if "mtd_grid" in ck:
+                self.set_mtd_grid(ck["mtd_grid"])
             self.set_vr(ck["vr"])
         if "alive" in ck:
             b = np.ascontiguousarray(ck["basin"], dtype=np.int32)
@@ -339,6 +389,15 @@ class Engine:
     @property
     def kernel_name(self):
         return self.lib.nds_kernel_name(self.h).decode()
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId for :meth:`Engine.set_comm` (create on one rank, hand to all)."""
+    lib = _abi.load_library()
+    buf = C.create_string_buffer(128)
+    if lib.nds_nccl_unique_id(buf):
+        raise NdsError(lib.nds_last_error(None).decode())
+    return buf.raw
 
 
 def philox_kat(ctr, key, device=0):
