@@ -189,6 +189,12 @@ typedef struct nds_config {
    * colvardim 1, per-hill variance records like mtd_adapsig_geo.                                                 */
   int32_t mtd_adapsig_hist;
   int32_t reserved5;
+
+  /* colvar histogram accumulated ON THE DEVICE over the run ("CV histogram on-device"; the
+   * reference's io/plot.py:562-572 histogram, but of every walker at every dump step): bins hist_n per colvar over
+   * [hist_lo, hist_hi); sampled at dump_freq cadence (dump_freq > 0 required), read with nds_get_histogram().   */
+  int32_t hist_n[2];                    /* 0: off; n[1] = 1 for colvardim 1 */
+  double hist_lo[2], hist_hi[2];
 } nds_config;
 
 typedef struct nds_engine nds_engine;
@@ -385,6 +391,12 @@ NDS_API int nds_drain_frames(nds_engine* e, double* out, int64_t max_frames, int
  * grid of io/plot.py:517-519).  grid[ny][nx], X = x0 + i*dx, Y = y0 + j*dy.                     */
 NDS_API int nds_fes_grid(nds_engine* e, int64_t walker, double x0, double dx, int64_t nx, double y0,
                  double dy, int64_t ny, double* grid);
+
+/* the histogram accumulated inside the step kernels since nds_begin() (cfg.hist_n): counts[ny][nx]; clear != 0
+ * zeroes it afterwards.  nds_frames_f32() = 1 when the device frame ring holds float rows (fp32 engines;
+ * nds_drain_frames always delivers doubles).                                                            */
+NDS_API int nds_get_histogram(nds_engine* e, int64_t* counts, int clear);
+NDS_API int nds_frames_f32(const nds_engine* e);
 
 /* on-device histogram of the current colvar values of all local walkers (io/plot.py:562-572).
  * counts[ny][nx] (ny = 1 for colvardim 1).                                                       */

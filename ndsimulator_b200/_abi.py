@@ -86,6 +86,7 @@ class NdsConfig(C.Structure):
         ("mtd_grid", C.c_int32), ("mtd_grid_n", C.c_int32 * 2), ("reserved4", C.c_int32),
         ("mtd_grid_lo", C.c_double * 2), ("mtd_grid_hi", C.c_double * 2),
         ("mtd_adapsig_hist", C.c_int32), ("reserved5", C.c_int32),
+        ("hist_n", C.c_int32 * 2), ("hist_lo", C.c_double * 2), ("hist_hi", C.c_double * 2),
     ]
 
 
@@ -135,6 +136,8 @@ _PROTOTYPES = {
     "nds_get_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "nds_set_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "nds_mtd_grid_outside": (C.c_int64, [C.c_void_p]),
+    "nds_get_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "nds_frames_f32": (C.c_int, [C.c_void_p]),
     "nds_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "nds_wait": (C.c_int, [C.c_void_p]),
     "nds_get_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),

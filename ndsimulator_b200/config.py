@@ -96,6 +96,9 @@ class RunSpec:
     mtd_grid_lo: Optional[np.ndarray] = None
     mtd_grid_hi: Optional[np.ndarray] = None
     mtd_grid_n: Optional[np.ndarray] = None
+    hist_n: Optional[np.ndarray] = None        # in-kernel colvar histogram (new keys hist_n / hist_lo / hist_hi)
+    hist_lo: Optional[np.ndarray] = None
+    hist_hi: Optional[np.ndarray] = None
     pe_thred: float = 0.0
     n_basins: int = 0
     criteria: Optional[np.ndarray] = None
@@ -195,7 +198,14 @@ class RunSpec:
         c.emin = float(self.emin)
         c.min_gtol = float(self.min_gtol)
         c.min_maxiter = int(self.min_maxiter if self.min_maxiter is not None else self.steps * 10)
-        c.dump_freq = int(self.dump_freq) if self.dump else 0
+        if self.hist_n is not None:
+            for k in range(min(self.colvardim, 2)):
+                c.hist_n[k] = int(self.hist_n[k])
+                c.hist_lo[k] = float(self.hist_lo[k])
+                c.hist_hi[k] = float(self.hist_hi[k])
+            if self.colvardim == 1:
+                c.hist_n[1] = 1
+        c.dump_freq = int(self.dump_freq) if (self.dump or self.hist_n is not None) else 0
         c.dump_walkers = int(min(self.dump_walkers, self.n_walkers)) if self.dump else 0
         c.dump_capacity = int(self.dump_capacity)
         c.stat_freq = int(self.stat_freq)
@@ -456,6 +466,21 @@ def parse(config: dict) -> RunSpec:
             per = spec.n_walkers_global if spec.mtd_shared else 1
             cap = n_dep * per
         spec.mtd_capacity = int(cap)
+    if cfg.get("hist_n", None) is not None:
+        # colvar histogram accumulated inside the step kernel at dump_freq cadence over ALL walkers (new keys); the
+        # box defaults to the reference's plot boundary (plot.py:42-46, 562-572)
+        if cd > 2:
+            raise ValueError("hist_n: colvardim > 2")
+        box = cfg.get("plot_boundary", cfg.get("boundary", None))
+        lo, hi = cfg.get("hist_lo", None), cfg.get("hist_hi", None)
+        if lo is None or hi is None:
+            if box is None:
+                raise TypeError("hist_n needs hist_lo / hist_hi (or boundary)")
+            box = np.asarray(box, dtype=float).reshape(-1, 2)
+            lo, hi = box[:cd, 0], box[:cd, 1]
+        spec.hist_lo = np.asarray(lo, dtype=float).reshape(-1)[:cd]
+        spec.hist_hi = np.asarray(hi, dtype=float).reshape(-1)[:cd]
+        spec.hist_n = np.broadcast_to(np.asarray(cfg["hist_n"], dtype=int), (cd,)).copy()
     if spec.dump:
         # dump rows + the lagged stat sample before each of them
         spec.dump_capacity = int(cfg.get("dump_capacity", 2 * (spec.steps // max(spec.dump_freq, 1)) + 2))

@@ -23,6 +23,13 @@ const Variant* variants_hot(int* n) {
       // C2 physics with device-side frames (dump rows of io/dump.py) for the dump-bandwidth measurement
       make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, 1>>(
           "md_block<f32,nd2,Mueller2d,Original,langevin,nobias,frames>"),
+      // C2 as SURVEY 8d defines it: frames for a walker prefix (packed, float rows) and the in-kernel colvar histogram
+      make_variant<Spec<f2, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, 1>>(
+          "md_block<f32x2,nd2,Mueller2d,Original,langevin,nobias,frames>"),
+      make_variant<Spec<f2, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, 2>>(
+          "md_block<f32x2,nd2,Mueller2d,Original,langevin,nobias,hist>"),
+      make_variant<Spec<f2, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, MD, PHX, 3>>(
+          "md_block<f32x2,nd2,Mueller2d,Original,langevin,nobias,frames+hist>"),
       // C3: committor shooting on the same surface
       make_variant<Spec<float, 2, NDS_POT_MUELLER2D, ORI, ORI, NDS_INT_LANGEVIN, 0, CM, PHX, OFF>>(
           "md_block<f32,nd2,Mueller2d,Original,langevin,committor>"),

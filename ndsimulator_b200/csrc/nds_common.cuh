@@ -81,6 +81,8 @@ struct Consts {
   // Minimize (engines/minimize.py) and the T = 0 committor criterion pe < emin (committor.py:128-131)
   R min_gtol, emin; long long min_maxiter; int zero_temperature;
   long long dump_freq, stat_freq, dump_walkers;
+  int hist_nx, hist_ny;  // in-kernel colvar histogram (0: off)
+  float hist_lo[2], hist_inv[2];
   unsigned int key0, key1;  // Philox key = seed
   PhiloxKeys rk_step;       // round keys of the per-step noise stream (domain 0)
   PhiloxKeys rk_init;       // round keys of the initial-velocity stream (domain 1)
@@ -115,8 +117,11 @@ struct BlockArgs {
   int begin_mode;          // 1: NDRun.begin semantics: totale = ke + pe, bias omitted (ndrun.py:196)
   // external noise table [step - noise_first][j][M] (parity tests)
   const double* noise; long long noise_first;
-  // frames
-  double* frames; long long frame_base; long long frame_cap; int frame_width;
+  // frames: rows in the engine's real type, [frame][field][walker]
+  R* frames; long long frame_base; long long frame_cap; int frame_width;
+  // colvar histogram accumulated at dump cadence: global counts [ny][nx]; shared-memory bins at this byte offset
+  unsigned long long* hist; int hist_smem_off;
+  int dyn_smem;            // dynamic shared memory of the launch: grid copy (mtd_grid) + histogram bins
 };
 
 }  // namespace nds

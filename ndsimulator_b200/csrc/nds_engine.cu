@@ -78,6 +78,8 @@ struct nds_engine {
   virtual int64_t mtd_grid_outside() = 0;
   virtual int submit(const void* host_in, int64_t nsteps, void* host_out, int chunks) = 0;
   virtual int exchange_info(double* exchange_ms, int64_t* n_exchanges) = 0;
+  virtual int get_histogram(int64_t* counts, int clear) = 0;
+  virtual int frames_f32() const = 0;
   virtual int table_checksum(uint64_t* sum, int64_t first, int64_t n) = 0;
 
   nds_config cfg;
@@ -247,6 +249,16 @@ static int validate(const nds_config* c) {
   if (c->steps_per_launch <= 0) return fail(nullptr, "steps_per_launch must be positive");
   if (c->dump_freq > 0 && c->dump_walkers > 0 && c->dump_capacity <= 0)
     return fail(nullptr, "dump_capacity must be positive when frames are recorded");
+  if (c->hist_n[0] > 0) {
+    const int hcd = nds_colvar_dim(c->colvar, c->ndim);
+    if (hcd > 2) return fail(nullptr, "hist_n: colvardim %d > 2", hcd);
+    if (c->dump_freq <= 0) return fail(nullptr, "hist_n needs dump_freq > 0 (the histogram is sampled at dump cadence)");
+    if (c->method != NDS_METHOD_MD && c->method != NDS_METHOD_COMMITTOR) return fail(nullptr, "hist_n needs method md / committor");
+    const long long nb = (long long)c->hist_n[0] * (hcd > 1 ? c->hist_n[1] : 1);
+    if (nb <= 0 || nb > 12288) return fail(nullptr, "hist_n: %lld bins do not fit the shared-memory histogram (max 12288)", nb);
+    for (int k = 0; k < hcd; k++)
+      if (!(c->hist_hi[k] > c->hist_lo[k])) return fail(nullptr, "hist_hi[%d] must exceed hist_lo[%d]", k, k);
+  }
   return 0;
 }
 
@@ -376,7 +388,18 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.min_gtol = (R)c.min_gtol; K.emin = (R)c.emin; K.min_maxiter = c.min_maxiter;
   K.zero_temperature = (c.temperature == 0) ? 1 : 0;
   const bool dumping = c.dump_freq > 0 && c.dump_walkers > 0;
-  K.dump_freq = dumping ? c.dump_freq : 0;
+  const bool hist = c.dump_freq > 0 && c.hist_n[0] > 0;
+  if (hist) {
+    K.hist_nx = c.hist_n[0];
+    K.hist_ny = K.cd > 1 ? c.hist_n[1] : 1;
+    for (int k = 0; k < 2; k++) {
+      const int n = k == 0 ? K.hist_nx : K.hist_ny;
+      const bool used = k < K.cd;
+      K.hist_lo[k] = used ? (float)c.hist_lo[k] : 0.f;
+      K.hist_inv[k] = used ? (float)(n / (c.hist_hi[k] - c.hist_lo[k])) : 1.f;
+    }
+  }
+  K.dump_freq = (dumping || hist) ? c.dump_freq : 0;
   K.stat_freq = c.stat_freq > 0 ? c.stat_freq : 1;
   K.dump_walkers = dumping ? (c.dump_walkers < c.n_walkers ? c.dump_walkers : c.n_walkers) : 0;
   K.key0 = (unsigned)(c.seed & 0xffffffffull);
@@ -389,7 +412,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
 }
 
 // -------------------------------------------------------------------------- variant lookup
-static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dumping, int prec_override = -1) {
+// dump: bit 0 = frames, bit 1 = in-kernel histogram (the DUMP field of Spec)
+static const Variant* pick_variant(const nds_config& c, int bias_mask, int dump, int prec_override = -1) {
   typedef const Variant* (*table_fn)(int*);
   static const table_fn tables[] = {variants_hot, variants_grid,
                                     variants_generic_f32_nd1, variants_generic_f32_nd2,
@@ -398,7 +422,7 @@ static const Variant* pick_variant(const nds_config& c, int bias_mask, bool dump
   const Variant* best = nullptr;
   int best_score = -1;
   const int want[11] = {prec_override >= 0 ? prec_override : c.precision, c.ndim, c.potential, c.colvar,
-                        c.true_colvar, c.integrator, bias_mask, c.method, c.noise_mode, dumping ? 1 : 0,
+                        c.true_colvar, c.integrator, bias_mask, c.method, c.noise_mode, dump,
                         c.n_basins};
   for (table_fn t : tables) {
     int n = 0;
@@ -538,7 +562,16 @@ struct Engine : nds_engine {
   unsigned char* d_alive = nullptr;
   int* d_basin = nullptr;
   long long* d_exit = nullptr;
-  double* d_frames = nullptr;
+  R* d_frames = nullptr;               // frame ring in the engine's real type
+  unsigned long long* d_hist = nullptr;  // in-kernel colvar histogram [ny][nx]
+  bool frames_on = false, hist_on = false;
+  // subset dumps: walkers [0, split_at) run the frame-recording variant on a second stream, the rest the plain one
+  BlockLaunchFn<R> launch_block_rest = nullptr;
+  BlockLaunchFn<f2> launch_packed_rest = nullptr;
+  Consts<R> K_rest;
+  Consts<f2> K2_rest;
+  int64_t split_at = 0;
+  int dyn_smem = 0, hist_smem_off = 0;
   R *d_path_ref = nullptr, *d_path_ind = nullptr;
   long long* d_mc_accepted = nullptr;
   double* d_mc_time = nullptr;   // MC: per-walker NDRun.time (accepted moves * dt)
@@ -606,7 +639,7 @@ struct Engine : nds_engine {
     for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
-                    (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_noise, (void*)d_stage,
+                    (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
                     (void*)d_path_ref, (void*)d_path_ind, (void*)d_mc_accepted, (void*)d_mc_time, (void*)d_mc_dep, (void*)d_wl, (void*)d_ids, (void*)d_flags, (void*)d_scan,
                     (void*)d_holes, (void*)d_movers, (void*)d_nholes, d_cub,
                     (void*)d_counter})
@@ -659,21 +692,46 @@ struct Engine : nds_engine {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
-    const bool dumping = K.dump_freq > 0;
+    frames_on = K.dump_freq > 0 && K.dump_walkers > 0;
+    hist_on = K.hist_nx > 0;
+    const bool dumping = frames_on || hist_on;
+    const int dump_code = (frames_on ? 1 : 0) | (hist_on ? 2 : 0);
     grid_mode = c.mtd_enabled && c.mtd_grid;
     nranks_cfg = (int)((c.n_walkers_global + c.n_walkers - 1) / c.n_walkers);
-    const Variant* var = pick_variant(c, K.bias_mask, dumping);
+    const Variant* var = pick_variant(c, K.bias_mask, dump_code);
     if (!var) return fail(this, "no compiled md_block variant matches this configuration");
     launch_block = (BlockLaunchFn<R>)var->launch;
     kernel_name = var->name;
     variant_wide = var->wide;
-    if (std::is_same<R, float>::value && M % 2 == 0 && !getenv("NDS_NO_PACKED")) {
-      const Variant* pv = pick_variant(c, K.bias_mask, dumping, PREC_F32_PACKED);
+    // packed kernels see pairs of walkers: the frame prefix must then be a whole number of pairs
+    const bool can_pack = std::is_same<R, float>::value && M % 2 == 0 && K.dump_walkers % 2 == 0 && !getenv("NDS_NO_PACKED");
+    if (can_pack) {
+      const Variant* pv = pick_variant(c, K.bias_mask, dump_code, PREC_F32_PACKED);
       if (pv) {
         fill_consts<f2>(c, K2);
+        K2.dump_walkers = K.dump_walkers / 2;
         launch_packed = (BlockLaunchFn<f2>)pv->launch;
         packed_name = pv->name;
         kernel_name = pv->name;
+      }
+    }
+    // subset dumps ("full state of walkers 0..4095"): only the CTAs that own dumping walkers run the
+    // frame-recording variant (on a second stream); all other walkers keep the kernel without frames
+    if (frames_on && K.dump_walkers < M && c.method == NDS_METHOD_MD && !c.mtd_enabled && !getenv("NDS_NO_SPLIT")) {
+      const int64_t unit = 256;  // whole CTAs of either kernel (128 threads, two walkers per thread when packed)
+      const int64_t pad = (K.dump_walkers + unit - 1) / unit * unit;
+      const Variant* rv = pick_variant(c, K.bias_mask, dump_code & 2);
+      if (pad < M && rv) {
+        split_at = pad;
+        launch_block_rest = (BlockLaunchFn<R>)rv->launch;
+        K_rest = K;
+        K_rest.dump_walkers = 0;
+        if (!hist_on) K_rest.dump_freq = 0;
+        if (launch_packed) {
+          const Variant* rp = pick_variant(c, K.bias_mask, dump_code & 2, PREC_F32_PACKED);
+          if (rp) { launch_packed_rest = (BlockLaunchFn<f2>)rp->launch; K2_rest = K2; K2_rest.dump_walkers = 0; if (!hist_on) K2_rest.dump_freq = 0; }
+          else { launch_packed = nullptr; kernel_name = var->name; }  // both halves must agree on the walker layout
+        }
       }
     }
     if (c.mtd_enabled && c.mtd_shared && !grid_mode && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping) {
@@ -762,10 +820,18 @@ struct Engine : nds_engine {
     }
     CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     frame_width = 2 + 3 * nd + cd + 6;
-    if (dumping) {
+    if (frames_on) {
       const size_t n = (size_t)c.dump_capacity * frame_width * (size_t)K.dump_walkers;
-      CU(cudaMalloc(&d_frames, sizeof(double) * n));
-      CU(cudaMemsetAsync(d_frames, 0xff, sizeof(double) * n, stream));  // NaN pattern
+      CU(cudaMalloc(&d_frames, sizeof(R) * n));
+      CU(cudaMemsetAsync(d_frames, 0xff, sizeof(R) * n, stream));  // NaN pattern
+    }
+    hist_smem_off = grid_in_smem ? (int)(sizeof(R) * grid_elems) : 0;
+    dyn_smem = hist_smem_off;
+    if (hist_on) {
+      const size_t nb = (size_t)K.hist_nx * K.hist_ny;
+      CU(cudaMalloc(&d_hist, sizeof(unsigned long long) * nb));
+      CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nb, stream));
+      dyn_smem += (int)(sizeof(unsigned int) * nb);
     }
     CU(cudaStreamSynchronize(stream));
     return 0;
@@ -933,6 +999,7 @@ struct Engine : nds_engine {
     A.noise = d_noise; A.noise_first = noise_first;
     A.frames = d_frames; A.frame_base = frames_written; A.frame_cap = cfg.dump_capacity;
     A.frame_width = frame_width;
+    A.hist = d_hist; A.hist_smem_off = hist_smem_off; A.dyn_smem = dyn_smem;
     return A;
   }
 
@@ -963,7 +1030,8 @@ struct Engine : nds_engine {
     if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
     launches++;
     have_v = true; begun = true; need_refresh_vr = false;
-    if (K.dump_freq > 0) frames_written = 1;
+    if (frames_on) frames_written = 1;
+    if (d_hist) CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)(K.hist_nx * K.hist_ny), stream));
     return 0;
   }
 
@@ -1311,8 +1379,9 @@ struct Engine : nds_engine {
     return 0;
   }
 
-  // one fused launch of k steps over slots [slot0, slot0 + nslots) (nslots == 0: every launched slot) on stream st
-  cudaError_t launch_steps(int64_t k, int64_t slot0, int64_t nslots, cudaStream_t st) {
+  // one fused launch of k steps over slots [slot0, slot0 + nslots) (nslots == 0: every launched slot) on stream st;
+  // rest = true: the variant without frames (walkers beyond the dump prefix of a split launch)
+  cudaError_t launch_steps(int64_t k, int64_t slot0, int64_t nslots, cudaStream_t st, bool rest = false) {
     BlockArgs<R> A = make_args(k);
     A.refresh_vr = need_refresh_vr ? 1 : 0;
     if (nslots > 0) { A.slot0 = slot0; A.n_active = slot0 + nslots; }
@@ -1329,9 +1398,36 @@ struct Engine : nds_engine {
       P.alive = A.alive; P.basin = A.basin; P.exit_step = A.exit_step; P.ids = A.ids;
       P.n_active = A.n_active > 0 ? (A.n_active + 1) / 2 : 0;
       P.slot0 = A.slot0 / 2;
-      return launch_packed(K2, P, st);
+      P.frames = (f2*)A.frames; P.frame_base = A.frame_base; P.frame_cap = A.frame_cap; P.frame_width = A.frame_width;
+      P.hist = A.hist; P.hist_smem_off = A.hist_smem_off; P.dyn_smem = A.dyn_smem;
+      P.begin_mode = A.begin_mode; P.need_init_v = A.need_init_v;
+      return rest ? launch_packed_rest(K2_rest, P, st) : launch_packed(K2, P, st);
     }
-    return launch_block(K, A, st);
+    return rest ? launch_block_rest(K_rest, A, st) : launch_block(K, A, st);
+  }
+
+  // k steps for every walker: one launch, or -- subset dumps -- the dump prefix on a second stream beside the rest
+  cudaError_t launch_all(int64_t k) {
+    if (split_at <= 0 || split_at >= M) return launch_steps(k, 0, 0, stream);
+    if (!s_alt) {
+      cudaError_t e = cudaStreamCreateWithFlags(&s_alt, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+    }
+    while (pipe_events.size() < 2) {
+      cudaEvent_t ev;
+      cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      pipe_events.push_back(ev);
+    }
+    cudaEventRecord(pipe_events[0], stream);
+    cudaStreamWaitEvent(s_alt, pipe_events[0], 0);
+    cudaError_t e = launch_steps(k, 0, split_at, s_alt);
+    if (e != cudaSuccess) return e;
+    e = launch_steps(k, split_at, M - split_at, stream, true);
+    if (e != cudaSuccess) return e;
+    launches++;
+    cudaEventRecord(pipe_events[1], s_alt);
+    return cudaStreamWaitEvent(stream, pipe_events[1], 0);
   }
 
   // asynchronous host path: ONE pinned block per direction.  host_in = [2 ndim][M] (x rows, then v rows), host_out =
@@ -1344,7 +1440,7 @@ struct Engine : nds_engine {
     if (!begun) return fail(this, "nds_submit before nds_begin");
     if (permuted || compactable) return fail(this, "nds_submit: committor ensembles with lane compaction use nds_set_state / nds_run / nds_get_state");
     const size_t row = sizeof(R) * (size_t)M;
-    const bool can_chunk = chunks > 1 && !cfg.mtd_enabled && cfg.method == NDS_METHOD_MD && K.dump_freq == 0 &&
+    const bool can_chunk = chunks > 1 && !cfg.mtd_enabled && cfg.method == NDS_METHOD_MD && (K.dump_freq == 0 || split_at > 0) &&
                            nsteps <= cfg.steps_per_launch && cfg.integrator != NDS_INT_RESCALE &&
                            (cfg.noise_mode == NDS_NOISE_PHILOX || normals_per_step(cfg.integrator, nd) == 0);
     if (!can_chunk) {
@@ -1367,6 +1463,13 @@ struct Engine : nds_engine {
       CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       pipe_events.push_back(ev);
     }
+    int64_t events = 0;
+    if (frames_on) {
+      for (int64_t s = step + 1; s <= step + nsteps; s++) events += frame_event(s, K.dump_freq, K.stat_freq) ? 1 : 0;
+      if (frames_written + events > cfg.dump_capacity)
+        return fail(this, "frame ring full (%lld frames pending, capacity %lld): call nds_drain_frames",
+                    (long long)frames_written, (long long)cfg.dump_capacity);
+    }
     cudaEvent_t ev_start = pipe_events[(size_t)(2 * nch)], ev_end = pipe_events[(size_t)(2 * nch + 1)];
     CU(cudaEventRecord(ev0, stream));
     CU(cudaEventRecord(ev_start, stream));  // everything queued so far (previous pass) precedes the new copies
@@ -1384,10 +1487,15 @@ struct Engine : nds_engine {
         CU(cudaEventRecord(e_in, s_h2d));
         CU(cudaStreamWaitEvent(cs, e_in, 0));
       }
-      const int64_t pk = launch_packed ? 2 : 1;
-      cudaError_t err = launch_steps(nsteps, w0 / pk * pk, wn, cs);
+      // subset dumps: the part of the chunk inside the dump prefix runs the frame-recording variant
+      const int64_t npre = split_at > w0 ? (split_at - w0 < wn ? split_at - w0 : wn) : 0;
+      cudaError_t err = cudaSuccess;
+      if (split_at == 0) { err = launch_steps(nsteps, w0, wn, cs); launches++; }
+      else {
+        if (npre > 0) { err = launch_steps(nsteps, w0, npre, cs); launches++; }
+        if (err == cudaSuccess && wn > npre) { err = launch_steps(nsteps, w0 + npre, wn - npre, cs, true); launches++; }
+      }
       if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
-      launches++;
       if (host_out) {
         CU(cudaEventRecord(e_k, cs));
         CU(cudaStreamWaitEvent(s_d2h, e_k, 0));
@@ -1405,6 +1513,7 @@ struct Engine : nds_engine {
     need_refresh_vr = false;
     for (int64_t j = 0; j < nsteps; j++) time += step_dt();  // ndrun.py:240
     step += nsteps;
+    frames_written += events;
     return 0;
   }
 
@@ -1436,13 +1545,13 @@ struct Engine : nds_engine {
         k = j;
       }
       int64_t events = 0;
-      if (K.dump_freq > 0) {
+      if (frames_on) {
         for (int64_t s = step + 1; s <= step + k; s++) events += frame_event(s, K.dump_freq, K.stat_freq) ? 1 : 0;
         if (frames_written + events > cfg.dump_capacity)
           return fail(this, "frame ring full (%lld frames pending, capacity %lld): call nds_drain_frames",
                       (long long)frames_written, (long long)cfg.dump_capacity);
       }
-      cudaError_t err = launch_steps(k, 0, 0, stream);
+      cudaError_t err = launch_all(k);
       if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
       launches++;
       need_refresh_vr = false;
@@ -1761,8 +1870,15 @@ struct Engine : nds_engine {
     if (n <= 0) return 0;
     if (n != frames_written) return fail(this, "nds_drain_frames: buffer holds %lld frames, %lld pending", (long long)max_frames, (long long)frames_written);
     const size_t cnt = (size_t)n * frame_width * (size_t)K.dump_walkers;
-    CU(cudaMemcpyAsync(out, d_frames, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemsetAsync(d_frames, 0xff, sizeof(double) * cnt, stream));
+    if (sizeof(R) == sizeof(double)) {
+      CU(cudaMemcpyAsync(out, d_frames, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream));
+    } else {  // float ring: widen on the host (the API delivers doubles)
+      std::vector<R> tmp(cnt);
+      CU(cudaMemcpyAsync(tmp.data(), d_frames, sizeof(R) * cnt, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < cnt; i++) out[i] = (double)tmp[i];
+    }
+    CU(cudaMemsetAsync(d_frames, 0xff, sizeof(R) * cnt, stream));
     CU(cudaStreamSynchronize(stream));
     frames_written = 0;
     return 0;
@@ -1809,6 +1925,17 @@ struct Engine : nds_engine {
     cudaStreamSynchronize(stream);
     cudaFree(d_counts);
     if (err != cudaSuccess) return fail(this, "nds_colvar_histogram: %s", cudaGetErrorString(err));
+    return 0;
+  }
+
+  int frames_f32() const override { return sizeof(R) == 4 ? 1 : 0; }
+  int get_histogram(int64_t* counts, int clear) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_hist) return fail(this, "nds_get_histogram: hist_n is 0 (no in-kernel histogram configured)");
+    const size_t nb = (size_t)K.hist_nx * K.hist_ny;
+    CU(cudaMemcpyAsync(counts, d_hist, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, stream));
+    if (clear) CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nb, stream));
+    CU(cudaStreamSynchronize(stream));
     return 0;
   }
 
@@ -2112,6 +2239,8 @@ int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum) {
 int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap) { return e->get_mtd_grid(out, cap); }
 int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n) { return e->set_mtd_grid(in, n); }
 int64_t nds_mtd_grid_outside(nds_engine* e) { return e->mtd_grid_outside(); }
+int nds_get_histogram(nds_engine* e, int64_t* counts, int clear) { return e->get_histogram(counts, clear); }
+int nds_frames_f32(const nds_engine* e) { return e->frames_f32(); }
 int nds_submit(nds_engine* e, const void* host_xv, int64_t nsteps, void* host_xvt, int32_t chunks) {
   return e->submit(host_xv, nsteps, host_xvt, chunks);
 }

@@ -119,36 +119,48 @@ NDS_DEV void eval_all(const Consts<R>& K, int pot, int cv, int tcv, int cd, int 
   }
 }
 
-// one frame row of walker w (layout documented at nds_drain_frames in include/ndsb200.h)
+// one frame row of walker w (layout documented at nds_drain_frames in include/ndsb200.h).  Rows are written in the
+// engine's own real type: fp32 engines record float rows (half the HBM bytes of fp64 rows, no F2F.F64 per field),
+// the packed kernel stores the pair (walker 2w, 2w+1) with one 8-byte store per field; every store of a warp
+// covers one contiguous 128 / 256-byte run of the [frame][field][walker] ring.
 template <typename R, int ND>
 NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w, long long frame,
                          long long s, double time, int cd, int bias_mask, const R (&x)[ND],
                          const R (&v)[ND], const Eval<R, ND>& o, bool begin_mode) {
   if (frame >= A.frame_cap) return;
-  double* row = A.frames + (frame * A.frame_width) * K.dump_walkers + w;
   const long long st = K.dump_walkers;
+  R* row = A.frames + (frame * A.frame_width) * st + w;
   int r = 0;
-  row[(r++) * st] = (double)s;
-  row[(r++) * st] = time;
+  row[(r++) * st] = (R)(double)s;
+  row[(r++) * st] = (R)time;
 #pragma unroll
-  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)x[d];
+  for (int d = 0; d < ND; d++) row[(r++) * st] = x[d];
 #pragma unroll
-  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)v[d];
+  for (int d = 0; d < ND; d++) row[(r++) * st] = v[d];
 #pragma unroll
-  for (int d = 0; d < ND; d++) row[(r++) * st] = (double)o.fp[d];
+  for (int d = 0; d < ND; d++) row[(r++) * st] = o.fp[d];
 #pragma unroll
   for (int k = 0; k < ND; k++)
-    if (k < cd) row[(r++) * st] = (double)o.cv.c[k];
+    if (k < cd) row[(r++) * st] = o.cv.c[k];
   R v2 = (R)0;
 #pragma unroll
   for (int d = 0; d < ND; d++) v2 += v[d] * v[d];
   const R ke = v2 * K.m / (R)2.0;
-  row[(r++) * st] = (double)(ke / (R)ND / K.kB * (R)2.0);
-  row[(r++) * st] = (double)o.pe;
-  row[(r++) * st] = (double)ke;
-  row[(r++) * st] = (double)o.be;
-  row[(r++) * st] = begin_mode ? (double)(ke + o.pe) : (double)(o.pe + ke + o.be);
-  row[(r++) * st] = (bias_mask & BIAS_MTD) ? (double)A.vr[w] : 0.0;
+  row[(r++) * st] = ke / (R)ND / K.kB * (R)2.0;
+  row[(r++) * st] = o.pe;
+  row[(r++) * st] = ke;
+  row[(r++) * st] = o.be;
+  row[(r++) * st] = begin_mode ? (ke + o.pe) : (o.pe + ke + o.be);
+  row[(r++) * st] = (bias_mask & BIAS_MTD) ? A.vr[w] : (R)0;
+}
+
+// in-kernel colvar histogram at dump cadence (io/plot.py:562-572 accumulated over the run): shared-memory bins
+NDS_DEV void hist_count(unsigned int* bins, float c0, float c1, float lo0, float inv0, int nx, float lo1, float inv1, int ny) {
+  const float u = (c0 - lo0) * inv0, v = (c1 - lo1) * inv1;
+  if (u >= 0.f && v >= 0.f) {
+    const int i = (int)u, j = (int)v;
+    if (i < nx && j < ny) atomicAdd(&bins[j * nx + i], 1u);
+  }
 }
 
 // resident CTAs per SM asked of ptxas (register cap): the packed committor kernel is held to 64 registers
@@ -164,9 +176,14 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   constexpr int INTEG = S::INTEG;  // always compile-time
   constexpr int PACK = pack_of<R>::value;  // walkers per thread (2 for the packed-FP32 real type f2)
   static_assert(PACK == 1 || ((S::METHOD == NDS_METHOD_MD || S::METHOD == NDS_METHOD_COMMITTOR) &&
-                              S::NOISE == NDS_NOISE_PHILOX && S::DUMP == 0 && INTEG != NDS_INT_MINIMIZE &&
+                              S::NOISE == NDS_NOISE_PHILOX && S::DUMP >= 0 && INTEG != NDS_INT_MINIMIZE &&
+                              (S::DUMP == 0 || S::METHOD == NDS_METHOD_MD) &&
                               S::BIAS >= 0 && (S::BIAS & (BIAS_PE | BIAS_MTD)) == 0),
-                "packed kernels: md / committor, Philox noise, no frames, no PE / metadynamics bias");
+                "packed kernels: md / committor, Philox noise, frames only for md, no PE / metadynamics bias");
+  // S::DUMP: bit 0 = frames (dump rows of the first dump_walkers walkers), bit 1 = colvar histogram of ALL walkers
+  // at dump cadence; DYN: both decided by the constant block
+  const bool frames_on = S::DUMP >= 0 ? (S::DUMP & 1) != 0 : (K.dump_freq > 0 && K.dump_walkers > 0);
+  const bool hist_on = S::DUMP >= 0 ? (S::DUMP & 2) != 0 : (K.hist_nx > 0);
   constexpr int NN = normals_per_step(INTEG, ND);
   constexpr int G = noise_group(NN);
   constexpr int CG = noise_calls(NN);
@@ -178,13 +195,21 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   const long long M = A.M;
   // mtd_grid: every CTA first copies the whole bias grid into its shared memory (1-D TMA bulk copies)
   GridView<R> gv{A.grid, 0, A.grid_outside};
+  extern __shared__ __align__(128) unsigned char md_smem[];
+  unsigned int* hist_bins = nullptr;
   if constexpr (PACK == 1 && (S::BIAS < 0 || (S::BIAS & BIAS_MTD_GRID) != 0)) {
     if (A.grid_smem) {
-      extern __shared__ __align__(128) unsigned char md_smem[];
       __shared__ uint64_t grid_bar;
       grid_to_smem(md_smem, A.grid, (uint32_t)(4u * sizeof(R)) * (uint32_t)(K.grid_nx * K.grid_ny), &grid_bar);
       gv.grid = reinterpret_cast<const R*>(md_smem);
       gv.smem = 1;
+    }
+  }
+  if constexpr (S::DUMP < 0 || (S::DUMP & 2) != 0) {
+    if (hist_on) {  // bins behind the grid copy (if any); cleared before any thread leaves
+      hist_bins = reinterpret_cast<unsigned int*>(md_smem + A.hist_smem_off);
+      for (int b = threadIdx.x; b < K.hist_nx * K.hist_ny; b += blockDim.x) hist_bins[b] = 0u;
+      __syncthreads();
     }
   }
   if (w >= (A.n_active > 0 ? A.n_active : M)) return;
@@ -199,7 +224,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   const int bias_mask = S::BIAS >= 0 ? S::BIAS : K.bias_mask;
   const bool committor = S::METHOD >= 0 ? (S::METHOD == NDS_METHOD_COMMITTOR) : (K.method == NDS_METHOD_COMMITTOR);
   const bool ext_noise = S::NOISE >= 0 ? (S::NOISE == NDS_NOISE_EXTERNAL) : (K.noise == NDS_NOISE_EXTERNAL);
-  const bool dumping = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0)) && w < K.dump_walkers;
+  const bool dumping = frames_on && w < K.dump_walkers;
 
   // committor: lanes that stopped in an earlier launch (packed: a0 / a1 for slots 2w, 2w+1)
   bool a0 = true, a1 = true;
@@ -261,7 +286,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   long long frame = A.frame_base;
   // frame_event(s) evaluated incrementally: rd = s % dump_freq, rs = s % stat_freq are carried along instead
   // of two 64-bit divisions per step
-  const bool any_frames = (S::DUMP >= 0 ? (S::DUMP != 0) : (K.dump_freq > 0));
+  const bool any_frames = frames_on || hist_on;
   long long rd = 0, rs = 0;
   if (any_frames) {
     rd = A.step0 % K.dump_freq;
@@ -438,9 +463,33 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
             eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o, gv);
             write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
           }
+          if constexpr (S::DUMP < 0 || (S::DUMP & 2) != 0) {
+            if (hist_on && any_frames && rd == 0)  // colvars of the step's own evaluation = atoms.colv at this step
+              hist_count(hist_bins, (float)e.cv.c[0], cd > 1 ? (float)e.cv.c[ND > 1 ? 1 : 0] : K.hist_lo[1], K.hist_lo[0],
+                         K.hist_inv[0], K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
+          }
           }
           if (event) frame += 1;
         } else {
+          if constexpr (S::DUMP > 0) {  // packed md kernel: frames / histogram, no committor here (static_assert)
+            rd += 1; if (rd == K.dump_freq) rd = 0;
+            if (K.stat_freq > 0) { rs += 1; if (rs == K.stat_freq) rs = 0; }
+            const bool event = rd == 0 || (K.stat_freq > 0 && rs == 0 && K.dump_freq - rd <= K.stat_freq);
+            if (dumping && event) {
+              Eval<R, ND> o;
+              eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o, gv);
+              write_frame<R, ND>(K, A, w, frame, s, time, cd, bias_mask, x, v, o, false);
+            }
+            if constexpr ((S::DUMP & 2) != 0) {
+              if (rd == 0) {
+                hist_count(hist_bins, e.cv.c[0].v.x, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.x : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],
+                           K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
+                hist_count(hist_bins, e.cv.c[0].v.y, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.y : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],
+                           K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
+              }
+            }
+            if (event) frame += 1;
+          }
           if (committor && left <= commit_left) {  // committor.py:100-111, once per lane
             float c0[ND], c1[ND];
 #pragma unroll
@@ -510,6 +559,9 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
     // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
     if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
   } else {
+    if constexpr (S::DUMP > 0) {
+      if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
+    }
     if (committor) {
       if (was0) {
         if (!a0) { A.alive[2 * w] = 0; A.exit_step[2 * w] = exit_s; }
@@ -519,6 +571,13 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
         if (!a1) { A.alive[2 * w + 1] = 0; A.exit_step[2 * w + 1] = exit_b; }
         A.basin[2 * w + 1] = basin_b;
       }
+    }
+  }
+  if constexpr (S::DUMP < 0 || (S::DUMP & 2) != 0) {
+    if (hist_on) {  // one global atomic per non-empty bin per CTA (threads that left early count as arrived)
+      __syncthreads();
+      for (int b = threadIdx.x; b < K.hist_nx * K.hist_ny; b += blockDim.x)
+        if (hist_bins[b]) atomicAdd(&A.hist[b], (unsigned long long)hist_bins[b]);
     }
   }
 }

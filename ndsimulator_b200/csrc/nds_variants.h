@@ -26,7 +26,7 @@ cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<type
                             cudaStream_t st) {
   const long long n = (A.n_active > 0 ? A.n_active : A.M) - A.slot0;
   const unsigned grid = (unsigned)((n + NDS_BLOCK - 1) / NDS_BLOCK);
-  md_block<S><<<grid, NDS_BLOCK, 0, st>>>(K, A);
+  md_block<S><<<grid, NDS_BLOCK, (size_t)A.dyn_smem, st>>>(K, A);
   return cudaGetLastError();
 }
 
@@ -34,9 +34,8 @@ cudaError_t launch_md_block(const Consts<typename S::R>& K, const BlockArgs<type
 template <class S>
 cudaError_t launch_md_block_wide(const Consts<typename S::R>& K, const BlockArgs<typename S::R>& A,
                                  cudaStream_t st) {
-  using R = typename S::R;
   const long long n = (A.n_active > 0 ? A.n_active : A.M) - A.slot0;
-  const size_t smem = A.grid_smem ? sizeof(R) * 4 * (size_t)K.grid_nx * (size_t)K.grid_ny : 0;
+  const size_t smem = (size_t)A.dyn_smem;
   // few walkers: many small CTAs (latency-bound, one warp per scheduler); many walkers: one wide CTA per SM
   const int threads = n >= 148LL * 512 ? 512 : (n >= 148LL * 256 ? 256 : 128);
   if (smem > 48 * 1024) {  // per device, cheap: set on every launch that needs the opt-in

@@ -346,6 +346,11 @@ class Engine:
 
     # ---- frames
     @property
+    def frames_f32(self):
+        """True when the device frame ring holds float32 rows (fp32 engines)."""
+        return bool(self.lib.nds_frames_f32(self.h)) if hasattr(self.lib, "nds_frames_f32") else False
+
+    @property
     def frame_width(self):
         return int(self.lib.nds_frame_width(self.h))
 
@@ -360,6 +365,13 @@ class Engine:
         got = C.c_int64()
         self._check(self.lib.nds_drain_frames(self.h, _p(out), n, C.byref(got)))
         return out[:got.value]
+
+    def get_histogram(self, clear=False):
+        """Colvar histogram accumulated inside the step kernels since ``begin()``: ``counts[ny][nx]``."""
+        ny = int(self.cfg.hist_n[1]) if self.cd > 1 else 1
+        counts = np.zeros((ny, int(self.cfg.hist_n[0])), dtype=np.int64)
+        self._check(self.lib.nds_get_histogram(self.h, counts.ctypes.data_as(C.POINTER(C.c_int64)), int(bool(clear))))
+        return counts
 
     def frame_fields(self):
         nd, cd = self.ndim, self.cd
