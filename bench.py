@@ -680,7 +680,7 @@ def bench_e2e(ctx, eng, spec, cfg, name, M, md_steps, precision, steps):
     serial(1)(2)
     t1 = timed(serial(1), n)
     out["unchunked_value"] = work * n / t1
-    chunks = 8
+    chunks = int(os.environ.get("NDS_BENCH_CHUNKS", "8"))
     serial(chunks)(2)
     tc = timed(serial(chunks), n)
     out["value"] = work * n / tc
@@ -715,6 +715,8 @@ def bench_e2e(ctx, eng, spec, cfg, name, M, md_steps, precision, steps):
             eng2.set_walker_bias(extra2["k"], extra2["r0"])
         eng2.begin()
         eng2.run(md_steps)
+        if cfg.get("dump"):
+            eng2.lib.nds_drain_frames(eng2.h, None, 0, None)
         b1 = Batch(eng2)
         bs = [b0, b1]
 

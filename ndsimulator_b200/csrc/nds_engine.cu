@@ -609,6 +609,7 @@ struct Engine : nds_engine {
   int64_t grid_elems = 0;                  // 4 * nx * ny
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
+  R* d_gpart = nullptr;                    // partial sums of the record slices of one accumulation [16][grid]
   R** d_slot_dst = nullptr;                // [nranks] slot of THIS rank on every peer, parity 0 then parity 1
   R** d_slot_src = nullptr;                // [nranks] slots of every rank in THIS rank's window, parity 0 then 1
   R** d_ginc_list = nullptr;               // {d_ginc}
@@ -636,7 +637,7 @@ struct Engine : nds_engine {
   ~Engine() override {
     cudaSetDevice(cfg.device);
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
-    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
@@ -1102,27 +1103,23 @@ struct Engine : nds_engine {
       deposit_kernel<R><<<g, 128, 0, stream>>>(K, M, 0, d_colv, d_vr, d_alive, d_hills, n_hills, first);
       CU(cudaGetLastError());
       const R* rec = d_hills + n_hills * K.hill_stride;
-      const unsigned tiles = (unsigned)(((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY));
       const unsigned ga = (unsigned)((grid_elems + 255) / 256);
-      launches += 2;
+      launches += 1;
       if (!multi) {
-        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, nullptr, 0, d_grid, 1);
-        CU(cudaGetLastError());
+        if (accumulate(rec, M, nullptr, 0, true)) return 1;
       } else if (d_slot_dst) {
         // fused with the exchange: the increment goes straight into this rank's slot on EVERY peer over NVLink;
         // after the barrier each rank adds the slots in rank order (bit-identical grids everywhere)
         const int par = (int)(dep_count & 1);
         exchange_mark(true);
-        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_slot_dst + par * n_peers, n_peers, nullptr, 0);
-        CU(cudaGetLastError());
+        if (accumulate(rec, M, d_slot_dst + par * n_peers, n_peers, false)) return 1;
         if (peer_barrier()) return 1;
         grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
         CU(cudaGetLastError());
         exchange_mark(false);
         launches++;
       } else if (comm) {
-        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_ginc_list, 1, nullptr, 0);
-        CU(cudaGetLastError());
+        if (accumulate(rec, M, d_ginc_list, 1, false)) return 1;
         exchange_mark(true);
         if (nccl_check(nccl_api().AllReduce(d_ginc, d_ginc, (size_t)grid_elems, sizeof(R) == 4 ? 7 : 8, 0, comm, stream), "ncclAllReduce")) return 1;
         exchange_mark(false);
@@ -1130,8 +1127,7 @@ struct Engine : nds_engine {
         CU(cudaGetLastError());
         launches++;
       } else if (exchange) {
-        grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, rec, M, d_ginc_list, 1, nullptr, 0);
-        CU(cudaGetLastError());
+        if (accumulate(rec, M, d_ginc_list, 1, false)) return 1;
         exchange_mark(true);
         CU(cudaStreamSynchronize(stream));
         // rank_offset_bytes == -1: all-reduce (sum) of bytes / sizeof(real) reals of the engine's precision, in place
@@ -2039,15 +2035,26 @@ struct Engine : nds_engine {
     return (int64_t)h;
   }
 
+  // footprint of n records on the grid: partial sums per record slice, then the slices in order -> grid += (add),
+  // or -> the destination list (increment slots on the peers / the all-reduce buffer)
+  int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add) {
+    const int tiles = ((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY);
+    int slices = (int)((n + 511) / 512);
+    if (slices < 1) slices = 1;
+    if (slices > 16) slices = 16;
+    if (!d_gpart) CU(cudaMalloc(&d_gpart, sizeof(R) * (size_t)grid_elems * 16));
+    grid_accumulate_kernel<R><<<(unsigned)(tiles * slices), GRID_TX * GRID_TY, 0, stream>>>(K, rec, n, slices, d_gpart);
+    CU(cudaGetLastError());
+    grid_reduce_kernel<R><<<(unsigned)((grid_elems + 255) / 256), 256, 0, stream>>>(grid_elems, slices, d_gpart, dst, ndst, d_grid, add ? 1 : 0);
+    CU(cudaGetLastError());
+    launches += 2;
+    return 0;
+  }
+
   // grid <- footprint of the first n records of the (local) hill table
   int rebuild_grid(int64_t n) {
     CU(cudaMemsetAsync(d_grid, 0, sizeof(R) * (size_t)grid_elems, stream));
-    if (n > 0) {
-      const unsigned tiles = (unsigned)(((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY));
-      grid_accumulate_kernel<R><<<tiles, GRID_TX * GRID_TY, 0, stream>>>(K, d_hills, n, nullptr, 0, d_grid, 1);
-      CU(cudaGetLastError());
-      launches++;
-    }
+    if (n > 0 && accumulate(d_hills, n, nullptr, 0, true)) return 1;
     return 0;
   }
 

@@ -156,11 +156,9 @@ NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w,
 
 // in-kernel colvar histogram at dump cadence (io/plot.py:562-572 accumulated over the run): shared-memory bins
 NDS_DEV void hist_count(unsigned int* bins, float c0, float c1, float lo0, float inv0, int nx, float lo1, float inv1, int ny) {
-  const float u = (c0 - lo0) * inv0, v = (c1 - lo1) * inv1;
-  if (u >= 0.f && v >= 0.f) {
-    const int i = (int)u, j = (int)v;
-    if (i < nx && j < ny) atomicAdd(&bins[j * nx + i], 1u);
-  }
+  // floor to int, then ONE unsigned compare per axis rejects both sides of the box (negative indices wrap high)
+  const int i = __float2int_rd((c0 - lo0) * inv0), j = __float2int_rd((c1 - lo1) * inv1);
+  if ((unsigned)i < (unsigned)nx && (unsigned)j < (unsigned)ny) atomicAdd(&bins[j * nx + i], 1u);
 }
 
 // resident CTAs per SM asked of ptxas (register cap): the packed committor kernel is held to 64 registers
@@ -287,11 +285,15 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   // frame_event(s) evaluated incrementally: rd = s % dump_freq, rs = s % stat_freq are carried along instead
   // of two 64-bit divisions per step
   const bool any_frames = frames_on || hist_on;
-  long long rd = 0, rs = 0;
+  // 32-bit counters (the frequencies are far below 2^31): 64-bit compares and selects cost two issue slots each
+  const int dfreq = (int)K.dump_freq, sfreq = (int)K.stat_freq;
+  int rd = 0, rs = 0;
   if (any_frames) {
-    rd = A.step0 % K.dump_freq;
-    rs = K.stat_freq > 0 ? A.step0 % K.stat_freq : 0;
+    rd = (int)(A.step0 % K.dump_freq);
+    rs = K.stat_freq > 0 ? (int)(A.step0 % K.stat_freq) : 0;
   }
+  // value of `left` right after the next dump step (hist-only kernels): steps to the next multiple of dump_freq
+  int hist_left = any_frames ? (int)A.nsteps - (dfreq - rd) : -1;
   bool alive = true;
   int basin = -1;
 
@@ -452,9 +454,9 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
           }
           bool event = false;
           if (any_frames) {
-            rd += 1; if (rd == K.dump_freq) rd = 0;
-            if (K.stat_freq > 0) { rs += 1; if (rs == K.stat_freq) rs = 0; }
-            event = rd == 0 || (K.stat_freq > 0 && rs == 0 && K.dump_freq - rd <= K.stat_freq);
+            rd += 1; if (rd == dfreq) rd = 0;
+            if (sfreq > 0) { rs += 1; if (rs == sfreq) rs = 0; }
+            event = rd == 0 || (sfreq > 0 && rs == 0 && dfreq - rd <= sfreq);
           }
           if (alive || exit_s == s) {
           if (dumping && event) {
@@ -471,10 +473,19 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
           }
           if (event) frame += 1;
         } else {
-          if constexpr (S::DUMP > 0) {  // packed md kernel: frames / histogram, no committor here (static_assert)
-            rd += 1; if (rd == K.dump_freq) rd = 0;
-            if (K.stat_freq > 0) { rs += 1; if (rs == K.stat_freq) rs = 0; }
-            const bool event = rd == 0 || (K.stat_freq > 0 && rs == 0 && K.dump_freq - rd <= K.stat_freq);
+          if constexpr (S::DUMP == 2) {
+            // histogram only: one compare per step against the value `left` has at the next dump step
+            if (left == hist_left) {
+              hist_left -= dfreq;
+              hist_count(hist_bins, e.cv.c[0].v.x, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.x : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],
+                         K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
+              hist_count(hist_bins, e.cv.c[0].v.y, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.y : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],
+                         K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
+            }
+          } else if constexpr (S::DUMP > 0) {  // packed md kernel: frames (+ histogram), no committor here (static_assert)
+            rd += 1; if (rd == dfreq) rd = 0;
+            if (sfreq > 0) { rs += 1; if (rs == sfreq) rs = 0; }
+            const bool event = rd == 0 || (sfreq > 0 && rs == 0 && dfreq - rd <= sfreq);
             if (dumping && event) {
               Eval<R, ND> o;
               eval_all<R, ND, true>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, o, gv);
