@@ -184,9 +184,10 @@ typedef struct nds_config {
   int32_t reserved4;
   double mtd_grid_lo[2], mtd_grid_hi[2];
 
-  /* history-based adaptive sigma (gaus.py:166-183 `adapsig` without `adapsig_geo`): the variance of a new hill is
-   * Var(colvar) over the last mtd_hist_window stat samples of the walker (Stat.colv history, io/stat.py:57-74);
-   * colvardim 1, per-hill variance records like mtd_adapsig_geo.                                                 */
+  /* history-based adaptive sigma (gaus.py:166-183, 193-212: `adapsig` without `adapsig_geo`): the variance of a new
+   * hill is the exponentially weighted variance of the walker's last tao_d = min(50 mtd_dep_freq, 100) Stat samples
+   * of the colvar (io/stat.py:57-74, sampled every stat_freq steps); the step kernel keeps that window in a device
+   * ring.  colvardim 1, method md; per-hill variance records like mtd_adapsig_geo.                                */
   int32_t mtd_adapsig_hist;
   int32_t reserved5;
 
@@ -348,6 +349,12 @@ NDS_API int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t
 NDS_API int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap);
 NDS_API int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n);
 NDS_API int64_t nds_mtd_grid_outside(nds_engine* e);
+
+/* mtd_adapsig_hist: the colvar history window of every walker (Stat.colv, io/stat.py:70-72), for checkpoints:
+ * ring[(j % window) * n_walkers + w] = sample j of walker w, *n_samples = len(stat.colv).  ring may be NULL to
+ * query the sizes only.                                                                                    */
+NDS_API int nds_get_cv_history(nds_engine* e, double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window);
+NDS_API int nds_set_cv_history(nds_engine* e, const double* ring, int64_t n_samples);
 
 /* asynchronous host path, one block per direction: host_xv = [2 ndim][M] (x rows, then v rows) and host_xvt =
  * [2 ndim + 5][M] (x, v, thermo) in the ENGINE's precision (float for NDS_F32), ideally pinned; either may be

@@ -356,9 +356,12 @@ def parse(config: dict) -> RunSpec:
     for b in biases:
         if b == "mtd":  # bias/gaus.py:48-128
             adapsig, geo = pick(cfg, "adapsig", "mtd", False), pick(cfg, "adapsig_geo", "mtd", False)
-            if adapsig and not geo:  # gaus.py:166-181: variance from the Stat history of the colvar
-                raise NotImplementedError("mtd_adapsig without mtd_adapsig_geo needs the host-side Stat history "
-                                          "(gaus.py:166-181) and is outside the B200 hot path")
+            if adapsig and not geo:  # gaus.py:166-183,193-212: variance from the Stat history of the colvar
+                if cd != 1:
+                    raise ValueError("mtd_adapsig needs a 1-D colvar: for colvardim > 1 the reference sums "
+                                     "exp(-dc_i dc_j / (2 S_ij)) over the ELEMENTS of the covariance matrix "
+                                     "(gaus.py:268-277), which diverges for negative covariances")
+                spec.mtd_adapsig_hist = True
             if adapsig and geo:      # gaus.py:162-165,189-192: every hill gets the variance J.J^T (* sigma^2)
                 if cd != 1:
                     raise ValueError("mtd_adapsig_geo needs a 1-D colvar: for colvardim > 1 the reference takes the "
@@ -440,7 +443,7 @@ def parse(config: dict) -> RunSpec:
     if "mtd" in biases and cfg.get("mtd_grid", False):
         # grid-accumulated bias (new keys): box [mtd_grid_lo, mtd_grid_hi] per colvar -- default: the reference's
         # `boundary` / `plot_boundary` key (plot.py:42-46) -- and spacing mtd_grid_spacing (default sigma / 4)
-        if spec.mtd_adapsig_geo or not spec.mtd_shared or cd > 2:
+        if spec.mtd_adapsig_geo or spec.mtd_adapsig_hist or not spec.mtd_shared or cd > 2:
             raise ValueError("mtd_grid needs a shared table, a fixed sigma and colvardim <= 2")
         box = cfg.get("mtd_grid_box", cfg.get("plot_boundary", cfg.get("boundary", None)))
         lo, hi = cfg.get("mtd_grid_lo", None), cfg.get("mtd_grid_hi", None)

@@ -20,6 +20,8 @@ constexpr int BIAS_MTD = 2;         // metadynamics hill sum (bias/gaus.py)
 constexpr int BIAS_PE = 4;          // potential-energy bias (bias/pe.py)
 constexpr int BIAS_UMB_WALKER = 8;  // restraint 0 takes (k, r0) per walker
 constexpr int BIAS_MTD_GRID = 16;   // metadynamics bias interpolated from the accumulated grid (mtd_grid)
+constexpr int BIAS_CVHIST = 32;     // the step kernel keeps Stat.colv (io/stat.py:70-72) of every walker in a ring:
+                                    // history-based adaptive hill widths (gaus.py:166-183, 193-212)
 
 template <typename R_, int ND_, int POT_ = DYN, int CV_ = DYN, int TCV_ = DYN, int INTEG_ = DYN,
           int BIAS_ = DYN, int METHOD_ = DYN, int NOISE_ = DYN, int DUMP_ = DYN, int NBASIN_ = DYN>
@@ -122,6 +124,9 @@ struct BlockArgs {
   // colvar histogram accumulated at dump cadence: global counts [ny][nx]; shared-memory bins at this byte offset
   unsigned long long* hist; int hist_smem_off;
   int dyn_smem;            // dynamic shared memory of the launch: grid copy (mtd_grid) + histogram bins
+  // Stat.colv ring (BIAS_CVHIST): sample j of walker w lives at cvhist[(j % cvhist_cap) * M + w]; cvhist_n samples
+  // exist at launch entry
+  R* cvhist; long long cvhist_n; int cvhist_cap;
 };
 
 }  // namespace nds

@@ -76,6 +76,8 @@ struct nds_engine {
   virtual int get_mtd_grid(double* out, int64_t cap) = 0;
   virtual int set_mtd_grid(const double* in, int64_t n) = 0;
   virtual int64_t mtd_grid_outside() = 0;
+  virtual int get_cv_history(double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) = 0;
+  virtual int set_cv_history(const double* ring, int64_t n_samples) = 0;
   virtual int submit(const void* host_in, int64_t nsteps, void* host_out, int chunks) = 0;
   virtual int exchange_info(double* exchange_ms, int64_t* n_exchanges) = 0;
   virtual int get_histogram(int64_t* counts, int clear) = 0;
@@ -179,6 +181,12 @@ extern "C" int nds_colvar_dim(int cv, int ndim) {
   }
 }
 
+// Gaussian.tao_d = np.min([dep_freq * 50, 100]) (gaus.py:94): window of the colvar history; 0 if not an integer
+static int nds_tao_d(const nds_config* c) {
+  const double t = c->mtd_dep_freq * 50 < 100 ? c->mtd_dep_freq * 50 : 100;
+  return (t >= 1 && t == std::floor(t)) ? (int)t : 0;
+}
+
 static int validate(const nds_config* c) {
   if (!c) return fail(nullptr, "nds_create: null config");
   if (c->abi_version != NDS_ABI_VERSION)
@@ -240,7 +248,15 @@ static int validate(const nds_config* c) {
       if (pts > (1 << 24)) return fail(nullptr, "mtd_grid: %lld grid points > 2^24", pts);
     }
   }
-  if (c->mtd_adapsig_hist) return fail(nullptr, "mtd_adapsig (history-based variance, gaus.py:166-183) is not built into this library");
+  if (c->mtd_enabled && c->mtd_adapsig_hist) {  // gaus.py:166-183, 193-212: variance from the Stat history of the colvar
+    if (c->mtd_adapsig_geo) return fail(nullptr, "mtd_adapsig_hist and mtd_adapsig_geo exclude each other (gaus.py:163,191)");
+    if (nds_colvar_dim(c->colvar, c->ndim) != 1)
+      return fail(nullptr, "mtd_adapsig needs a 1-D colvar: for colvardim > 1 the reference sums exp(-dc_i dc_j / (2 S_ij)) over "
+                           "the ELEMENTS of the covariance matrix (gaus.py:268-277), which diverges for negative covariances");
+    if (c->method != NDS_METHOD_MD) return fail(nullptr, "mtd_adapsig (history-based) needs method md");
+    if (nds_tao_d(c) < 1) return fail(nullptr, "mtd_adapsig: tao_d = min(50 * mtd_dep_freq, 100) must be a positive integer "
+                                                "(gaus.py:94; the reference slices stat.colv with it)");
+  }
   if (c->method == NDS_METHOD_COMMITTOR) {
     if (c->n_basins < 1 || c->n_basins > NDS_MAX_BASINS) return fail(nullptr, "n_basins out of range");
     if (c->temperature == 0 && c->integrator != NDS_INT_MINIMIZE)  // engines/__init__.py:22-23
@@ -281,7 +297,8 @@ static void fill_consts(const nds_config& c, Consts<R>& K) {
   K.bias_mask = (c.n_umb > 0 ? BIAS_UMB : 0) | (c.mtd_enabled ? BIAS_MTD : 0) |
                 (c.pe_enabled ? BIAS_PE : 0) | ((c.n_umb > 0 && c.umb_per_walker) ? BIAS_UMB_WALKER : 0);
   K.mtd_shared = c.mtd_shared;
-  K.mtd_adaptive = (c.mtd_enabled && c.mtd_adapsig_geo) ? 1 : 0;
+  K.mtd_adaptive = (c.mtd_enabled && (c.mtd_adapsig_geo || c.mtd_adapsig_hist)) ? 1 : 0;
+  if (c.mtd_enabled && c.mtd_adapsig_hist) K.bias_mask |= BIAS_CVHIST;
   K.mtd_dep_freq64 = c.mtd_dep_freq; K.mtd_capacity = c.mtd_capacity;
   // 4-word records (c0, c1 | 0, w, log2 w) for every shared table with colvardim <= 2 (mtd_block streams them
   // through TMA tiles); adaptive records are (c, w, 1/s, s); everything else is (c_0..c_{cd-1}, w)
@@ -610,6 +627,9 @@ struct Engine : nds_engine {
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
   R* d_gpart = nullptr;                    // partial sums of the record slices of one accumulation [16][grid]
+  R* d_cvhist = nullptr;                   // Stat.colv ring [tao_d][M] (mtd_adapsig_hist)
+  int64_t cv_n = 0;                        // samples taken so far (len(stat.colv))
+  int tao_d = 0;
   R** d_slot_dst = nullptr;                // [nranks] slot of THIS rank on every peer, parity 0 then parity 1
   R** d_slot_src = nullptr;                // [nranks] slots of every rank in THIS rank's window, parity 0 then 1
   R** d_ginc_list = nullptr;               // {d_ginc}
@@ -637,7 +657,7 @@ struct Engine : nds_engine {
   ~Engine() override {
     cudaSetDevice(cfg.device);
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
-    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_cvhist, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
@@ -780,6 +800,11 @@ struct Engine : nds_engine {
         CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
         grid_in_smem = variant_wide && (int64_t)sizeof(R) * grid_elems <= (int64_t)dev_smem - 1024 && !getenv("NDS_GRID_NO_SMEM");
       }
+      if (c.mtd_adapsig_hist) {
+        tao_d = nds_tao_d(&c);
+        CU(cudaMalloc(&d_cvhist, sizeof(R) * (size_t)tao_d * sM));
+        CU(cudaMemsetAsync(d_cvhist, 0, sizeof(R) * (size_t)tao_d * sM, stream));
+      }
     }
     if (c.method == NDS_METHOD_COMMITTOR) {
       CU(cudaMalloc(&d_alive, sM));
@@ -808,9 +833,9 @@ struct Engine : nds_engine {
       CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * sM, stream));
       if (c.mtd_enabled) {
         CU(cudaMalloc(&d_mc_time, sizeof(double) * sM));
-        CU(cudaMalloc(&d_mc_dep, sizeof(long long) * sM));
+        CU(cudaMalloc(&d_mc_dep, sizeof(long long) * (sM + 1)));  // [M]: overflow flag (first walker + 1)
         CU(cudaMemsetAsync(d_mc_time, 0, sizeof(double) * sM, stream));
-        CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * sM, stream));
+        CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (sM + 1), stream));
       }
       kernel_name = sizeof(R) == 4 ? "mc_block<f32>" : "mc_block<f64>";
       if (c.method == NDS_METHOD_WL) {
@@ -1001,6 +1026,7 @@ struct Engine : nds_engine {
     A.frames = d_frames; A.frame_base = frames_written; A.frame_cap = cfg.dump_capacity;
     A.frame_width = frame_width;
     A.hist = d_hist; A.hist_smem_off = hist_smem_off; A.dyn_smem = dyn_smem;
+    A.cvhist = d_cvhist; A.cvhist_n = cv_n; A.cvhist_cap = tao_d;
     return A;
   }
 
@@ -1014,7 +1040,7 @@ struct Engine : nds_engine {
     step = 0; time = 0.0; rescale_count = 0; frames_written = 0;
     if (d_mc_accepted) CU(cudaMemsetAsync(d_mc_accepted, 0, sizeof(long long) * (size_t)M, stream));
     if (d_mc_time) CU(cudaMemsetAsync(d_mc_time, 0, sizeof(double) * (size_t)M, stream));
-    if (d_mc_dep) { CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (size_t)M, stream)); n_hills = 0; dep_count = 0; }
+    if (d_mc_dep) { CU(cudaMemsetAsync(d_mc_dep, 0, sizeof(long long) * (size_t)(M + 1), stream)); n_hills = 0; dep_count = 0; }
     if (d_wl) CU(cudaMemsetAsync(d_wl, 0, sizeof(R) * NDS_WL_GRID * (size_t)M, stream));
     if (cfg.method == NDS_METHOD_COMMITTOR) {
       if (permuted && unpermute_device()) return 1;
@@ -1031,6 +1057,7 @@ struct Engine : nds_engine {
     if (err != cudaSuccess) return fail(this, "md_block launch failed: %s", cudaGetErrorString(err));
     launches++;
     have_v = true; begun = true; need_refresh_vr = false;
+    if (d_cvhist) cv_n += 1;  // stat.append of NDRun.begin (ndrun.py:201); Stat survives a second begin()
     if (frames_on) frames_written = 1;
     if (d_hist) CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)(K.hist_nx * K.hist_ny), stream));
     return 0;
@@ -1163,7 +1190,11 @@ struct Engine : nds_engine {
         K, M, cfg.walker_offset, d_colv, d_vr, d_alive, d_hills, n_hills, first);
     CU(cudaGetLastError());
     launches++;
-    if (K.mtd_adaptive) {  // per-hill variance J.J^T (* sigma^2) at the deposition point
+    if (d_cvhist) {  // per-hill variance from the walker's colvar history (gaus.py:166-183, 193-212)
+      hill_variance_hist_kernel<R><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_cvhist, tao_d, cv_n, tao_d, d_hills, n_hills, first);
+      CU(cudaGetLastError());
+      launches++;
+    } else if (K.mtd_adaptive) {  // per-hill variance J.J^T (* sigma^2) at the deposition point
       if (nd == 1) hill_variance_kernel<R, 1><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
       else if (nd == 2) hill_variance_kernel<R, 2><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
       else hill_variance_kernel<R, 5><<<g, 128, 0, stream>>>(K, M, cfg.walker_offset, d_x, d_hills, n_hills, first);
@@ -1282,6 +1313,13 @@ struct Engine : nds_engine {
     }
     CU(cudaEventRecord(ev1, stream));
     timed = true;
+    if (cfg.mtd_enabled) {  // a walker that had a hill to deposit and no room: same failure as the MD path's deposit()
+      long long over = 0;
+      CU(cudaMemcpyAsync(&over, d_mc_dep + M, sizeof over, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      if (over) return fail(this, "hill table full: walker %lld needed more than mtd_capacity %lld hills (MC deposits on the "
+                                  "accepted-move clock); raise mtd_capacity", over - 1, (long long)K.mtd_capacity);
+    }
     return 0;
   }
 
@@ -1558,6 +1596,7 @@ struct Engine : nds_engine {
         }
         time += step_dt();  // ndrun.py:240 (engine.current_dt)
       }
+      if (d_cvhist) cv_n += (step + k) / K.stat_freq - step / K.stat_freq;  // samples the launch appended
       step += k;
       frames_written += events;
       remaining -= k;
@@ -2026,6 +2065,25 @@ struct Engine : nds_engine {
     need_refresh_vr = false;
     return upload(in, d_grid, grid_elems);
   }
+  // Stat.colv window of every walker (mtd_adapsig_hist): ring[(j % window) * M + w] = sample j; checkpoint / resume
+  int get_cv_history(double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) override {
+    CU(cudaSetDevice(cfg.device));
+    if (n_samples) *n_samples = cv_n;
+    if (window) *window = tao_d;
+    if (!ring) return 0;
+    if (!d_cvhist) return fail(this, "nds_get_cv_history: the config has no history-based mtd_adapsig");
+    if (cap_elems < (int64_t)tao_d * M) return fail(this, "nds_get_cv_history: buffer of %lld < %lld elements", (long long)cap_elems, (long long)tao_d * M);
+    return download(d_cvhist, ring, (int64_t)tao_d * M);
+  }
+  int set_cv_history(const double* ring, int64_t n_samples) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_cvhist) return fail(this, "nds_set_cv_history: the config has no history-based mtd_adapsig");
+    if (n_samples < 0) return fail(this, "nds_set_cv_history: negative sample count");
+    if (upload(ring, d_cvhist, (int64_t)tao_d * M)) return 1;
+    cv_n = n_samples;
+    return 0;
+  }
+
   int64_t mtd_grid_outside() override {
     if (!grid_mode) return 0;
     cudaSetDevice(cfg.device);
@@ -2246,6 +2304,10 @@ int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum) {
 int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap) { return e->get_mtd_grid(out, cap); }
 int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n) { return e->set_mtd_grid(in, n); }
 int64_t nds_mtd_grid_outside(nds_engine* e) { return e->mtd_grid_outside(); }
+int nds_get_cv_history(nds_engine* e, double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) {
+  return e->get_cv_history(ring, cap_elems, n_samples, window);
+}
+int nds_set_cv_history(nds_engine* e, const double* ring, int64_t n_samples) { return e->set_cv_history(ring, n_samples); }
 int nds_get_histogram(nds_engine* e, int64_t* counts, int clear) { return e->get_histogram(counts, clear); }
 int nds_frames_f32(const nds_engine* e) { return e->frames_f32(); }
 int nds_submit(nds_engine* e, const void* host_xv, int64_t nsteps, void* host_xvt, int32_t chunks) {

@@ -296,6 +296,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   int hist_left = any_frames ? (int)A.nsteps - (dfreq - rd) : -1;
   bool alive = true;
   int basin = -1;
+  long long cv_taken = 0;  // Stat.colv samples written by this launch (BIAS_CVHIST)
 
   long long exit_s = 0, exit_b = 0;
   int basin_b = -1;
@@ -443,6 +444,13 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
         left -= 1;
         s += 1;            // ndrun.py:232
         time += K.dt64;    // ndrun.py:240
+        if constexpr (PACK == 1 && S::BIAS < 0) {
+          // Stat.append (ndrun.py:250-251, io/stat.py:70-72): atoms.colv joins the history when step % stat.freq == 0
+          if ((bias_mask & BIAS_CVHIST) && s % K.stat_freq == 0) {
+            A.cvhist[((A.cvhist_n + cv_taken) % A.cvhist_cap) * M + w] = e.cv.c[0];
+            cv_taken += 1;
+          }
+        }
         if constexpr (PACK == 1) {
           if (committor && alive) {
             bool stopped = (INTEG == NDS_INT_MINIMIZE) && min_stop;  // committor.py:95-97
@@ -569,6 +577,9 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
     }
     // frame 0: Dump.begin() writes the initial state (io/dump.py:45-47)
     if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
+    if constexpr (S::BIAS < 0) {  // NDRun.begin appends the initial state to Stat (ndrun.py:201)
+      if (A.begin_mode && (bias_mask & BIAS_CVHIST)) A.cvhist[(A.cvhist_n % A.cvhist_cap) * M + w] = o.cv.c[0];
+    }
   } else {
     if constexpr (S::DUMP > 0) {
       if (A.begin_mode && dumping) write_frame<R, ND>(K, A, w, A.frame_base, s, time, cd, bias_mask, x, v, o, true);
@@ -697,6 +708,44 @@ __global__ void hill_variance_kernel(const __grid_constant__ Consts<R> K, long l
 #pragma unroll
   for (int d = 0; d < ND; d++) jj += row[d] * row[d];
   const R s = first ? jj : jj * K.mtd_sig2[0];
+  const R inv = (R)1.0 / s;
+  const int rs = K.hill_stride;
+  if (K.mtd_shared) {
+    R* rec = hills + (n_hills + walker_offset + w) * rs;
+    rec[2] = inv; rec[3] = s;
+  } else {
+    hills[(n_hills * rs + 2) * M + w] = inv;
+    hills[(n_hills * rs + 3) * M + w] = s;
+  }
+}
+
+// adapsig without adapsig_geo (gaus.py:166-183 first hill, :193-212 later hills): the variance of the new hill is the
+// exponentially weighted variance of the walker's recent colvar history, Stat.colv, kept by the step kernel in a ring
+// (BIAS_CVHIST).  n samples exist; the window is the last tao_d of them -- the FIRST hill of a table takes
+// stat.colv[-tao_d:-1] (one sample fewer) when the history is longer than tao_d.  A sample within 1e-10 of the mean
+// (in particular a history of one sample) gives variance 1.  colvardim 1.
+template <typename R>
+__global__ void hill_variance_hist_kernel(const __grid_constant__ Consts<R> K, long long M, long long walker_offset,
+                                          const R* __restrict__ ring, int cap, long long n, int tao_d,
+                                          R* hills, long long n_hills, int first) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= M) return;
+  long long j0, j1;  // samples [j0, j1)
+  if (n <= tao_d) { j0 = 0; j1 = n; }
+  else if (first) { j0 = n - tao_d; j1 = n - 1; }
+  else { j0 = n - tao_d; j1 = n; }
+  const int n0 = (int)(j1 - j0);
+  R avg = (R)0;
+  for (long long j = j0; j < j1; j++) avg += ring[(j % cap) * M + w];
+  avg /= (R)n0;  // np.average(colv, axis=0)
+  R mind = (R)1e300 < (R)3e38 ? (R)1e300 : (R)3e38, acc = (R)0;
+  for (int i = 0; i < n0; i++) {
+    const R d = ring[((j0 + i) % cap) * M + w] - avg;
+    const R ad = d < (R)0 ? -d : d;
+    mind = ad < mind ? ad : mind;
+    acc += nds_exp(-((R)(n0 - i)) / (R)n0) * d * d;  // exp(-(n0 - arange(n0)) / n0), gaus.py:180,208
+  }
+  const R s = (n0 == 0 || mind < (R)1e-10) ? (R)1 : acc / (R)n0;
   const R inv = (R)1.0 / s;
   const int rs = K.hill_stride;
   if (K.mtd_shared) {

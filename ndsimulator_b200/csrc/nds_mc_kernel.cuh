@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(NDS_BLOCK)
 mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<R> A, long long* accepted,
          R* wl_hE /* [NDS_WL_GRID][M] per-walker histograms, Wang-Landau only */,
          double* mc_time /* [M] NDRun.time of each walker: advances on ACCEPTED moves only (ndrun.py:234-237) */,
-         long long* mc_dep /* [M] Gaussian._dep_count of each walker's own table */,
+         long long* mc_dep /* [M] Gaussian._dep_count of each walker's own table; [M] = overflow flag */,
          R* hills_rw /* per-walker hill tables, written by the in-kernel deposition */) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long M = A.M;
@@ -75,10 +75,16 @@ mc_block(const __grid_constant__ Consts<R> K, const __grid_constant__ BlockArgs<
   long long acc = accepted[w];
   const long long acc0 = acc;
 
-  bool deposited = false;
+  bool deposited = false, overflowed = false;
   R ke = A.thermo[2 * M + w], tot = A.thermo[4 * M + w];  // atoms.ke / atoms.totale follow the last event
   for (long long s = A.step0; s < A.step0 + A.nsteps; s++) {
-    if (mtd && (long long)floor(tw / K.mtd_dep_freq64) + 1 > dep && dep < K.mtd_capacity) {
+    const bool dep_due = mtd && (long long)floor(tw / K.mtd_dep_freq64) + 1 > dep;
+    if (dep_due && dep >= K.mtd_capacity && !overflowed) {
+      // no room for the hill the reference would deposit here: reported by run_mc ("hill table full")
+      atomicMax(reinterpret_cast<unsigned long long*>(mc_dep + M), (unsigned long long)(w + 1));
+      overflowed = true;
+    }
+    if (dep_due && dep < K.mtd_capacity) {
       // Gaussian.update -> _deposite (gaus.py:130-213) at atoms.colv with the VR of the last refresh, then the
       // refresh itself (pe, forces, fixf, biase with the new hill, VR, totale), gaus.py:138-146
       const R h = dep == 0 ? K.mtd_w : K.mtd_w * nds_exp(-vr / K.mtd_kBdT);

@@ -47,13 +47,15 @@ class DumpWriter:
         self.hills_dumped = 0
         self.umb_vr = None
 
-    def open_files(self):
+    def open_files(self, append=False):
+        """append: continue the files of an interrupted run (NDRun.load_checkpoint); no second header."""
         names = ["thermo", "pos", "force", "velocity", "colvar"] + [f"fix{i}" for i in range(len(self.fix_names))]
         for d in self.dirs:
-            self.files.append({n: open(os.path.join(d, f"{n}.dat"), "w") for n in names})
+            self.files.append({n: open(os.path.join(d, f"{n}.dat"), "a" if append else "w") for n in names})
         header = "#time dt T pe ke biase totale" + "".join(f" fix_VR_{i}" for i in range(len(self.fix_names)))
         for f in self.files:
-            f["thermo"].write(header + "\n")  # dump.py:71-74
+            if not (append and f["thermo"].tell() > 0):
+                f["thermo"].write(header + "\n")  # dump.py:71-74
 
     def close_files(self):
         for f in self.files:

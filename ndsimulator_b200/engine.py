@@ -228,6 +228,18 @@ class Engine:
         g = _f64(g, self.grid_shape())
         self._check(self.lib.nds_set_mtd_grid(self.h, _p(g), g.size))
 
+    def get_cv_history(self):
+        """-> (ring [window][M], n_samples): the Stat.colv window the history-based adaptive sigma reads."""
+        n, win = C.c_int64(), C.c_int64()
+        self._check(self.lib.nds_get_cv_history(self.h, None, 0, C.byref(n), C.byref(win)))
+        ring = np.empty((win.value, self.M))
+        self._check(self.lib.nds_get_cv_history(self.h, _p(ring), ring.size, C.byref(n), C.byref(win)))
+        return ring, int(n.value)
+
+    def set_cv_history(self, ring, n_samples):
+        ring = _f64(ring)
+        self._check(self.lib.nds_set_cv_history(self.h, _p(ring), int(n_samples)))
+
     def mtd_grid_outside(self):
         return int(self.lib.nds_mtd_grid_outside(self.h))
 
@@ -280,7 +292,7 @@ class Engine:
             if self.cfg.mtd_shared:
                 c, h = self.get_hills(0)
                 ck.update(hills_centers=c, hills_heights=h)
-                if self.cfg.mtd_adapsig_geo:
+                if self.cfg.mtd_adapsig_geo or self.cfg.mtd_adapsig_hist:
                     ck["hills_sigma2"] = self.get_hill_sigma2(0)
                 if self.cfg.mtd_grid:  # the grid holds every rank's hills; the table only this rank's
                     ck["mtd_grid"] = self.get_mtd_grid()
@@ -290,6 +302,8 @@ class Engine:
                 self._check(self.lib.nds_get_hill_table_raw(self.h, _p(raw), raw.size))
                 ck.update(hills_raw=raw, hills_n=n)
             ck["vr"] = self.get_vr()
+            if self.cfg.mtd_adapsig_hist:
+                ck["cv_history"], ck["cv_history_n"] = self.get_cv_history()
         return ck
 
     def restore(self, ck):
@@ -304,6 +318,8 @@ class Engine:
             if "mtd_grid" in ck:
                 self.set_mtd_grid(ck["mtd_grid"])
             self.set_vr(ck["vr"])
+        if "cv_history" in ck:  # after begin(), which appended a sample of its own
+            self.set_cv_history(ck["cv_history"], int(ck["cv_history_n"]))
         if "alive" in ck:
             b = np.ascontiguousarray(ck["basin"], dtype=np.int32)
             e = np.ascontiguousarray(ck["exit_step"], dtype=np.int64)
@@ -365,6 +381,10 @@ class Engine:
         got = C.c_int64()
         self._check(self.lib.nds_drain_frames(self.h, _p(out), n, C.byref(got)))
         return out[:got.value]
+
+    def discard_frames(self):
+        """Rewind the frame ring without reading it (nds_drain_frames with a NULL destination)."""
+        self._check(self.lib.nds_drain_frames(self.h, None, 0, None))
 
     def get_histogram(self, clear=False):
         """Colvar histogram accumulated inside the step kernels since ``begin()``: ``counts[ny][nx]``."""

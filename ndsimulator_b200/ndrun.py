@@ -225,7 +225,7 @@ class NDRun:
         if len(frames) == 0:
             return
         hills = self.engine.get_hills(0) if "mtd" in self.spec.biases else None
-        if hills is not None and self.spec.mtd_adapsig_geo:
+        if hills is not None and (self.spec.mtd_adapsig_geo or self.spec.mtd_adapsig_hist):
             hills = hills + (self.engine.get_hill_sigma2(0),)
         self._dump.write_frames(frames, self.engine.frame_fields(), hills=hills, hills_at=self._hills_at)
         if self.spec.screen:  # ndrun.py:222-224: "<step> temperature: <T>" every dump.freq steps
@@ -306,8 +306,16 @@ class NDRun:
         return self.engine.colvar_histogram(boundary[0][0], increment[0], nx, boundary[1][0], increment[1], ny)
 
     def save_checkpoint(self, path):
-        """(x, v, clock, hill table, VR) -> .npz; with the same config + seed the run continues bit for bit."""
+        """(x, v, clock, hill table, VR) and the host-side dump bookkeeping -> .npz; with the same config + seed the
+        run -- and its dump files -- continue exactly where they stopped."""
         ck = self.engine.checkpoint()
+        ck["host_dep_steps"] = np.asarray(getattr(self, "_dep_steps", []), dtype=np.int64)
+        if self._dump is not None:
+            ck["host_hills_dumped"] = self._dump.hills_dumped
+            if self._dump.lag is not None:
+                ck["host_lag"] = np.asarray(self._dump.lag)
+            if self._dump.umb_vr is not None:
+                ck["host_umb_vr"] = np.asarray(self._dump.umb_vr)
         np.savez(path, **{k: np.asarray(v) for k, v in ck.items()})
 
     def load_checkpoint(self, path):
@@ -315,8 +323,18 @@ class NDRun:
         ck = {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
         self.engine.restore(ck)
         self.step, self.time = int(ck["step"]), float(ck["time"])
-        self._dep_steps = []
+        # deposition steps so far: fix{i}.dat lists the hills that existed at each dump row (_hills_at)
+        self._dep_steps = [int(s) for s in np.atleast_1d(ck.get("host_dep_steps", []))]
         self._cache = None
+        if self.spec.dump:
+            # Engine.restore() ran begin(), which recorded a frame labelled step 0: not part of a continued run
+            self.engine.discard_frames()
+            if self._dump is None:  # fresh process: continue the files of the interrupted run
+                self._dump = DumpWriter(self.spec, int(min(self.spec.dump_walkers, self.spec.n_walkers)))
+                self._dump.open_files(append=True)
+            self._dump.hills_dumped = int(ck.get("host_hills_dumped", 0))
+            self._dump.lag = ck.get("host_lag")
+            self._dump.umb_vr = ck.get("host_umb_vr")
 
     @classmethod
     def from_dict(cls, dictionary):  # ndrun.py:270-282

@@ -277,6 +277,22 @@ def trajectories():
     out["5d_mtd_adapsig_geo_Proj5dto1d_seed3"] = run_traj(
         base_cfg(ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
                  x0=[12.0] * 5, seed=3, steps=1000, **adap), 100)
+    # adapsig WITHOUT adapsig_geo (gaus.py:166-183, 193-212): the variance of every hill is the exponentially weighted
+    # variance of the last tao_d = min(50 dep_freq, 100) Stat samples of the colvar.  In the reference this only runs
+    # for a colvar of shape (1,) -- ndim 1 with the Original colvar: the (1, 1)-shaped 1-output colvars of two.py /
+    # five.py (A28) make dcol.T.dot(exp) fail at the second deposition, and for 2-D colvars the element-wise
+    # 1 / covariance of gaus.py:268-277 makes the bias diverge.  Case 1 crosses n > tao_d (a sample every step,
+    # tao_d = 100); case 2 samples every 5 steps with a shorter window (dep_freq 1 -> tao_d = 50, a hill every step
+    # of time... every dt).
+    hist = dict(ndim=1, potential="DoubleWell1d", x0=30.0, integrate="langevin", gamma=0.1, biases=["mtd"],
+                mtd_sigma=2.0, mtd_biasf=10.0, mtd_adapsig=True, mtd_adapsig_geo=False, plot_boundary=[[0.0, 40.0]])
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # gaus.py:203 prints the window on every deposition
+        out["1d_mtd_adapsig_hist_doublewell_seed5"] = run_traj(
+            base_cfg(seed=5, steps=1200, mtd_w=0.05, mtd_dep_freq=50, **hist), 100)
+        out["1d_mtd_adapsig_hist_doublewell_stat5_seed6"] = run_traj(
+            base_cfg(seed=6, steps=1500, stat_freq=5, mtd_w=0.002, mtd_dep_freq=7, **hist), 100)
     dump("trajectories.json", out)
 
 
@@ -485,8 +501,55 @@ def mc_runs():
     dump("mc.json", out)
 
 
+def fes_projection():
+    """Gaussian.projection (gaus.py:365-438) on the plot grid np.meshgrid(arange(b0, b1, inc), ...) of io/plot.py:483-488,
+    called the way Plot does: once while the run is under way and again at the end, so that the incremental
+    bookkeeping (_dep_projection) is the reference's own.  The 1-D adaptive branch (gaus.py:425-436) has no
+    `if value is False` guard and re-adds EVERY hill on every call: that case records one call only."""
+    out = {}
+    mtd = yaml.safe_load(open(os.path.join(EXAMPLES, "2d-mtd.yaml")))
+    mtd.update(root=TMP, run_name="g", dump=False, screen=False, seed=0, steps=1000)
+    cases = {
+        "2d_fixed_sigma_incremental": (mtd, [[0.0, 48.0], [0.0, 40.0]], [1.0, 1.0], 2),
+        "1d_fixed_sigma_incremental": (
+            base_cfg(ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], seed=2, steps=1000,
+                     integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05, mtd_sigma=[1.5], mtd_dep_freq=50,
+                     mtd_biasf=10.0), [[-30.0, 30.0]], [0.25], 2),
+        "1d_adapsig_geo_single_call": (
+            base_cfg(ndim=5, potential="Mueller5d", colvar_name="Proj5dto1d", true_colvar_name="Proj5dto2d",
+                     x0=[12.0] * 5, seed=3, steps=600, integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05,
+                     mtd_sigma=2.0, mtd_dep_freq=50, mtd_biasf=10.0, mtd_adapsig=True, mtd_adapsig_geo=True),
+            [[0.0, 30.0]], [0.2], 1),
+    }
+    for name, (cfg, boundary, inc, calls) in cases.items():
+        sim = unshadow(ref_stub.make_run(cfg))
+        sim.begin()
+        fix = [f for f in sim.fixes if type(f).__name__ == "Gaussian"][0]
+        b = np.array(boundary, dtype=float)
+        if len(boundary) == 2:
+            X, Y = np.meshgrid(np.arange(b[0, 0], b[0, 1], inc[0]), np.arange(b[1, 0], b[1, 1], inc[1]))
+        else:
+            X, Y = np.arange(b[0, 0], b[0, 1], inc[0]), None
+        total, done, maps, n_at_call = cfg["steps"], 0, [], []
+        for c in range(calls):
+            sim.steps = total * (c + 1) // calls
+            sim.run()
+            m = fix.projection(X, Y)
+            maps.append(np.array(m, dtype=float).copy())
+            n_at_call.append(int(fix._history.shape[0]))
+        rec = dict(config={k: v for k, v in cfg.items() if k not in ("root", "run_name")}, boundary=boundary,
+                   increment=inc, shape=list(maps[-1].shape), hills_at_call=n_at_call,
+                   hills_centers=np.asarray(fix._history, dtype=float).tolist(), hills_heights=tolist(fix._w),
+                   maps=[tolist(m) for m in maps])
+        if fix.adapsig:
+            rec["hills_sigma2"] = [float(np.asarray(m).reshape(-1)[0]) for m in fix._sigma_history]
+        out[name] = rec
+    dump("fes_projection.json", out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor", "mc_runs"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor", "mc_runs", "trajectories",
+                                             "fes_projection"):
         globals()[sys.argv[1]]()
         sys.exit(0)
     eval_points()
@@ -497,3 +560,4 @@ if __name__ == "__main__":
     dump_files()
     path_colvars()
     mc_runs()
+    fes_projection()

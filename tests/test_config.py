@@ -90,8 +90,11 @@ def test_out_of_scope_is_refused_loudly():
     s = config.parse(base(method="committor", temperature=0, n_basins=1, criteria=[[[0, 1], [0, 1]]]))
     assert s.integrate == "minimize" and s.emin == -1.2 and s.to_struct().min_maxiter == 1000
     assert config.parse(base(method="minimize")).integrate == "minimize"
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # history-based adapsig with a 2-D colvar: divergent in the reference (gaus.py:268-277)
         config.parse(base(biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=2.0, mtd_adapsig=True))
+    h = config.parse(base(colvar_name="XmY", biases=["mtd"], mtd_w=0.1, mtd_sigma=1.5, mtd_biasf=2.0,
+                          mtd_adapsig=True)).to_struct()
+    assert h.mtd_adapsig_hist == 1 and h.mtd_adapsig_geo == 0
     with pytest.raises(ValueError):  # adapsig_geo with a 2-D colvar: inf / NaN in the reference (gaus.py:268-275)
         config.parse(base(biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=2.0, mtd_adapsig=True,
                           mtd_adapsig_geo=True))

@@ -60,6 +60,31 @@ def test_dump_files_match_reference(name, tmp_path):
     assert f"end condition {cfg['steps']} {cfg['steps']} True" in log
 
 
+@pytest.mark.parametrize("name,stop", [("2d_mtd_gamma0_dump100", 150), ("2d_mtd_gamma0_dump100", 200),
+                                       ("5d_umb_nve_stat10", 30), ("2d_mtd_adapsig_geo_xmy_gamma0", 70)])
+def test_dump_files_after_checkpoint_resume(name, stop, tmp_path):
+    """Stop at `stop`, save, load into a fresh NDRun (which appends to the files), finish: the dump files are still
+    the reference's -- no duplicate step-0 row, the hill listing of fix{i}.dat and the lagged thermo sample survive."""
+    rec = load_golden("dump_files.json")[name]
+    cfg = dict(rec["config"], root=str(tmp_path), run_name="r", screen=False, precision="f64")
+    sim = NDRun(**cfg)
+    sim.modify.set_velocity(v=np.array(rec["v0"]))
+    sim.begin()
+    sim.run(stop)
+    ck = os.path.join(str(tmp_path), "ck.npz")
+    sim.save_checkpoint(ck)
+    sim.end()
+    sim = NDRun(**cfg)
+    sim.load_checkpoint(ck)
+    assert sim.step == stop and sim.engine.frames_pending() == 0
+    sim.run()
+    sim.end()
+    for fn, want in rec["files"].items():
+        with open(os.path.join(str(tmp_path), "r", fn)) as f:
+            got = f.read()
+        assert_same_text(got, want, what=f"{name}/{fn}")
+
+
 def test_ndrun_protocol_and_atoms_view(tmp_path):
     cfg = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 24.0], method="md", integrate="nve",
                temperature=300, dt=1.0, seed=7, steps=500, dump=False, screen=False, root=str(tmp_path),

@@ -327,6 +327,24 @@ def _check_against_reference(sim, rec, every=1):
         assert np.array_equal(sim.get_wl_histogram(0), np.array(rec["hE"]))
 
 
+@pytest.mark.gpu
+def test_gpu_mc_metadynamics_full_table_fails_loudly():
+    """A walker that has a hill to deposit and no room left in its table must not silently stop depositing: nds_run
+    fails with the MD path's 'hill table full'."""
+    from ndsimulator_b200.engine import Engine, NdsError
+    M, n = 8, 600
+    cfg = dict(M2, dt=0.5, biases=["mtd"], mtd_w=0.02, mtd_dep_freq=10, mtd_biasf=8.0, mtd_sigma=[1.5, 1.5],
+               steps=n, mtd_capacity=5)
+    spec = spec_from(cfg, n_walkers=M, steps_per_launch=64)
+    eng = Engine(spec.to_struct())
+    eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
+    eng.begin()
+    eng.run(100)                       # <= 100 accepted moves * 0.5 / 10 + 1 = 6 > 5 only if everything is accepted
+    assert max(eng.n_hills(w) for w in range(M)) <= 5
+    with pytest.raises(NdsError, match="hill table full"):
+        eng.run(n)
+
+
 MC_CASES = ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo", "wl_single_2d"]
 
 

@@ -161,3 +161,31 @@ def test_committor_temperature_zero_minimize():
     assert np.allclose(st["x"].T, np.array([r["x"] for r in runs]), rtol=1e-12)
     assert np.allclose(st["pe"], [r["pe"] for r in runs], rtol=1e-12)
     assert np.allclose(st["colv"].T, np.array([r["colv"] for r in runs]), rtol=1e-12)
+
+
+FES = load_golden("fes_projection.json")
+
+
+def fes_case_grid(rec):
+    """(x0, dx, nx[, y0, dy, ny]) of np.arange(b0, b1, inc) per colvar (io/plot.py:483-488)."""
+    args = []
+    for (b0, b1), inc in zip(rec["boundary"], rec["increment"]):
+        args += [b0, inc, len(np.arange(b0, b1, inc))]
+    return args
+
+
+@pytest.mark.parametrize("name", sorted(FES))
+def test_fes_projection_matches_reference(name):
+    """Gaussian.projection (gaus.py:365-438) as the reference's Plot calls it, incremental calls included: the map
+    after call k is the sum of the hills deposited by then."""
+    rec = FES[name]
+    spec = spec_from(rec["config"])
+    centers, heights = np.array(rec["hills_centers"]), np.array(rec["hills_heights"])
+    for n, want in zip(rec["hills_at_call"], rec["maps"]):
+        o = oracle.OracleSim(spec.to_struct(), seeds=[0])
+        o.set_hills(centers[:n], heights[:n])
+        if "hills_sigma2" in rec:
+            o.set_hill_sigma2(rec["hills_sigma2"][:n])
+        g = o.fes_grid(*fes_case_grid(rec))
+        want = np.array(want).reshape(rec["shape"])
+        assert g.reshape(want.shape) == pytest.approx(want, rel=1e-12, abs=1e-300)

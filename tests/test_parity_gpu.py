@@ -147,7 +147,8 @@ def test_trajectories(name):
 # ------------------------------------------ the reference's STOCHASTIC runs, given the reference's own Gaussians
 STOCHASTIC = ["2d_langevin_gamma0.1_seed0", "2d_md_yaml_as_shipped_seed0", "2d_langevin2_seed3", "5d_umb_seed0",
               "2d_umb_seed1", "2d_mtd_seed0", "5d_mtd_seed2", "1d_doublewell_langevin_seed4",
-              "2d_doublewell_pe_seed6", "2d_mtd_adapsig_geo_XmY_seed2", "5d_mtd_adapsig_geo_Proj5dto1d_seed3"]
+              "2d_doublewell_pe_seed6", "2d_mtd_adapsig_geo_XmY_seed2", "5d_mtd_adapsig_geo_Proj5dto1d_seed3",
+              "1d_mtd_adapsig_hist_doublewell_seed5", "1d_mtd_adapsig_hist_doublewell_stat5_seed6"]
 
 
 def reference_normals(seed, ndim, nsteps, per_step):
@@ -198,8 +199,8 @@ def test_stochastic_trajectories_with_the_references_own_noise(name):
         c, h = eng.get_hills()
         assert np.allclose(h, rec["hills_heights"], rtol=1e-9) and np.allclose(c, np.array(rec["hills_centers"]), rtol=1e-9)
         assert eng.get_vr()[0] == pytest.approx(rec["VR"], rel=1e-8)
-    if "hills_sigma2" in rec:
-        assert np.allclose(eng.get_hill_sigma2(), rec["hills_sigma2"], rtol=1e-12)
+    if "hills_sigma2" in rec:  # adapsig_geo: J.J^T (* sigma^2); history-based adapsig: weighted variance of Stat.colv
+        assert np.allclose(eng.get_hill_sigma2(), rec["hills_sigma2"], rtol=1e-12 if cfg.get("mtd_adapsig_geo") else 1e-9)
 
 
 # -------------------------------------------------- every integrator / bias with externally given noise
@@ -356,6 +357,83 @@ def test_mtd_adapsig_geo_external_noise(case):
         eng2.restore(ck)
         assert np.array_equal(eng2.get_hill_sigma2(0), s0)
         assert scaled_err(eng2.eval_at(pts)["Vb"], ea["Vb"]) < 1e-14
+
+
+@pytest.mark.parametrize("case", ["1d_shared_f64", "2d_xmy_per_walker_f64", "1d_shared_f32"])
+def test_mtd_adapsig_history_external_noise(case):
+    """adapsig without adapsig_geo (gaus.py:166-183, 193-212): the step kernel keeps the Stat.colv window of every
+    walker in a device ring (sampled every stat_freq steps, launch boundaries anywhere), the deposition takes the
+    exponentially weighted variance of it.  Many walkers, shared and per-walker tables, against the oracle (pinned to
+    the reference's own runs by tests/golden/trajectories.json); checkpoint / resume carries the window."""
+    M, n = 12, 700
+    hist = dict(integrate="langevin", gamma=0.1, dt=1.0, temperature=300, mass=1.0, biases=["mtd"], mtd_w=0.02,
+                mtd_sigma=2.0, mtd_dep_freq=30, mtd_biasf=10.0, mtd_adapsig=True, mtd_adapsig_geo=False, steps=n)
+    if case.startswith("1d"):
+        cfg = dict(hist, ndim=1, potential="DoubleWell1d", x0=30.0, mtd_shared=True, stat_freq=3)
+    else:  # a (1, 1)-shaped colvar: the reference cannot run this one (dcol.T.dot fails), the engine and oracle can
+        cfg = dict(hist, ndim=2, potential="Mueller2d", colvar_name="XmY", x0=[22.0, 24.0], mtd_shared=False)
+    f32 = case.endswith("f32")
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=37,
+                               precision="f32" if f32 else "f64")
+    nd = spec.ndim
+    noise = noise_table(33, n, nd, M)
+    rng = np.random.RandomState(4)
+    x0 = spec.x0.reshape(-1, 1) + rng.normal(scale=0.5, size=(nd, M))
+    for sim in (eng, orc):
+        sim.set_state(x0, np.zeros((nd, M)))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(400)
+    ck = eng.checkpoint()
+    for sim in (eng, orc):
+        sim.run(n - 400)
+    tol = 5e-3 if f32 else TRAJ_TOL
+    ndep = n // 30 + 1
+    for wk in (0, M - 1):
+        (ce, we), (co, wo) = eng.get_hills(wk), orc.get_hills(wk)
+        se, so = eng.get_hill_sigma2(wk), orc.get_hill_sigma2(wk)
+        assert len(we) == len(wo) == len(se) == (ndep * M if cfg["mtd_shared"] else ndep)
+        assert np.allclose(se, so, rtol=1e-3 if f32 else 1e-8)
+        assert np.allclose(we, wo, rtol=tol) and np.allclose(ce, co, rtol=tol)
+    s0 = eng.get_hill_sigma2(0)
+    assert np.all(s0[:M if cfg["mtd_shared"] else 1] == 1.0)    # one sample: |dcol| < 1e-10 -> variance 1
+    assert len(np.unique(s0)) > ndep // 2                       # later hills: each its own variance
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "biase") if f32 else ("x", "v", "fixf", "biase"):  # fp32: narrow hills amplify rounding in fixf
+        assert scaled_err(a[k], b[k]) < tol, k
+    if not f32:
+        ring, ns = eng.get_cv_history()
+        assert ns == 1 + n // spec.stat_freq and ring.shape == (100, M)
+        # resume from step 400 on a fresh engine: same hills, same state
+        eng2 = Engine(spec.to_struct())
+        eng2.restore(ck)
+        eng2.set_noise(noise)
+        eng2.run(n - 400)
+        a2 = eng2.get_state()
+        for k in ("x", "v", "biase"):
+            assert np.array_equal(a2[k], a[k]), k
+        assert np.array_equal(eng2.get_hill_sigma2(0), s0)
+
+
+FES = load_golden("fes_projection.json")
+
+
+@pytest.mark.parametrize("name", sorted(FES))
+def test_fes_grid_matches_reference_projection(name):
+    """nds_fes_grid against Gaussian.projection of the reference itself (gaus.py:365-438 on the plot grid of
+    io/plot.py:483-488), incremental calls included."""
+    rec = FES[name]
+    spec = spec_from(rec["config"], precision="f64")
+    centers, heights = np.array(rec["hills_centers"]), np.array(rec["hills_heights"])
+    args = []
+    for (b0, b1), inc in zip(rec["boundary"], rec["increment"]):
+        args += [b0, inc, len(np.arange(b0, b1, inc))]
+    for n, want in zip(rec["hills_at_call"], rec["maps"]):
+        eng = Engine(spec.to_struct())
+        eng.set_hills(centers[:n], heights[:n], sigma2=rec["hills_sigma2"][:n] if "hills_sigma2" in rec else None)
+        g = eng.fes_grid(*args)
+        want = np.array(want).reshape(rec["shape"])
+        assert g.reshape(want.shape) == pytest.approx(want, rel=1e-11, abs=1e-300)
 
 
 def test_committor_external_noise():
