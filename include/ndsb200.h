@@ -426,6 +426,13 @@ NDS_API const char* nds_kernel_name(const nds_engine* e);
 /* Philox4x32-10 known-answer hook (tests): out[4] = philox(ctr[4], key[2]) computed ON DEVICE.  */
 NDS_API int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 
+/* Tail census of the Gaussian stream (tests): draws n_walkers * calls_per_walker * 6 normals of the per-step stream
+ * of `seed` through the very function the step kernels call, in the given precision, and returns counts[t] =
+ * #{|z| > thresholds[t]} (n_thresholds <= 8) and stats4 = {sum z, sum z^2, sum z^4, max |z|}.               */
+NDS_API int nds_noise_tail_counts(int device, int precision, uint64_t seed, int64_t n_walkers,
+                                  int64_t calls_per_walker, const double* thresholds, int n_thresholds,
+                                  uint64_t* counts, double* stats4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,6 +170,8 @@ _PROTOTYPES = {
     "nds_kernel_name": (C.c_char_p, [C.c_void_p]),
     "nds_philox_kat": (C.c_int, [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                  C.POINTER(C.c_uint32)]),
+    "nds_noise_tail_counts": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_double),
+                                        C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

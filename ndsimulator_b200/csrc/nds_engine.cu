@@ -506,6 +506,50 @@ static __global__ void philox_kat_kernel(u32x4 c, uint32_t k0, uint32_t k1, uint
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+// Tail census of the step-noise stream (tests): every thread draws `calls` Philox calls of one
+// walker through normals6<R> -- the function the step kernels use -- and counts |z| above each threshold.
+constexpr int NDS_MAX_THR = 8;
+struct TailArgs { double thr[NDS_MAX_THR]; int n_thr; };
+template <typename R>
+static __global__ void noise_tail_kernel(PhiloxKeys rk, long long n_walkers, long long calls, TailArgs T,
+                                         unsigned long long* counts, double* stats) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long cnt[NDS_MAX_THR];
+  R thr[NDS_MAX_THR];
+#pragma unroll
+  for (int t = 0; t < NDS_MAX_THR; t++) { cnt[t] = 0ull; thr[t] = t < T.n_thr ? (R)T.thr[t] : (R)1e30; }
+  double s1 = 0.0, s2 = 0.0, s4 = 0.0, mx = 0.0;
+  if (w < n_walkers) {
+    for (long long c = 0; c < calls; c++) {
+      R z[NDS_NPC];
+      normals6<R>(rk, (unsigned long long)c, (unsigned long long)w, z);
+      R p1 = (R)0, p2 = (R)0, p4 = (R)0;
+#pragma unroll
+      for (int j = 0; j < NDS_NPC; j++) {
+        const R a = z[j] < (R)0 ? -z[j] : z[j];
+        p1 += z[j]; p2 += a * a; p4 += (a * a) * (a * a);
+        mx = (double)a > mx ? (double)a : mx;
+#pragma unroll
+        for (int t = 0; t < NDS_MAX_THR; t++) cnt[t] += a > thr[t] ? 1ull : 0ull;
+      }
+      s1 += (double)p1; s2 += (double)p2; s4 += (double)p4;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    s4 += __shfl_down_sync(0xffffffffu, s4, o);
+    const double m2 = __shfl_down_sync(0xffffffffu, mx, o); mx = m2 > mx ? m2 : mx;
+#pragma unroll
+    for (int t = 0; t < NDS_MAX_THR; t++) cnt[t] += __shfl_down_sync(0xffffffffu, cnt[t], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&stats[0], s1); atomicAdd(&stats[1], s2); atomicAdd(&stats[2], s4);
+    atomicMax(reinterpret_cast<unsigned long long*>(&stats[3]), (unsigned long long)__double_as_longlong(mx));
+    for (int t = 0; t < T.n_thr; t++) atomicAdd(&counts[t], cnt[t]);
+  }
+}
+
 static __global__ void compact_lists_kernel(long long n, long long n_alive, const unsigned char* alive,
                                      const int* scan, int* holes, int* movers, int* n_holes) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -755,7 +799,8 @@ struct Engine : nds_engine {
         }
       }
     }
-    if (c.mtd_enabled && c.mtd_shared && !grid_mode && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping) {
+    if (c.mtd_enabled && c.mtd_shared && !grid_mode && (cd == 2 || cd == 1) && !K.mtd_adaptive && c.method == NDS_METHOD_MD && !dumping &&
+        !getenv("NDS_NO_MTD_BLOCK")) {
       cudaDeviceProp prop;
       CU(cudaGetDeviceProperties(&prop, c.device));
       const MtdVariant* mv = pick_mtd_variant(c, K.bias_mask, prop.multiProcessorCount);
@@ -2331,6 +2376,34 @@ int nds_philox_kat(int device, const uint32_t* ctr, const uint32_t* key, uint32_
   cudaError_t err = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
   cudaFree(d);
   return err == cudaSuccess ? 0 : fail(nullptr, "nds_philox_kat: %s", cudaGetErrorString(err));
+}
+
+int nds_noise_tail_counts(int device, int precision, uint64_t seed, int64_t n_walkers, int64_t calls_per_walker,
+                          const double* thresholds, int n_thresholds, uint64_t* counts, double* stats4) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "nds_noise_tail_counts: no CUDA device");
+  if (n_thresholds < 0 || n_thresholds > NDS_MAX_THR) return fail(nullptr, "nds_noise_tail_counts: at most %d thresholds", NDS_MAX_THR);
+  if (n_walkers <= 0 || calls_per_walker <= 0) return fail(nullptr, "nds_noise_tail_counts: empty request");
+  TailArgs T;
+  for (int t = 0; t < NDS_MAX_THR; t++) T.thr[t] = t < n_thresholds ? thresholds[t] : 1e30;
+  T.n_thr = n_thresholds;
+  unsigned long long* d_counts = nullptr;
+  double* d_stats = nullptr;
+  if (cudaMalloc(&d_counts, sizeof(unsigned long long) * NDS_MAX_THR) != cudaSuccess || cudaMalloc(&d_stats, sizeof(double) * 4) != cudaSuccess)
+    return fail(nullptr, "nds_noise_tail_counts: cudaMalloc failed");
+  cudaMemset(d_counts, 0, sizeof(unsigned long long) * NDS_MAX_THR);
+  cudaMemset(d_stats, 0, sizeof(double) * 4);
+  // the per-step stream of a run with this seed (domain 0), see nds_philox.cuh
+  const PhiloxKeys rk = philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+  const unsigned grid = (unsigned)((n_walkers + 127) / 128);
+  if (precision == NDS_F64) noise_tail_kernel<double><<<grid, 128>>>(rk, n_walkers, calls_per_walker, T, d_counts, d_stats);
+  else noise_tail_kernel<float><<<grid, 128>>>(rk, n_walkers, calls_per_walker, T, d_counts, d_stats);
+  unsigned long long h[NDS_MAX_THR];
+  cudaError_t err = cudaMemcpy(h, d_counts, sizeof h, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && stats4) err = cudaMemcpy(stats4, d_stats, sizeof(double) * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_counts); cudaFree(d_stats);
+  if (err != cudaSuccess) return fail(nullptr, "nds_noise_tail_counts: %s", cudaGetErrorString(err));
+  for (int t = 0; t < n_thresholds; t++) counts[t] = h[t];
+  return 0;
 }
 
 }  // extern "C"

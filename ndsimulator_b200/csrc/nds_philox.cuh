@@ -9,9 +9,13 @@
 //   key     = (seed_lo, seed_hi ^ domain)          domain 0: per-step noise, 1: initial velocities
 //   counter = (call_lo, call_hi, walker_lo, walker_hi)   walker = GLOBAL walker id
 //   one call yields SIX normals: its 128 bits are cut into six 21-bit fields (three Box-Muller pairs of
-//   a 21-bit radius variate and a 21-bit angle).  32x32 -> 64-bit multiplies run at a quarter of the FP32
-//   rate on sm_100 (profiles/microbench), so Philox is the most expensive part of a 2-D step; fp32 keeps
-//   24 bits at most anyway.  Radius cut-off: sqrt(2 ln 2^21) = 5.40 sigma (24 bits: 5.77).
+//   a radius variate and an angle).  32x32 -> 64-bit multiplies run at a quarter of the FP32 rate on sm_100
+//   (profiles/microbench), so Philox is the most expensive part of a 2-D step.
+//   fp32: u1 = (a + 1/2) 2^-21 (cell midpoint: the tail mass of every cell is right to first order), radius
+//         cut-off sqrt(2 ln 2^22) = 5.52 sigma; fp32 keeps 24 bits at most anyway.
+//   fp64: the parity-precision engine spends a SECOND Philox call (same counter, top bit of the call word set) to
+//         extend every field: 53-bit radius variates u1 = (a 2^32 + e + 1/2) 2^-53 (cut-off 8.57 sigma) and
+//         32 / 32 / 31-bit angles.
 //   Steps are grouped so that a group of G steps uses whole calls (noise_group() in nds_kernels.cuh).
 #pragma once
 #include <cstdint>
@@ -84,20 +88,22 @@ __host__ __device__ inline BmScale bm_scale(double scale) {
 
 __device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, float& z0, float& z1,
                                              BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
-  // u1 = n * 2^-21 with n = a + 1 in [1, 2^21]  (never 0):
+  // u1 = n * 2^-21 with n = a + 1/2 in (0, 2^21)  (never 0; midpoint of the cell):
   //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 21)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
   // angle = 2 pi * b * 2^-21                   -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
-  const float n = (float)(a + 1u);
-  // |.|: at n = 2^21 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
+  const float n = (float)a + 0.5f;  // exact: 22 significant bits
+  // |.|: near n = 2^21 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
   const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), k.ra, k.rb)));
   const float ang = (float)b * 2.9960562263391724e-06f;  // 2 pi 2^-21
   z0 = r * cos_approx(ang);
   z1 = r * sin_approx(ang);
 }
 
-__device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, double& z0, double& z1, BmScale = BmScale{0.f, 0.f}) {
-  const double u1 = ((double)a + 1.0) * 4.76837158203125e-07;  // (0, 1], 2^-21
-  const double u2 = (double)b * 4.76837158203125e-07;          // [0, 1)
+// fp64: 21-bit fields a, b extended by ea (32 bits) and eb (eb_bits bits) from the second Philox call
+__device__ __forceinline__ void box_muller53(uint32_t a, uint32_t ea, uint32_t b, uint32_t eb, int eb_bits, double& z0, double& z1) {
+  const double u1 = ((double)(((unsigned long long)a << 32) | ea) + 0.5) * 1.1102230246251565e-16;  // (0, 1), 2^-53
+  const double u2 = (double)(((unsigned long long)b << eb_bits) | eb) * (eb_bits == 11 ? 2.3283064365386963e-10   // 2^-32
+                                                                                      : 4.6566128730773926e-10);  // 2^-31
   const double r = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi(2.0 * u2, &s, &c);
@@ -117,6 +123,18 @@ __device__ __forceinline__ void normals6(const PhiloxKeys& rk, unsigned long lon
   box_muller21(r.x >> 11, r.y >> 11, z[0], z[1], k);
   box_muller21(r.z >> 11, r.w >> 11, z[2], z[3], k);
   box_muller21((r.x & 0x7FFu) | ((r.y & 0x3FFu) << 11), (r.z & 0x7FFu) | ((r.w & 0x3FFu) << 11), z[4], z[5], k);
+}
+
+template <>
+__device__ __forceinline__ void normals6<double>(const PhiloxKeys& rk, unsigned long long call,
+                                                 unsigned long long walker, double (&z)[NDS_NPC], BmScale) {
+  const u32x4 r = philox4x32_10(
+      u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
+  const u32x4 e = philox4x32_10(
+      u32x4{(uint32_t)call, (uint32_t)(call >> 32) | 0x80000000u, (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
+  box_muller53(r.x >> 11, e.x, r.y >> 11, e.w >> 21, 11, z[0], z[1]);
+  box_muller53(r.z >> 11, e.y, r.w >> 11, (e.w >> 10) & 0x7FFu, 11, z[2], z[3]);
+  box_muller53((r.x & 0x7FFu) | ((r.y & 0x3FFu) << 11), e.z, (r.z & 0x7FFu) | ((r.w & 0x3FFu) << 11), e.w & 0x3FFu, 10, z[4], z[5]);
 }
 
 // f2: the walker pair (walker_a, walker_b), one Philox call each (neighbours, or any two compacted lanes)

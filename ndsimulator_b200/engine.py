@@ -440,3 +440,17 @@ def philox_kat(ctr, key, device=0):
     if lib.nds_philox_kat(device, c, k, out):
         raise NdsError(lib.nds_last_error(None).decode())
     return list(out)
+
+
+def noise_tail_counts(precision, seed, n_walkers, calls_per_walker, thresholds, device=0):
+    """Census of the per-step Gaussian stream on the device: -> (counts of |z| > threshold, dict of moments)."""
+    lib = _abi.load_library()
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+    counts = np.zeros(len(thr), dtype=np.uint64)
+    stats = np.zeros(4)
+    prec = _abi.NDS_F64 if precision == "f64" else _abi.NDS_F32
+    if lib.nds_noise_tail_counts(device, prec, int(seed), int(n_walkers), int(calls_per_walker), _p(thr), len(thr),
+                                 counts.ctypes.data_as(C.POINTER(C.c_uint64)), _p(stats)):
+        raise NdsError(lib.nds_last_error(None).decode())
+    n = 6.0 * n_walkers * calls_per_walker
+    return counts.astype(np.int64), dict(n=n, mean=stats[0] / n, m2=stats[1] / n, m4=stats[2] / n, max=stats[3])

@@ -61,21 +61,55 @@ PHILOX_KAT = [
 ]
 
 
-def philox_normals_f64(seed, walker, n_normals, domain=0):
-    """The engine's fp64 normal stream of one walker (ndsimulator_b200/csrc/nds_philox.cuh)."""
+def philox_normal_fields(seed, walker, call, domain=0):
+    """The three (radius field, angle field) pairs of 21 bits of one Philox call and the words of the extension call
+    (same counter, top bit of the call word set) the fp64 engine adds (ndsimulator_b200/csrc/nds_philox.cuh)."""
     k0 = seed & 0xFFFFFFFF
     k1 = ((seed >> 32) & 0xFFFFFFFF) ^ domain
+    ctr = (call & 0xFFFFFFFF, call >> 32, walker & 0xFFFFFFFF, walker >> 32)
+    r = philox4x32_10(ctr, (k0, k1))
+    e = philox4x32_10((ctr[0], ctr[1] | 0x80000000, ctr[2], ctr[3]), (k0, k1))
+    fields = ((r[0] >> 11, r[1] >> 11), (r[2] >> 11, r[3] >> 11),
+              ((r[0] & 0x7FF) | ((r[1] & 0x3FF) << 11), (r[2] & 0x7FF) | ((r[3] & 0x3FF) << 11)))
+    ext = ((e[0], e[3] >> 21, 11), (e[1], (e[3] >> 10) & 0x7FF, 11), (e[2], e[3] & 0x3FF, 10))
+    return fields, ext
+
+
+def philox_normals_f64(seed, walker, n_normals, domain=0):
+    """The engine's fp64 normal stream of one walker: six normals per call, three Box-Muller pairs of a 53-bit radius
+    variate u1 = (a 2^32 + e + 1/2) 2^-53 and a 32 / 32 / 31-bit angle (nds_philox.cuh normals6<double>)."""
     out = []
     call = 0
     while len(out) < n_normals:
-        r = philox4x32_10((call & 0xFFFFFFFF, call >> 32, walker & 0xFFFFFFFF, walker >> 32), (k0, k1))
-        # six normals per call: three Box-Muller pairs of 21-bit fields (nds_philox.cuh normals6)
-        fields = ((r[0] >> 11, r[1] >> 11), (r[2] >> 11, r[3] >> 11),
-                  ((r[0] & 0x7FF) | ((r[1] & 0x3FF) << 11), (r[2] & 0x7FF) | ((r[3] & 0x3FF) << 11)))
-        for a, b in fields:
-            u1 = (a + 1.0) * 2.0 ** -21
-            u2 = b * 2.0 ** -21
+        fields, ext = philox_normal_fields(seed, walker, call, domain)
+        for (a, b), (ea, eb, bits) in zip(fields, ext):
+            u1 = (float((a << 32) | ea) + 0.5) * 2.0 ** -53
+            u2 = float((b << bits) | eb) * 2.0 ** -(21 + bits)
             rad = np.sqrt(-2.0 * np.log(u1))
             out += [rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)]
         call += 1
     return np.array(out[:n_normals])
+
+
+def philox_normals_f32(seed, walker, n_normals, domain=0):
+    """The fp32 engines' stream in exact arithmetic: 21-bit fields, u1 = (a + 1/2) 2^-21 (cell midpoint), angle
+    2 pi b 2^-21.  The device evaluates this with MUFU approximations (lg2 / sqrt / sin / cos .approx)."""
+    out = []
+    call = 0
+    while len(out) < n_normals:
+        fields, _ = philox_normal_fields(seed, walker, call, domain)
+        for a, b in fields:
+            rad = np.sqrt(-2.0 * np.log((a + 0.5) * 2.0 ** -21))
+            out += [rad * np.cos(2 * np.pi * b * 2.0 ** -21), rad * np.sin(2 * np.pi * b * 2.0 ** -21)]
+        call += 1
+    return np.array(out[:n_normals])
+
+
+def fp32_tail_probability(t):
+    """P(|z| > t) of ONE normal of the fp32 scheme in exact arithmetic: the radius takes the 2^21 values r_n =
+    sqrt(-2 ln((n + 1/2) 2^-21)), the angle is (to 2^-21) uniform, z = r cos / sin(angle)."""
+    n_max = int(np.floor(2.0 ** 21 * np.exp(-t * t / 2.0) + 1))
+    n = np.arange(0, min(n_max, 2 ** 21))
+    r = np.sqrt(-2.0 * np.log((n + 0.5) * 2.0 ** -21))
+    r = r[r > t]
+    return float(np.sum(2.0 / np.pi * np.arccos(t / r)) * 2.0 ** -21)

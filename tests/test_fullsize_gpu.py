@@ -215,39 +215,70 @@ def test_c2_long_horizon_fp32_vs_oracle():
 
 
 def test_c5_multiwalker_fes_fp32_vs_oracle():
-    """Multiple-walker metadynamics (shared table, fp32 mtd_block with MUFU.EX2 / packed FP32) against the
-    oracle's shared-table ensemble: the free-energy estimate (sum of hills on the reference's 48 x 40 grid)
-    agrees within the run-to-run spread of the oracle itself plus 0.1 kT."""
-    M, n = 256, 3000
+    """Multiple-walker metadynamics (shared table, fp32 mtd_block with MUFU.EX2 / packed FP32) against the oracle's
+    shared-table ensembles: the free-energy estimate (sum of hills on the reference's 48 x 40 grid), averaged over
+    600 independent ensembles of 64 walkers on either side, agrees within the north star's plain 0.1 kT RMS.  One
+    ensemble scatters by 0.9 kT; 600 bring the error of either mean to 0.035 kT, so the bar is not met by noise.
+    Second, sharper check: given the same Philox noise the fp32 mtd_block ensemble and the fp64 generic-kernel
+    ensemble stay synchronised (Langevin dynamics contract), so their hill tables give the same surface to 0.01 kT."""
+    from concurrent.futures import ThreadPoolExecutor
+    M, n, S = 64, 3000, 600
     cfg = dict(ndim=5, mass=1.0, potential="Mueller5d", colvar_name="Proj5dto2d",
                true_colvar_name="Proj5dto2d", x0=[12.0] * 5, integrate="langevin", gamma=0.1, dt=1.0,
-               temperature=300, biases=["mtd"], mtd_w=0.002, mtd_sigma=[2.0, 2.0], mtd_dep_freq=100,
-               mtd_biasf=10.0, steps=n, mtd_shared=True, seed=1)
+               temperature=300, biases=["mtd"], mtd_w=0.008, mtd_sigma=[2.0, 2.0], mtd_dep_freq=100,
+               mtd_biasf=10.0, steps=n, mtd_shared=True)
     rng = np.random.RandomState(0)
     x0 = np.stack([rng.uniform(14, 26, M), rng.uniform(-2, 2, M), rng.uniform(20, 32, M),
                    rng.uniform(-2, 2, M), np.full(M, 12.0)])
-    grids = []
-    eng = Engine(spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=100).to_struct())
-    assert eng.kernel_name.startswith("mtd_block")
-    eng.set_state(x0)
-    eng.begin()
-    eng.run(n)
-    grids.append(eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40))
-    for seed0 in (100, 900):
-        orc = oracle.OracleSim(spec_from(cfg, n_walkers=M).to_struct(), seeds=np.arange(seed0, seed0 + M))
-        orc.set_threads(oracle.max_threads())
+
+    def gpu_run(seed, precision="f32"):
+        eng = Engine(spec_from(dict(cfg, seed=seed), n_walkers=M, precision=precision, steps_per_launch=100).to_struct())
+        eng.set_state(x0)
+        eng.begin()
+        eng.run(n)
+        return eng.kernel_name, eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40)
+
+    G = []
+    for s in range(S):
+        name, g = gpu_run(1 + s)
+        assert name.startswith("mtd_block<f32")
+        G.append(g)
+    G = np.array(G)
+
+    ost = spec_from(cfg, n_walkers=M).to_struct()
+
+    def oracle_run(s):  # one thread per ensemble (ctypes releases the GIL): no barrier per step
+        orc = oracle.OracleSim(ost, seeds=np.arange(1000 * (s + 1), 1000 * (s + 1) + M))
+        orc.set_threads(1)
         orc.set_state(x0)
         orc.begin()
         orc.run(n)
-        grids.append(orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40))
+        return orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40)
+
+    with ThreadPoolExecutor(max_workers=oracle.max_threads()) as pool:
+        O = np.array(list(pool.map(oracle_run, range(S))))
     kT = kB * 300
-    mask = grids[1] > 2 * kT
+    mask = O.mean(axis=0) > 2 * kT
+    assert mask.sum() > 100
 
     def rms(u, v):
         d = (u - v)[mask]
         return np.sqrt(((d - d.mean()) ** 2).mean())
 
-    assert mask.sum() > 100
-    spread = rms(grids[1], grids[2])                      # oracle vs oracle, different seeds
-    assert rms(grids[0], grids[1]) < 2 * spread + 0.1 * kT, (rms(grids[0], grids[1]) / kT, spread / kT)
-    assert rms(grids[0], grids[2]) < 2 * spread + 0.1 * kT
+    sem_o = O[:, mask].std(axis=0).mean() / np.sqrt(S)
+    sem_g = G[:, mask].std(axis=0).mean() / np.sqrt(S)
+    assert sem_o < 0.04 * kT and sem_g < 0.04 * kT, (sem_o / kT, sem_g / kT)
+    r = rms(G.mean(axis=0), O.mean(axis=0))
+    assert r < 0.1 * kT, (r / kT, sem_o / kT, sem_g / kT)
+    # same noise, fp32 hot kernel vs fp64 generic kernel
+    import os
+    for seed in (1, 2, 3):
+        os.environ["NDS_NO_MTD_BLOCK"] = "1"
+        try:
+            name64, g64 = gpu_run(seed, "f64")
+        finally:
+            del os.environ["NDS_NO_MTD_BLOCK"]
+        assert name64.startswith("md_block<f64")
+        assert rms(G[seed - 1], g64) < 0.01 * kT, rms(G[seed - 1], g64) / kT
+
+

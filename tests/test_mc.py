@@ -339,7 +339,7 @@ def test_gpu_mc_metadynamics_full_table_fails_loudly():
     eng = Engine(spec.to_struct())
     eng.set_state(np.repeat(spec.x0.reshape(-1, 1), M, axis=1))
     eng.begin()
-    eng.run(100)                       # <= 100 accepted moves * 0.5 / 10 + 1 = 6 > 5 only if everything is accepted
+    eng.run(80)                        # at most 80 accepted moves: floor(80 * 0.5 / 10) + 1 = 5 hills fit
     assert max(eng.n_hills(w) for w in range(M)) <= 5
     with pytest.raises(NdsError, match="hill table full"):
         eng.run(n)

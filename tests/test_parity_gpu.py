@@ -16,7 +16,7 @@ import pytest
 from ndsimulator_b200 import _abi
 from ndsimulator_b200.engine import Engine
 from oracle import oracle
-from tests.helpers import load_golden, spec_from, scaled_err
+from tests.helpers import relerr, load_golden, spec_from, scaled_err
 
 pytestmark = pytest.mark.gpu
 
@@ -108,6 +108,11 @@ def test_one_step_map_10k(integrate, gamma):
     assert scaled_err(st["pe"], fr["pe"][:, 0]) < STEP_TOL
     assert scaled_err(st["f"], fr["f"][:, :, 0].T) < STEP_TOL
     assert scaled_err(st["totale"], fr["totale"][:, 0]) < STEP_TOL
+    # per element, not only against the largest entry of the vector: every component of every state within 1e-10 of
+    # its own magnitude (absolute floor: 1e-3 of the largest entry, where zero crossings of v and f live)
+    for k, ref in (("x", fr["x"][:, :, 0].T), ("v", fr["v"][:, :, 0].T), ("f", fr["f"][:, :, 0].T),
+                   ("pe", fr["pe"][:, 0]), ("totale", fr["totale"][:, 0])):
+        assert relerr(st[k], ref, floor=1e-3) < STEP_TOL, k
 
 
 # ------------------------------------------------------------------ golden deterministic trajectories

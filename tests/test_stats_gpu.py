@@ -225,9 +225,11 @@ def test_committor_fraction_within_binomial_ci():
 
 def test_mtd_fes_matches_oracle_ensemble():
     """Free-energy surface estimate (sum of hills on the 48x40 grid, gaus.py:365-393) of a single-walker
-    well-tempered run, averaged over independent runs: GPU vs oracle within 0.1 kT RMS over the
-    visited region after aligning the additive constant."""
-    R, nsteps = 48, 20000
+    well-tempered run (the parameters of examples/2d-mtd.yaml), averaged over 8192 independent runs on either side:
+    GPU vs oracle within the north star's plain 0.1 kT RMS over the filled region after aligning the additive
+    constant.  8192 runs bring the statistical error of either mean below 0.03 kT (one run scatters by 2.3 kT), so
+    the bar is not met by noise."""
+    R, nsteps = 8192, 20000
     cfg = dict(MD2D, x0=[22.0, 30.0], integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05,
                mtd_sigma=[2.0, 2.0], mtd_dep_freq=100, mtd_biasf=10.0, steps=nsteps, mtd_shared=False)
     spec = spec_from(cfg, n_walkers=R, precision="f64")
@@ -242,18 +244,19 @@ def test_mtd_fes_matches_oracle_ensemble():
     orc.set_state(x0)
     orc.begin()
     orc.run(nsteps)
-    ga = np.mean([eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)], axis=0)
-    gb = np.mean([orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)], axis=0)
+    ga_all = np.array([eng.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)])
+    gb_all = np.array([orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w) for w in range(R)])
+    ga, gb = ga_all.mean(axis=0), gb_all.mean(axis=0)
     kT = kB * 300
     mask = gb > 2 * kT  # region the bias has filled
     assert mask.sum() > 50
     d = (ga - gb)[mask]
     d = d - d.mean()
-    # statistical error of the mean over R runs, estimated from the oracle's own run-to-run spread
-    per_run = np.array([orc.fes_grid(0.0, 1.0, 48, 0.0, 1.0, 40, walker=w)[mask] for w in range(R)])
-    sem = per_run.std(axis=0).mean() / np.sqrt(R)
     rms = np.sqrt((d ** 2).mean())
-    assert rms < max(0.1 * kT, 3 * np.sqrt(2) * sem), (rms / kT, sem / kT)
+    sem_o = gb_all[:, mask].std(axis=0).mean() / np.sqrt(R)
+    sem_g = ga_all[:, mask].std(axis=0).mean() / np.sqrt(R)
+    assert sem_o < 0.035 * kT and sem_g < 0.035 * kT, (sem_o / kT, sem_g / kT)
+    assert rms < 0.1 * kT, (rms / kT, sem_o / kT, sem_g / kT)
 
 
 @pytest.mark.parametrize("precision", ["f64", "f32"])
@@ -286,3 +289,40 @@ def test_six_normals_of_one_call_are_independent_standard_normals(precision):
     assert np.abs(z).max() <= np.sqrt(2 * np.log(2.0 ** 21)) + (1e-9 if precision == "f64" else 1e-3)
     # walkers are independent too: neighbouring walkers (the two lanes of a packed thread)
     assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5 / np.sqrt(3 * M)
+
+
+def test_noise_tails_fp32_ten_billion_draws():
+    """Tail mass of the fp32 step noise over 1.007e10 normals drawn on the device through normals6<float>: counts of
+    |z| > 4, 4.5, 5 follow the exact tail mass of the 21-bit midpoint scheme (tests/helpers.py) within 5 sigma of the
+    Poisson error -- which is the Gaussian tail within 0.3 % / 1 % / 3 % -- nothing lies beyond the documented
+    cut-off sqrt(2 ln 2^22) = 5.52 sigma, and the second and fourth moments are those of N(0, 1)."""
+    from ndsimulator_b200.engine import noise_tail_counts
+    from tests.helpers import fp32_tail_probability
+    thr = [3.0, 4.0, 4.5, 5.0, 5.4, 5.53]
+    counts, st = noise_tail_counts("f32", 987654321, 1 << 20, 1600, thr)
+    n = st["n"]
+    assert n > 1e10
+    for t, c in zip(thr[:5], counts[:5]):
+        want = fp32_tail_probability(t) * n
+        assert abs(c - want) < 5 * np.sqrt(want) + 1e-4 * want, (t, c, want)
+    assert counts[3] == pytest.approx(2 * stats.norm.sf(5.0) * n, rel=0.05)   # the Gaussian itself, 5 sigma
+    assert counts[5] == 0 and 5.3 < st["max"] <= np.sqrt(2 * np.log(2.0 ** 22)) * (1 + 1e-5)
+    assert abs(st["mean"]) < 5 / np.sqrt(n)
+    assert abs(st["m2"] - 1) < 5 * np.sqrt(2 / n) + 2e-6
+    assert abs(st["m4"] - 3) < 5 * np.sqrt(96 / n) + 3e-5
+
+
+def test_noise_tails_fp64_reach_beyond_five_and_a_half_sigma():
+    """The fp64 (parity-precision) engine draws 53-bit radius variates: over 2e9 normals the counts of |z| > 4 ... 5.5
+    are the Gaussian's own within 5 sigma of the Poisson error, and draws beyond 5.52 sigma (impossible with 21-bit
+    fields) do occur."""
+    from ndsimulator_b200.engine import noise_tail_counts
+    thr = [4.0, 4.5, 5.0, 5.5, 6.0]
+    counts, st = noise_tail_counts("f64", 24681357, 1 << 20, 320, thr)
+    n = st["n"]
+    assert n > 2e9
+    for t, c in zip(thr, counts):
+        want = 2 * stats.norm.sf(t) * n
+        assert abs(c - want) < 5 * np.sqrt(want) + 1, (t, c, want)
+    assert counts[3] > 40 and st["max"] > 5.7
+    assert abs(st["mean"]) < 5 / np.sqrt(n) and abs(st["m2"] - 1) < 5 * np.sqrt(2 / n) and abs(st["m4"] - 3) < 5 * np.sqrt(96 / n)
