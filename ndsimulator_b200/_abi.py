@@ -93,7 +93,8 @@ class NdsConfig(C.Structure):
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libndsb200.so")
+# NDSB200_LIB: another build of the same library (kernel experiments under profiles/experiments/); default: in-tree
+LIB_PATH = os.environ.get("NDSB200_LIB") or os.path.join(_HERE, "csrc", "libndsb200.so")
 _lib = None
 
 _dp = C.POINTER(C.c_double)

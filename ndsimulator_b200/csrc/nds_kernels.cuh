@@ -312,7 +312,10 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
     // the step counter stays warp-uniform: a stopped walker idles its lane until the whole warp is done
     if (committor && !__any_sync(0xffffffffu, PACK == 1 ? alive : (a0 || a1))) break;
     R zb[G * NN > 0 ? G * NN : 1];
-    if (NN > 0 && !ext_noise) {
+    // several Philox calls per group (2nd-order Langevin): draw them step by step, right before the step that needs
+    // them -- at most NN + NDS_NPC - 1 normals are live instead of G * NN (C4: 90 -> 64 registers, +3 %)
+    constexpr bool LAZY = PACK == 1 && NN > NDS_NPC / 2 && G > 1;
+    if (NN > 0 && !ext_noise && !LAZY) {
 #pragma unroll
       for (int c = 0; c < CG; c++) {
         R z6[NDS_NPC];
@@ -325,6 +328,19 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
     }
 #pragma unroll
     for (int i = 0; i < G; i++) {
+      if constexpr (LAZY) {
+        // the calls that complete the normals of step i: keeps at most NN + NDS_NPC - 1 normals live instead of G * NN
+        if (!ext_noise) {
+#pragma unroll
+          for (int c = (i * NN + NDS_NPC - 1) / NDS_NPC; c < ((i + 1) * NN + NDS_NPC - 1) / NDS_NPC; c++) {
+            R z6[NDS_NPC];
+            normals6_pair<R>(K.rk_step, (unsigned long long)(grp * CG + c), gid, gid_b, z6);
+#pragma unroll
+            for (int j = 0; j < NDS_NPC; j++)
+              if (NDS_NPC * c + j < G * NN) zb[NDS_NPC * c + j] = z6[j];
+          }
+        }
+      }
       if (i >= first && left > 0) {
         long long s = s_end - left;  // NDRun.step before this update
        if (alive) {

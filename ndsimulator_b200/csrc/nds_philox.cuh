@@ -79,20 +79,20 @@ constexpr int NDS_NPC = 6;  // normals per Philox call
 // Two standard normals from two 21-bit fields (Box-Muller).
 // fp32: u1 in (0,1] feeds lg2.approx / sqrt.approx, the angle uses sin/cos.approx (MUFU pipe);
 // fp64: full-precision log / sqrt / sincospi on the same 21-bit uniforms.
-// Radius constants: r^2 = ra * lg2(n) + rb with (ra, rb) = (-2 ln2, 42 ln2) * scale^2; scale = 1 gives
+// Radius constants: r^2 = ra * lg2(2a + 1) + rb with (ra, rb) = (-2 ln2, 44 ln2) * scale^2; scale = 1 gives
 // standard normals, scale = c2 gives the noise term c2 * xi of the Langevin kick without a multiply.
 struct BmScale { float ra, rb; };
 __host__ __device__ inline BmScale bm_scale(double scale) {
-  return BmScale{(float)(-1.3862943611198906 * scale * scale), (float)(29.112181583517703 * scale * scale)};
+  return BmScale{(float)(-1.3862943611198906 * scale * scale), (float)(30.498475944637594 * scale * scale)};
 }
 
 __device__ __forceinline__ void box_muller21(uint32_t a, uint32_t b, float& z0, float& z1,
-                                             BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
-  // u1 = n * 2^-21 with n = a + 1/2 in (0, 2^21)  (never 0; midpoint of the cell):
-  //   r^2 = -2 ln u1 = -2 ln2 * (lg2 n - 21)  -> one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
-  // angle = 2 pi * b * 2^-21                   -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
-  const float n = (float)a + 0.5f;  // exact: 22 significant bits
-  // |.|: near n = 2^21 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
+                                             BmScale k = BmScale{-1.3862943611198906f, 30.498475944637594f}) {
+  // u1 = (a + 1/2) 2^-21 = (2a + 1) 2^-22 (never 0; midpoint of the cell):
+  //   r^2 = -2 ln u1 = -2 ln2 * (lg2 (2a + 1) - 22)  -> one integer op, one I2F, one MUFU.LG2, one FFMA, one MUFU.SQRT
+  // angle = 2 pi * b * 2^-21                          -> one I2F, one FMUL, MUFU.SIN + MUFU.COS
+  const float n = (float)((a << 1) | 1u);  // exact: 22 significant bits
+  // |.|: near n = 2^22 the FFMA may round to -1e-7; the absolute value is a free MUFU operand modifier
   const float r = sqrt_approx(fabsf(fmaf(lg2_approx(n), k.ra, k.rb)));
   const float ang = (float)b * 2.9960562263391724e-06f;  // 2 pi 2^-21
   z0 = r * cos_approx(ang);
@@ -117,7 +117,7 @@ __device__ __forceinline__ void box_muller53(uint32_t a, uint32_t ea, uint32_t b
 template <typename R>
 __device__ __forceinline__ void normals6(const PhiloxKeys& rk, unsigned long long call,
                                          unsigned long long walker, R (&z)[NDS_NPC],
-                                         BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
+                                         BmScale k = BmScale{-1.3862943611198906f, 30.498475944637594f}) {
   const u32x4 r = philox4x32_10(
       u32x4{(uint32_t)call, (uint32_t)(call >> 32), (uint32_t)walker, (uint32_t)(walker >> 32)}, rk);
   box_muller21(r.x >> 11, r.y >> 11, z[0], z[1], k);
@@ -141,7 +141,7 @@ __device__ __forceinline__ void normals6<double>(const PhiloxKeys& rk, unsigned 
 template <typename R>
 __device__ __forceinline__ void normals6_pair(const PhiloxKeys& rk, unsigned long long call,
                                               unsigned long long walker, unsigned long long, R (&z)[NDS_NPC],
-                                              BmScale k = BmScale{-1.3862943611198906f, 29.112181583517703f}) {
+                                              BmScale k = BmScale{-1.3862943611198906f, 30.498475944637594f}) {
   normals6<R>(rk, call, walker, z, k);
 }
 template <>
