@@ -404,8 +404,6 @@ def parse(config: dict) -> RunSpec:
             raise UnboundLocalError(f"unknown bias {b}")  # bias/__init__.py:40 would fail on `instance`
 
     if method in ("mc", "wl-mc"):
-        if "mtd" in biases and method == "wl-mc":
-            raise NotImplementedError("metadynamics under Wang-Landau MC is not supported")
         cfg["dump"] = False  # the reference dumps only on accepted moves (ndrun.py:234-251): not recorded
 
     # ---- committor (engines/committor.py:31-75)

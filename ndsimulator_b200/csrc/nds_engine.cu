@@ -209,7 +209,6 @@ static int validate(const nds_config* c) {
     return fail(nullptr, "integrate=rescale needs rescale_freq > 0");
   if (c->method < NDS_METHOD_MD || c->method > NDS_METHOD_WL) return fail(nullptr, "unknown method %d", c->method);
   if (c->method == NDS_METHOD_MC || c->method == NDS_METHOD_WL) {
-    if (c->mtd_enabled && c->method == NDS_METHOD_WL) return fail(nullptr, "metadynamics under Wang-Landau MC is not supported");
     if (c->mtd_enabled && c->mtd_shared)  // ndrun.py:234-237: time (hence the deposition schedule) is per walker
       return fail(nullptr, "metadynamics under MC needs mtd_shared = 0: NDRun.time advances on accepted moves only, "
                            "so every walker deposits on its own clock");

@@ -472,6 +472,10 @@ def mc_runs():
                                  bounds=[2.0, 2.0], global_bounds=[48.0, 40.0], temperature=300, dump=False,
                                  screen=False, root=TMP, run_name="g", steps=400, seed=4,
                                  plot_boundary=[[0.0, 48.0], [0.0, 40.0]])
+    # metadynamics under Wang-Landau: fix.update deposits on the accepted-move clock, the acceptance compares
+    # pe + biase bins (wang_landau.py:98-126 with fix.energy, gaus.py:296-363)
+    cases["wl_single_2d_mtd"] = dict(cases["wl_single_2d"], biases=["mtd"], mtd_w=0.02, mtd_sigma=[1.5, 1.5],
+                                     mtd_dep_freq=10, mtd_biasf=8.0, dt=0.5, seed=6)
     for name, cfg in cases.items():
         global_seed = 1000 + len(out)
         sim = unshadow(ref_stub.make_run(cfg))

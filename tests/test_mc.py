@@ -27,8 +27,8 @@ def test_config_mc():
         config.parse(dict(M2, mc_bounds=[1.0]))  # mc.py:31-32
     m = config.parse(dict(M2, biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0, steps=100)).to_struct()
     assert m.mtd_enabled == 1 and m.method == _abi.NDS_METHOD_MC
-    with pytest.raises(NotImplementedError):
-        config.parse(dict(M2, method="wl-mc", biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0))
+    wl = config.parse(dict(M2, method="wl-mc", biases=["mtd"], mtd_w=0.1, mtd_sigma=[1.0, 1.0], mtd_biasf=5.0))
+    assert wl.to_struct().method == _abi.NDS_METHOD_WL and wl.mtd_shared is False  # per-walker deposition clocks
 
 
 def test_oracle_mc_samples_boltzmann():
@@ -345,7 +345,7 @@ def test_gpu_mc_metadynamics_full_table_fails_loudly():
         eng.run(n)
 
 
-MC_CASES = ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo", "wl_single_2d"]
+MC_CASES = ["single_2d", "all_2d_umb", "single_2d_mtd", "single_2d_mtd_adapsig_geo", "wl_single_2d", "wl_single_2d_mtd"]
 
 
 @pytest.mark.parametrize("name", MC_CASES)
