@@ -350,6 +350,12 @@ NDS_API int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap);
 NDS_API int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n);
 NDS_API int64_t nds_mtd_grid_outside(nds_engine* e);
 
+/* Harmonic.VR of every restraint as of the last refresh, [n_umb][n_walkers] (umb.py:32-33; refreshed by begin() and by
+ * every deposition, gaus.py:138-146).  Kept only when umbrella AND metadynamics biases record frames (it feeds the
+ * fix_VR column of thermo.dat); *n = 0 otherwise.  For checkpoints.                                          */
+NDS_API int nds_get_umb_vr(nds_engine* e, double* vr, int64_t cap, int64_t* n);
+NDS_API int nds_set_umb_vr(nds_engine* e, const double* vr, int64_t n);
+
 /* mtd_adapsig_hist: the colvar history window of every walker (Stat.colv, io/stat.py:70-72), for checkpoints:
  * ring[(j % window) * n_walkers + w] = sample j of walker w, *n_samples = len(stat.colv).  ring may be NULL to
  * query the sizes only.                                                                                    */

@@ -127,6 +127,9 @@ struct BlockArgs {
   // Stat.colv ring (BIAS_CVHIST): sample j of walker w lives at cvhist[(j % cvhist_cap) * M + w]; cvhist_n samples
   // exist at launch entry
   R* cvhist; long long cvhist_n; int cvhist_cap;
+  // Harmonic.VR of every restraint [n_umb][M], refreshed where Gaussian.update recomputes every fix (gaus.py:138-146)
+  // and by begin(); null unless umbrella AND metadynamics biases are present and frames are recorded
+  R* vr_umb;
 };
 
 }  // namespace nds

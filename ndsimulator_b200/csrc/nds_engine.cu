@@ -76,6 +76,8 @@ struct nds_engine {
   virtual int get_mtd_grid(double* out, int64_t cap) = 0;
   virtual int set_mtd_grid(const double* in, int64_t n) = 0;
   virtual int64_t mtd_grid_outside() = 0;
+  virtual int get_umb_vr(double* vr, int64_t cap, int64_t* n) = 0;
+  virtual int set_umb_vr(const double* vr, int64_t n) = 0;
   virtual int get_cv_history(double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) = 0;
   virtual int set_cv_history(const double* ring, int64_t n_samples) = 0;
   virtual int submit(const void* host_in, int64_t nsteps, void* host_out, int chunks) = 0;
@@ -670,6 +672,7 @@ struct Engine : nds_engine {
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
   R* d_gpart = nullptr;                    // partial sums of the record slices of one accumulation [16][grid]
+  R* d_vr_umb = nullptr;                   // Harmonic.VR per restraint [n_umb][M] (umbrella + metadynamics with frames)
   R* d_cvhist = nullptr;                   // Stat.colv ring [tao_d][M] (mtd_adapsig_hist)
   int64_t cv_n = 0;                        // samples taken so far (len(stat.colv))
   int tao_d = 0;
@@ -700,7 +703,7 @@ struct Engine : nds_engine {
   ~Engine() override {
     cudaSetDevice(cfg.device);
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
-    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_cvhist, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
@@ -890,6 +893,12 @@ struct Engine : nds_engine {
     }
     CU(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     frame_width = 2 + 3 * nd + cd + 6;
+    if (frames_on && c.mtd_enabled && c.n_umb > 0 && c.method == NDS_METHOD_MD) {
+      // Gaussian.update recomputes EVERY fix after a deposition (gaus.py:138-146): Harmonic.VR follows, one frame field each
+      CU(cudaMalloc(&d_vr_umb, sizeof(R) * (size_t)c.n_umb * (size_t)M));
+      CU(cudaMemsetAsync(d_vr_umb, 0, sizeof(R) * (size_t)c.n_umb * (size_t)M, stream));
+      frame_width += c.n_umb;
+    }
     if (frames_on) {
       const size_t n = (size_t)c.dump_capacity * frame_width * (size_t)K.dump_walkers;
       CU(cudaMalloc(&d_frames, sizeof(R) * n));
@@ -1071,6 +1080,7 @@ struct Engine : nds_engine {
     A.frame_width = frame_width;
     A.hist = d_hist; A.hist_smem_off = hist_smem_off; A.dyn_smem = dyn_smem;
     A.cvhist = d_cvhist; A.cvhist_n = cv_n; A.cvhist_cap = tao_d;
+    A.vr_umb = d_vr_umb;
     return A;
   }
 
@@ -1437,6 +1447,21 @@ struct Engine : nds_engine {
   int set_vr(const double* vr) override {
     CU(cudaSetDevice(cfg.device));
     return upload(vr, d_vr, M);
+  }
+  // Harmonic.VR of every restraint, [n_umb][M] (kept only when umbrella + metadynamics record frames): checkpoints
+  int get_umb_vr(double* vr, int64_t cap, int64_t* n) override {
+    CU(cudaSetDevice(cfg.device));
+    const int64_t want = d_vr_umb ? (int64_t)cfg.n_umb * M : 0;
+    if (n) *n = want;
+    if (!vr || want == 0) return 0;
+    if (cap < want) return fail(this, "nds_get_umb_vr: buffer of %lld < %lld elements", (long long)cap, (long long)want);
+    return download(d_vr_umb, vr, want);
+  }
+  int set_umb_vr(const double* vr, int64_t n) override {
+    CU(cudaSetDevice(cfg.device));
+    if (!d_vr_umb) return fail(this, "nds_set_umb_vr: this engine keeps no umbrella VR (needs umb + mtd biases and frames)");
+    if (n != (int64_t)cfg.n_umb * M) return fail(this, "nds_set_umb_vr: expected %lld elements", (long long)cfg.n_umb * M);
+    return upload(vr, d_vr_umb, n);
   }
   int64_t count_nonfinite() override {
     cudaSetDevice(cfg.device);
@@ -2348,6 +2373,8 @@ int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum) {
 int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap) { return e->get_mtd_grid(out, cap); }
 int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n) { return e->set_mtd_grid(in, n); }
 int64_t nds_mtd_grid_outside(nds_engine* e) { return e->mtd_grid_outside(); }
+int nds_get_umb_vr(nds_engine* e, double* vr, int64_t cap, int64_t* n) { return e->get_umb_vr(vr, cap, n); }
+int nds_set_umb_vr(nds_engine* e, const double* vr, int64_t n) { return e->set_umb_vr(vr, n); }
 int nds_get_cv_history(nds_engine* e, double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) {
   return e->get_cv_history(ring, cap_elems, n_samples, window);
 }

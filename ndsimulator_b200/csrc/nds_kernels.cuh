@@ -152,6 +152,10 @@ NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w,
   row[(r++) * st] = o.be;
   row[(r++) * st] = begin_mode ? (ke + o.pe) : (o.pe + ke + o.be);
   row[(r++) * st] = (bias_mask & BIAS_MTD) ? A.vr[w] : (R)0;
+  if constexpr (pack_of<R>::value == 1) {
+    if (A.vr_umb)  // one more field per harmonic restraint: its VR as of the last refresh
+      for (int u = 0; u < K.n_umb; u++) row[(r++) * st] = A.vr_umb[u * A.M + w];
+  }
 }
 
 // in-kernel colvar histogram at dump cadence (io/plot.py:562-572 accumulated over the run): shared-memory bins
@@ -266,6 +270,25 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   Eval<R, ND> e;
   eval_all<R, ND, INTEG == NDS_INT_MINIMIZE>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
   if (A.refresh_vr && (bias_mask & BIAS_MTD)) A.vr[w] = e.vm;  // Gaussian.VR, gaus.py:292-293
+  if constexpr (PACK == 1 && (S::BIAS < 0 || ((S::BIAS & BIAS_UMB) != 0 && (S::BIAS & BIAS_MTD) != 0))) {
+    // Harmonic.VR: the no-argument fix.compute() of Gaussian.update / MD.begin refreshes it too (umb.py:32-33)
+    if (A.refresh_vr && A.vr_umb) {
+#pragma unroll
+      for (int u = 0; u < NDS_MAX_UMB; u++) {
+        if (u >= K.n_umb) break;
+        R en = (R)0;
+#pragma unroll
+        for (int k = 0; k < ND; k++)
+          if (k < cd) {
+            const bool pw = (bias_mask & BIAS_UMB_WALKER) && u == 0;
+            const R kk = pw ? wb.k[k] : K.umb_k[u][k];
+            const R dR = e.cv.c[k] - (pw ? wb.r0[k] : K.umb_r0[u][k]);
+            en += kk * (dR * dR);
+          }
+        A.vr_umb[u * M + w] = (R)0.5 * en;
+      }
+    }
+  }
   R f[ND];
 #pragma unroll
   for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];  // md.py:133

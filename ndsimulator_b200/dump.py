@@ -92,11 +92,16 @@ class DumpWriter:
                     b_txt = "0" if not spec.biases else _fmt(lag[idx["biase"], w])
                     line = " ".join([t_txt, _fmt(spec.dt), _fmt(lag[idx["T"], w]), _fmt(lag[idx["pe"], w]),
                                      _fmt(lag[idx["ke"], w]), b_txt, _fmt(lag[idx["totale"], w])])
+                    n_umb_seen = 0
                     for name in self.fix_names:  # dump.py:98: current fix.VR of every bias
                         if name == "mtd":
                             line += f" {_fmt(fr[idx['VR'], w])}"
                         elif name == "umb":
-                            line += f" {_fmt(self.umb_vr[w]) if self.umb_vr is not None else 0.0}"
+                            if f"VRu{n_umb_seen}" in idx:  # refreshed by every deposition (gaus.py:138-146)
+                                line += f" {_fmt(fr[idx[f'VRu{n_umb_seen}'], w])}"
+                            else:                          # umbrella only: Harmonic.VR stays at its begin() value
+                                line += f" {_fmt(self.umb_vr[w]) if self.umb_vr is not None else 0.0}"
+                            n_umb_seen += 1
                         else:
                             line += " 0"
                     f["thermo"].write(line + "\n")

@@ -304,6 +304,12 @@ class Engine:
             ck["vr"] = self.get_vr()
             if self.cfg.mtd_adapsig_hist:
                 ck["cv_history"], ck["cv_history_n"] = self.get_cv_history()
+            n = C.c_int64()
+            self._check(self.lib.nds_get_umb_vr(self.h, None, 0, C.byref(n)))
+            if n.value:  # Harmonic.VR as of the last deposition (umbrella + metadynamics with frames)
+                uv = np.empty(n.value)
+                self._check(self.lib.nds_get_umb_vr(self.h, _p(uv), uv.size, C.byref(n)))
+                ck["umb_vr"] = uv
         return ck
 
     def restore(self, ck):
@@ -318,6 +324,9 @@ class Engine:
             if "mtd_grid" in ck:
                 self.set_mtd_grid(ck["mtd_grid"])
             self.set_vr(ck["vr"])
+        if "umb_vr" in ck:
+            uv = _f64(ck["umb_vr"]).reshape(-1)
+            self._check(self.lib.nds_set_umb_vr(self.h, _p(uv), uv.size))
         if "cv_history" in ck:  # after begin(), which appended a sample of its own
             self.set_cv_history(ck["cv_history"], int(ck["cv_history_n"]))
         if "alive" in ck:
@@ -398,6 +407,8 @@ class Engine:
         names = ["step", "time"] + [f"x{d}" for d in range(nd)] + [f"v{d}" for d in range(nd)] + \
                 [f"f{d}" for d in range(nd)] + [f"c{k}" for k in range(cd)] + \
                 ["T", "pe", "ke", "biase", "totale", "VR"]
+        # umbrella + metadynamics: Harmonic.VR of every restraint as of the last refresh (gaus.py:138-146)
+        names += [f"VRu{u}" for u in range(self.frame_width - len(names))]
         return names
 
     # ---- plumbing / introspection

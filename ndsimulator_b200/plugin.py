@@ -104,8 +104,11 @@ class B200Engine:
         a.fixf = ev["Fb"][:, 0].copy()
         np.copyto(a.colv, np.reshape(ev["colv"][:, 0], np.shape(a.colv)))  # keeps the (1, 1) shape of two.py (A28)
         a.totale = a.ke + a.pe + a.biase
-        if len(self.fixes) == 1 and self.fixes[0].kind == "umb":
-            self.fixes[0].VR = a.biase  # Harmonic.VR after the no-argument compute of MD.begin (umb.py:32-33)
+        umb = [fx for fx in self.fixes if fx.kind == "umb"]
+        if len(umb) == 1:  # Harmonic.VR after the no-argument compute of MD.begin (umb.py:32-33); hills: none yet
+            k = np.asarray(self.spec.umb_k[0], dtype=float).reshape(-1)
+            r0 = np.asarray(self.spec.umb_r0[0], dtype=float).reshape(-1)
+            umb[0].VR = float(0.5 * np.sum(k * (ev["colv"][:, 0] - r0) ** 2))
         self.started = False
 
     def hills_at(self, step):
@@ -153,7 +156,12 @@ class B200Engine:
         a.pe, a.ke, a.T = float(f[ix["pe"]]), float(f[ix["ke"]]), float(f[ix["T"]])
         a.biase = float(f[ix["biase"]]) if self.spec.biases else 0
         a.totale = float(f[ix["totale"]])
+        n_umb = 0
         for fx in self.fixes:
+            if fx.kind == "umb":  # refreshed by every deposition when a metadynamics bias is present (gaus.py:138-146)
+                if f"VRu{n_umb}" in ix:
+                    fx.VR = float(f[ix[f"VRu{n_umb}"]])
+                n_umb += 1
             if fx.kind == "mtd":
                 fx.VR = float(f[ix["VR"]])
         self.current_dt = self.spec.dt

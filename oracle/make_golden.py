@@ -432,6 +432,13 @@ def dump_files():
                                                mtd_adapsig=True, mtd_adapsig_geo=True, dump=True, dump_freq=50,
                                                screen=False),
     }
+    # umbrella + metadynamics: Gaussian.update recomputes every fix after a deposition (gaus.py:138-146), so the
+    # fix_VR column of the umbrella changes at the deposition steps only
+    cases["2d_umb_mtd_gamma0_dump20"] = dict(ndim=2, mass=1.0, potential="Mueller2d", x0=[22.0, 30.0], method="md",
+                                             integrate="langevin", gamma=0.0, temperature=300, dt=1.0, seed=3,
+                                             steps=160, biases=["umb", "mtd"], umb_k=0.02, umb_r0=[20, 28], mtd_w=0.05,
+                                             mtd_sigma=[2.0, 2.0], mtd_dep_freq=50, mtd_biasf=10.0, dump=True,
+                                             dump_freq=20, screen=False)
     for name, cfg in cases.items():
         d = tempfile.mkdtemp()
         sim = ref_stub.make_run(dict(cfg, root=d, run_name="r"))

@@ -31,7 +31,8 @@ def assert_same_text(got, want, rtol=1e-9, what=""):
 
 
 @pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve",
-                                  "2d_mtd_adapsig_geo_xmy_gamma0", "2d_md_yaml_langevin_dump10"])
+                                  "2d_mtd_adapsig_geo_xmy_gamma0", "2d_md_yaml_langevin_dump10",
+                                  "2d_umb_mtd_gamma0_dump20"])
 def test_dump_files_match_reference(name, tmp_path):
     """pos/force/velocity/colvar/thermo/fix*.dat against the files the Python reference wrote
     (tests/golden/dump_files.json), including the lagged thermo row (A16).  The stochastic case (examples/2d-md.yaml
@@ -61,7 +62,8 @@ def test_dump_files_match_reference(name, tmp_path):
 
 
 @pytest.mark.parametrize("name,stop", [("2d_mtd_gamma0_dump100", 150), ("2d_mtd_gamma0_dump100", 200),
-                                       ("5d_umb_nve_stat10", 30), ("2d_mtd_adapsig_geo_xmy_gamma0", 70)])
+                                       ("5d_umb_nve_stat10", 30), ("2d_mtd_adapsig_geo_xmy_gamma0", 70),
+                                       ("2d_umb_mtd_gamma0_dump20", 70)])
 def test_dump_files_after_checkpoint_resume(name, stop, tmp_path):
     """Stop at `stop`, save, load into a fresh NDRun (which appends to the files), finish: the dump files are still
     the reference's -- no duplicate step-0 row, the hill listing of fix{i}.dat and the lagged thermo sample survive."""

@@ -38,7 +38,7 @@ def ref_stub():
 
 
 @pytest.mark.parametrize("name", ["2d_nve_dump10", "2d_mtd_gamma0_dump100", "5d_umb_nve_stat10", "2d_xmy_nve",
-                                  "2d_mtd_adapsig_geo_xmy_gamma0"])
+                                  "2d_mtd_adapsig_geo_xmy_gamma0", "2d_umb_mtd_gamma0_dump20"])
 @pytest.mark.parametrize("block", [7, 256])
 def test_reference_ndrun_with_b200_engine_writes_the_reference_files(ref_stub, name, block, tmp_path):
     rec = load_golden("dump_files.json")[name]
