@@ -283,9 +283,10 @@ class PythonReference:
 def python_reference_baseline(name, target_seconds=10.0):
     ref = PythonReference(name)
     try:
-        n, dt = ref.step(200)
-        per = max(200, int(200 * target_seconds / max(dt, 1e-3)))
-        per = min(per, 60000)   # stay below Stat.mem = 10^5 samples
+        ref.step(200)               # imports, first-call overheads
+        n, dt = ref.step(2000)      # rate estimate
+        per = max(2000, int(2000 * target_seconds / max(dt, 1e-3)))
+        per = min(per, 60000)       # stay below Stat.mem = 10^5 samples in total
         n, dt = ref.step(per)
     finally:
         ref.close()
