@@ -162,7 +162,9 @@ NDS_DEV void write_frame(const Consts<R>& K, const BlockArgs<R>& A, long long w,
 NDS_DEV void hist_count(unsigned int* bins, float c0, float c1, float lo0, float inv0, int nx, float lo1, float inv1, int ny) {
   // floor to int, then ONE unsigned compare per axis rejects both sides of the box (negative indices wrap high)
   const int i = __float2int_rd((c0 - lo0) * inv0), j = __float2int_rd((c1 - lo1) * inv1);
-  if ((unsigned)i < (unsigned)nx && (unsigned)j < (unsigned)ny) atomicAdd(&bins[j * nx + i], 1u);
+  const int bin = ((unsigned)i < (unsigned)nx && (unsigned)j < (unsigned)ny) ? j * nx + i : -1;
+  // (one atomic per distinct bin of the warp through __match_any_sync was measured SLOWER: 3.00 vs 2.92 ms)
+  if (bin >= 0) atomicAdd(&bins[bin], 1u);
 }
 
 // resident CTAs per SM asked of ptxas (register cap): the packed committor kernel is held to 64 registers
@@ -315,8 +317,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
     rd = (int)(A.step0 % K.dump_freq);
     rs = K.stat_freq > 0 ? (int)(A.step0 % K.stat_freq) : 0;
   }
-  // value of `left` right after the next dump step (hist-only kernels): steps to the next multiple of dump_freq
-  int hist_left = any_frames ? (int)A.nsteps - (dfreq - rd) : -1;
+  int to_hist = any_frames ? dfreq - rd : 0x7fffffff;  // executed steps until the next dump step (hist-only kernels)
   bool alive = true;
   int basin = -1;
   long long cv_taken = 0;  // Stat.colv samples written by this launch (BIAS_CVHIST)
@@ -522,8 +523,10 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
         } else {
           if constexpr (S::DUMP == 2) {
             // histogram only: one compare per step against the value `left` has at the next dump step
-            if (left == hist_left) {
-              hist_left -= dfreq;
+            // warp-uniform countdown, updated by a select (not inside the branch) so that it stays on the uniform datapath
+            const bool hist_now = to_hist == 1;
+            to_hist = hist_now ? dfreq : to_hist - 1;
+            if (hist_now) {
               hist_count(hist_bins, e.cv.c[0].v.x, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.x : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],
                          K.hist_nx, K.hist_lo[1], K.hist_inv[1], K.hist_ny);
               hist_count(hist_bins, e.cv.c[0].v.y, cd > 1 ? e.cv.c[ND > 1 ? 1 : 0].v.y : K.hist_lo[1], K.hist_lo[0], K.hist_inv[0],

@@ -1078,3 +1078,27 @@ def test_walker_results_do_not_depend_on_ensemble_size():
             continue
         for k in ("x", "v", "pe", "T"):
             assert scaled_err(st[k], ref[k][..., :M]) < 2e-5, (M, k)
+
+
+def test_second_begin_keeps_hills_and_deposition_count():
+    """NDRun.begin() restarts step and time only (ndrun.py:199-200): Gaussian._history and _dep_count survive, so after
+    a second begin() nothing is deposited until the restarted clock passes the old count.  Engine and oracle agree."""
+    M = 4
+    cfg = dict(MD2D, integrate="langevin", gamma=0.1, biases=["mtd"], mtd_w=0.05, mtd_sigma=[2.0, 2.0], mtd_dep_freq=50,
+               mtd_biasf=10.0, steps=600, mtd_shared=False)
+    spec, eng, orc = make_pair(cfg, M=M, noise_mode=_abi.NDS_NOISE_EXTERNAL, steps_per_launch=64)
+    noise = noise_table(5, 300, 2, M)
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1)
+    for sim in (eng, orc):
+        sim.set_state(x0, np.zeros((2, M)))
+        sim.set_noise(noise)
+        sim.begin()
+        sim.run(170)            # hills at t = 0, 50, 100, 150
+        sim.begin()
+        sim.run(300)            # dep_count = 4: the next hill comes at t = 200 of the restarted clock, then 250
+    (ce, we), (co, wo) = eng.get_hills(0), orc.get_hills(0)
+    assert len(we) == len(wo) == 6
+    assert np.allclose(we, wo, rtol=1e-9) and np.allclose(ce, co, rtol=1e-9)
+    a, b = eng.get_state(), orc.get_state()
+    for k in ("x", "v", "biase"):
+        assert scaled_err(a[k], b[k]) < TRAJ_TOL, k
