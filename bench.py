@@ -44,6 +44,14 @@ FLOPS_PER_WALKER_STEP = {"c2": 128.0, "c2_nodump": 128.0, "c3": 128.0, "c4": 289
 # C5 with mtd_grid: colvar 19 + Mueller 92 + chain rule 5 + Langevin 60 + Box-Muller 36 (= the 212 of section 8d)
 # + bicubic Hermite interpolation: 2 x 8 basis ops + 2 x 4 x 7 column contractions + 3 x 7 row contractions + 4
 GRID_FLOPS_PER_WALKER_STEP = 212.0 + 97.0
+# Issue-slot model: issue cycles per 32 walker-steps per SM sub-partition that the executed
+# instruction mix needs when an IMAD.WIDE holds the issue port for 4.1 cycles and a packed FP32 instruction for 2.05
+# (profiles/microbench/pipes_b200.txt).  The mixes come from the ncu source pages named here (profiles/opmix.py);
+# they describe the kernels of this commit and have to be re-measured when a kernel changes.
+ISSUE_MODEL = {
+    "c2_nodump": (101.6, "profiles/r02_c2_nodump_raw.csv + source page: 58.9 instr, 6.0 IMAD.WIDE, 23.0 packed FP"),
+    "c4": (369.6, "profiles/r02_c4_raw.csv + source page: 276.4 instr, 30.1 IMAD.WIDE"),
+}
 L2_FLUSH_BYTES = 256 << 20
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
@@ -519,6 +527,11 @@ def bench_md(ctx, name, M, steps, warmup, precision="f32", sampler=None):
                     f"GPU; peak = {ctx.sm_count} SMs x 128 lanes x 2 x {ctx.sm_max_mhz:.0f} MHz (clocks.max.sm; "
                     "MEASURED_PEAKS.json holds no FP32 figure). HBM traffic is negligible (state is "
                     "register-resident for the whole launch)."}
+        if name in ISSUE_MODEL:
+            model, src = ISSUE_MODEL[name]
+            measured = 4 * ctx.sm_count * ctx.sm_max_mhz * 1e6 * 32.0 / per_gpu  # cycles per 32 walker-steps per SMSP
+            rec["roofline"]["issue_slots"] = {"model_cycles_per_32_walker_steps": model, "measured_cycles": measured,
+                                              "frac": model / measured, "source": src}
     return rec, eng, spec, cfg
 
 
