@@ -112,7 +112,7 @@ __global__ void grid_reduce_kernel(long long n_pts4, int n_slices, const R* __re
   for (int s2 = 0; s2 < n_slices; s2++) v += part[(long long)s2 * n_pts4 + p];
   if (add) { grid[p] += v; return; }
   for (int r = 0; r < ndst; r++) dst[r][p] = v;
-  if (ndst > 1) __threadfence_system();  // peer slots: visible before the barrier kernel signals
+  if (ndst > 1) __threadfence_system();  // peer slots: visible before the barrier kernel signals (measured: 2 us of a 109 us stride)
 }
 
 // grid += sum of nsrc increment buffers, in the given (rank) order: every rank ends with bit-identical grids
