@@ -780,7 +780,7 @@ __global__ void hill_variance_hist_kernel(const __grid_constant__ Consts<R> K, l
   R avg = (R)0;
   for (long long j = j0; j < j1; j++) avg += ring[(j % cap) * M + w];
   avg /= (R)n0;  // np.average(colv, axis=0)
-  R mind = (R)1e300 < (R)3e38 ? (R)1e300 : (R)3e38, acc = (R)0;
+  R mind = (R)3e38, acc = (R)0;
   for (int i = 0; i < n0; i++) {
     const R d = ring[((j0 + i) % cap) * M + w] - avg;
     const R ad = d < (R)0 ? -d : d;

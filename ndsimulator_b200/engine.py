@@ -313,6 +313,9 @@ class Engine:
         return ck
 
     def restore(self, ck):
+        """Continue from :meth:`checkpoint`.  Runs ``begin()`` first (forces, constants), so an engine that records
+        frames holds ONE pending frame labelled step 0 afterwards: callers that write dump files drop it with
+        :meth:`discard_frames` (``NDRun.load_checkpoint`` does)."""
         self.set_state(ck["x"], ck["v"])
         self.begin()
         if "hills_raw" in ck:
