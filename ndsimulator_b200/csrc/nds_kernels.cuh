@@ -101,11 +101,22 @@ struct Eval {
   R fp[ND], fb[ND];
 };
 
-template <typename R, int ND, bool ENERGY>
+// PREFETCH (kernels whose bias mask is the grid-accumulated metadynamics bias at compile time): the four grid nodes
+// are requested as soon as the colvar is known, the potential is evaluated while they travel from L2 / shared memory
+template <typename R, int ND, bool ENERGY, bool PREFETCH = false>
 NDS_DEV void eval_all(const Consts<R>& K, int pot, int cv, int tcv, int cd, int bias_mask,
                       const R (&x)[ND], const WalkerBias<R, ND>& wb, const R* hills, long long n_hills,
                       long long elem_stride, Eval<R, ND>& e, const GridView<R> gv = GridView<R>{nullptr, 0, nullptr}) {
   cv_eval<R, ND>(K, cv, K.rot, x, e.cv);
+  if constexpr (PREFETCH) {
+    GridFetch<R> gf;
+    if (gv.smem) grid_fetch<R, ND, true>(K, cd, gv.grid, e.cv.c, gf, gv.outside);
+    else grid_fetch<R, ND, false>(K, cd, gv.grid, e.cv.c, gf, gv.outside);
+    if (ENERGY || (bias_mask & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
+    else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
+    bias_eval<R, ND>(K, bias_mask, cv, cd, x, e.cv, wb, hills, n_hills, elem_stride, e.pe, e.fp, e.be, e.fb, e.vm, gv, &gf);
+    return;
+  }
   // PE bias needs the potential energy even when the caller does not
   if (ENERGY || (bias_mask & BIAS_PE)) pot_eval<R, ND, true>(K, pot, tcv, x, e.pe, e.fp);
   else pot_eval<R, ND, false>(K, pot, tcv, x, e.pe, e.fp);
@@ -194,6 +205,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
   // fp32 first-order Langevin: the noise enters only as c2 * xi (md.py:170,196), so the Box-Muller radius is
   // generated already multiplied by c2 and xi[] below holds c2 * xi
   constexpr bool PRESCALED = is_f32<R>::value && INTEG == NDS_INT_LANGEVIN;
+  constexpr bool PF = PACK == 1 && S::BIAS >= 0 && (S::BIAS & BIAS_MTD_GRID) != 0;  // grid nodes prefetched in eval_all
 
   const long long w = A.slot0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot
   const long long M = A.M;
@@ -441,7 +453,7 @@ NDS_DEV void md_body(const Consts<typename S::R>& K, const BlockArgs<typename S:
           x[d] = x[d] + dx;
         }
         // ---- colvar, potential and biases at the new positions, md.py:179-188
-        eval_all<R, ND, false>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
+        eval_all<R, ND, false, PF>(K, pot, cv, tcv, cd, bias_mask, x, wb, hills, A.n_hills, hstride, e, gv);
 #pragma unroll
         for (int d = 0; d < ND; d++) f[d] = bias_mask ? e.fp[d] + e.fb[d] : e.fp[d];
         // ---- second half kick, md.py:190-198

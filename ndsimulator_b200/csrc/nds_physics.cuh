@@ -479,6 +479,7 @@ NDS_DEV void hill_sum(const Consts<R>& K, int cd, const R* __restrict__ hills, l
 template <typename R> struct Real4;
 template <> struct Real4<float> { using type = float4; };
 template <> struct Real4<double> { using type = double4; };
+template <> struct Real4<f2> { using type = float4; };  // never used (no grid bias in packed kernels): keeps shared code well-formed
 
 template <typename R, bool SMEM>
 NDS_DEV typename Real4<R>::type grid_load(const R* grid, int idx) {
@@ -514,12 +515,19 @@ NDS_DEV void hermite_basis(R t, R (&a)[2], R (&b)[2], R (&da)[2], R (&db)[2]) {
   db[1] = t * ((R)3 * t - (R)2);
 }
 
+// The interpolation in two halves, so that the step kernel can issue the node loads right after the colvar is known
+// and evaluate the potential while they are in flight (grid_fetch), then contract (grid_combine).
+template <typename R>
+struct GridFetch {
+  typename Real4<R>::type n[4];  // nodes (j, i), (j + 1, i), (j, i + 1), (j + 1, i + 1); 1-D: nodes i, i + 1
+  R t, s;                        // position inside the cell
+  int state;                     // -1: not fetched (interpolate in place), 0: outside the box, 1: 1-D, 2: 2-D
+};
+
 template <typename R, int ND, bool SMEM>
-NDS_DEV void grid_interp(const Consts<R>& K, int cd, const R* grid, const R (&c)[ND], R& V, R (&g)[ND],
-                         unsigned long long* outside) {
-  V = (R)0;
-#pragma unroll
-  for (int k = 0; k < ND; k++) g[k] = (R)0;
+NDS_DEV void grid_fetch(const Consts<R>& K, int cd, const R* grid, const R (&c)[ND], GridFetch<R>& f,
+                        unsigned long long* outside) {
+  f.state = 0;
   if constexpr (pack_of<R>::value == 1) {
     const int nx = K.grid_nx, ny = K.grid_ny;
     const R u = (c[0] - K.grid_lo[0]) * K.grid_invh[0];
@@ -534,26 +542,48 @@ NDS_DEV void grid_interp(const Consts<R>& K, int cd, const R* grid, const R (&c)
     }
     int i = (int)u;
     if (i > nx - 2) i = nx - 2;
-    const R t = u - (R)i;
-    R a[2], b[2], da[2], db[2];
-    hermite_basis<R>(t, a, b, da, db);
+    f.t = u - (R)i;
     if (cd == 1) {
-      const auto G0 = grid_load<R, SMEM>(grid, i), G1 = grid_load<R, SMEM>(grid, i + 1);
+      f.n[0] = grid_load<R, SMEM>(grid, i);
+      f.n[1] = grid_load<R, SMEM>(grid, i + 1);
+      f.state = 1;
+      return;
+    }
+    int j = (int)w;
+    if (j > ny - 2) j = ny - 2;
+    f.s = w - (R)j;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      f.n[2 * p] = grid_load<R, SMEM>(grid, j * nx + i + p);
+      f.n[2 * p + 1] = grid_load<R, SMEM>(grid, (j + 1) * nx + i + p);
+    }
+    f.state = 2;
+  }
+}
+
+template <typename R, int ND>
+NDS_DEV void grid_combine(const Consts<R>& K, const GridFetch<R>& f, R& V, R (&g)[ND]) {
+  V = (R)0;
+#pragma unroll
+  for (int k = 0; k < ND; k++) g[k] = (R)0;
+  if constexpr (pack_of<R>::value == 1) {
+    if (f.state <= 0) return;
+    R a[2], b[2], da[2], db[2];
+    hermite_basis<R>(f.t, a, b, da, db);
+    if (f.state == 1) {
+      const auto G0 = f.n[0], G1 = f.n[1];
       V = a[0] * G0.x + b[0] * G0.y + a[1] * G1.x + b[1] * G1.y;
       const R dt = da[0] * G0.x + db[0] * G0.y + da[1] * G1.x + db[1] * G1.y;
       g[0] = -(dt * K.grid_invh[0]);
       return;
     }
-    int j = (int)w;
-    if (j > ny - 2) j = ny - 2;
-    const R s = w - (R)j;
     R as[2], bs[2], das[2], dbs[2];
-    hermite_basis<R>(s, as, bs, das, dbs);
+    hermite_basis<R>(f.s, as, bs, das, dbs);
     R Vt = (R)0, dVt = (R)0, dVs = (R)0;
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      const auto G0 = grid_load<R, SMEM>(grid, j * nx + i + p);
-      const auto G1 = grid_load<R, SMEM>(grid, (j + 1) * nx + i + p);
+      const auto G0 = f.n[2 * p];
+      const auto G1 = f.n[2 * p + 1];
       // contraction along s at column i + p: value, t-slope, and their s-derivatives
       const R vp = as[0] * G0.x + bs[0] * G0.z + as[1] * G1.x + bs[1] * G1.z;
       const R yp = as[0] * G0.y + bs[0] * G0.w + as[1] * G1.y + bs[1] * G1.w;
@@ -567,6 +597,14 @@ NDS_DEV void grid_interp(const Consts<R>& K, int cd, const R* grid, const R (&c)
     g[0] = -(dVt * K.grid_invh[0]);
     if constexpr (ND > 1) g[1] = -(dVs * K.grid_invh[1]);
   }
+}
+
+template <typename R, int ND, bool SMEM>
+NDS_DEV void grid_interp(const Consts<R>& K, int cd, const R* grid, const R (&c)[ND], R& V, R (&g)[ND],
+                         unsigned long long* outside) {
+  GridFetch<R> f;
+  grid_fetch<R, ND, SMEM>(K, cd, grid, c, f, outside);
+  grid_combine<R, ND>(K, f, V, g);
 }
 
 template <typename R>
@@ -589,7 +627,8 @@ template <typename R, int ND>
 NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const R (&x)[ND],
                        const CvOut<R, ND>& o, const WalkerBias<R, ND>& wb, const R* hills,
                        long long n_hills, long long elem_stride, R pe, const R (&fpot)[ND], R& Vb,
-                       R (&fb)[ND], R& Vm, const GridView<R> gv = GridView<R>{nullptr, 0, nullptr}) {
+                       R (&fb)[ND], R& Vm, const GridView<R> gv = GridView<R>{nullptr, 0, nullptr},
+                       const GridFetch<R>* pre = nullptr) {
   Vb = (R)0;
   Vm = (R)0;
 #pragma unroll
@@ -621,7 +660,8 @@ NDS_DEV void bias_eval(const Consts<R>& K, int bias_mask, int cv, int cd, const 
   if (bias_mask & BIAS_MTD) {
     R g[ND], f[ND];
     if (bias_mask & BIAS_MTD_GRID) {
-      if (gv.smem) grid_interp<R, ND, true>(K, cd, gv.grid, o.c, Vm, g, gv.outside);
+      if (pre) grid_combine<R, ND>(K, *pre, Vm, g);  // nodes were requested before the potential evaluation
+      else if (gv.smem) grid_interp<R, ND, true>(K, cd, gv.grid, o.c, Vm, g, gv.outside);
       else grid_interp<R, ND, false>(K, cd, gv.grid, o.c, Vm, g, gv.outside);
     } else {
       hill_sum<R, ND>(K, cd, hills, n_hills, elem_stride, o.c, Vm, g);
