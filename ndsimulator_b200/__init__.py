@@ -7,5 +7,6 @@ There is no CPU fallback: constructing an engine without the built library or wi
 from .config import parse as parse_config  # noqa: F401
 from .engine import Engine, NdsError  # noqa: F401
 from .ndrun import NDRun  # noqa: F401
+from .plugin import B200Engine, register as register_reference_plugin  # noqa: F401  (method: b200 for the reference's NDRun)
 
 __version__ = "0.1.0"

@@ -150,7 +150,8 @@ def test_user_defined_python_colvar_is_rejected(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["c2-2d-mueller-langevin", "c3-2d-committor", "c4-5d-umbrella-windows",
-                                  "c5-5d-multiwalker-mtd", "mc-2d-metropolis-mtd", "harmonic-quartic-5d"])
+                                  "c5-5d-multiwalker-mtd", "mc-2d-metropolis-mtd", "harmonic-quartic-5d",
+                                  "c2-side-work-frames-histogram", "c5-5d-multiwalker-mtd-grid", "1d-mtd-adaptive-sigma"])
 def test_shipped_examples_run(name, tmp_path):
     """examples/*.yaml (the BASELINE configurations) through the CLI, shortened."""
     from ndsimulator_b200.scripts.run import main
@@ -163,8 +164,18 @@ def test_shipped_examples_run(name, tmp_path):
         c = sim.colv
         k, r0 = sim._window
         assert np.abs(c - r0).mean() < 2.0          # walkers stay near their own window
-    if name.startswith("c5"):
+    if name == "c5-5d-multiwalker-mtd":
         assert sim.engine.n_hills() == 3 * 4096 and sim.engine.kernel_name.startswith("mtd_block")
+    if name == "c5-5d-multiwalker-mtd-grid":
+        assert sim.engine.n_hills() == 3 * 4096 and "mtd-grid" in sim.engine.kernel_name
+        assert sim.engine.get_mtd_grid()[..., 0].max() > 0
+    if name.startswith("c2-side-work"):
+        assert "frames+hist" in sim.engine.kernel_name
+        assert sim.engine.get_histogram().sum() > 0.99 * 30 * 4096      # 30 dump steps, every walker counted
+        assert os.path.exists(os.path.join(str(tmp_path), "c2_side_work", "walker_7", "pos.dat"))
+    if name.startswith("1d-mtd-adaptive"):
+        s2 = sim.engine.get_hill_sigma2(0)
+        assert len(s2) == 6 and s2[0] == 1.0 and len(np.unique(s2)) == 6  # first hill: one sample -> variance 1
     if name.startswith("mc"):
         assert sim.engine.kernel_name.startswith("mc_block")
         n0 = sim.engine.n_hills(0)
