@@ -52,6 +52,18 @@ ISSUE_MODEL = {
     "c2_nodump": (101.6, "profiles/r02_c2_nodump_raw.csv + source page: 58.9 instr, 6.0 IMAD.WIDE, 23.0 packed FP"),
     "c4": (369.6, "profiles/r02_c4_raw.csv + source page: 276.4 instr, 30.1 IMAD.WIDE"),
 }
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from ONE
+# `ncu --set full` capture each -- profiles/capture_r02*.sh, raw pages under profiles/ -- at the bench's own sizes.
+# Measured numbers of THIS commit's kernels, not derived ones: re-capture when a kernel changes.  For the step
+# kernels the algorithmic traffic is the state load at launch entry (2^20 x (x, v) floats = 16.8 MB for C2) plus the
+# part of the state written back that reaches DRAM before the kernel ends; the rest stays in L2.
+NCU_TRAFFIC = {
+    "c2": (16.737e6 + 5.486e6 + 0.095e6, "profiles/r02_c2_raw.csv (hist kernel + frames kernel of one step)"),
+    "c2_nodump": (16.800e6 + 6.057e6, "profiles/r02_c2_nodump_raw.csv"),
+    "c3": (24.165e6 + 10.055e6, "profiles/r02_c3_raw.csv"),
+    "c4": (59.324e6 + 56.141e6, "profiles/r02_c4_raw.csv"),
+    "dump1": (16.828e6 + 6714.608e6, "profiles/r02_dump1_raw.csv"),
+}
 L2_FLUSH_BYTES = 256 << 20
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
@@ -518,6 +530,8 @@ def bench_md(ctx, name, M, steps, warmup, precision="f32", sampler=None):
                     f"fields x {M} walkers per launch of {md_steps} steps; peak = MEASURED_PEAKS.json hbm_gbs "
                     f"({'measured' if 'hbm_gbs' in peaks else 'fallback'}); the launch also integrates the {md_steps} "
                     "steps (see compute_floor)"}
+        if name in NCU_TRAFFIC and M == (1 << 20):
+            rec["roofline"]["traffic"], rec["roofline"]["traffic_source"] = NCU_TRAFFIC[name]
     else:
         ach = per_gpu * FLOPS_PER_WALKER_STEP[name] / 1e12
         pk = ctx.fp32_peak_tflops()
@@ -527,6 +541,8 @@ def bench_md(ctx, name, M, steps, warmup, precision="f32", sampler=None):
                     f"GPU; peak = {ctx.sm_count} SMs x 128 lanes x 2 x {ctx.sm_max_mhz:.0f} MHz (clocks.max.sm; "
                     "MEASURED_PEAKS.json holds no FP32 figure). HBM traffic is negligible (state is "
                     "register-resident for the whole launch)."}
+        if name in NCU_TRAFFIC and M == (1 << 20):
+            rec["roofline"]["traffic"], rec["roofline"]["traffic_source"] = NCU_TRAFFIC[name]
         if name in ISSUE_MODEL:
             model, src = ISSUE_MODEL[name]
             measured = 4 * ctx.sm_count * ctx.sm_max_mhz * 1e6 * 32.0 / per_gpu  # cycles per 32 walker-steps per SMSP
