@@ -1192,8 +1192,8 @@ struct Engine : nds_engine {
         // fused with the exchange: the increment goes straight into this rank's slot on EVERY peer over NVLink;
         // after the barrier each rank adds the slots in rank order (bit-identical grids everywhere)
         const int par = (int)(dep_count & 1);
-        exchange_mark(true);
-        if (accumulate(rec, M, d_slot_dst + par * n_peers, n_peers, false)) return 1;
+        // (the exchange clock starts at the kernel that writes to the peers, not at the footprint computation)
+        if (accumulate(rec, M, d_slot_dst + par * n_peers, n_peers, false, true)) return 1;
         if (peer_barrier()) return 1;
         grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
         CU(cudaGetLastError());
@@ -2164,7 +2164,7 @@ struct Engine : nds_engine {
 
   // footprint of n records on the grid: partial sums per record slice, then the slices in order -> grid += (add),
   // or -> the destination list (increment slots on the peers / the all-reduce buffer)
-  int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add) {
+  int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add, bool mark_exchange = false) {
     const int tiles = ((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY);
     int slices = (int)((n + 511) / 512);
     if (slices < 1) slices = 1;
@@ -2172,6 +2172,7 @@ struct Engine : nds_engine {
     if (!d_gpart) CU(cudaMalloc(&d_gpart, sizeof(R) * (size_t)grid_elems * 16));
     grid_accumulate_kernel<R><<<(unsigned)(tiles * slices), GRID_TX * GRID_TY, 0, stream>>>(K, rec, n, slices, d_gpart);
     CU(cudaGetLastError());
+    if (mark_exchange) exchange_mark(true);
     grid_reduce_kernel<R><<<(unsigned)((grid_elems + 255) / 256), 256, 0, stream>>>(grid_elems, slices, d_gpart, dst, ndst, d_grid, add ? 1 : 0);
     CU(cudaGetLastError());
     launches += 2;
