@@ -350,6 +350,19 @@ NDS_API int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap);
 NDS_API int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n);
 NDS_API int64_t nds_mtd_grid_outside(nds_engine* e);
 
+/* Monte Carlo / Wang-Landau bookkeeping of EVERY walker, for checkpoints (nds_get_mc / nds_get_wl_histogram serve one
+ * quantity or one walker): accepted[M] (MC.accept_rate, mc.py:85); with a metadynamics bias time[M] and dep[M], each
+ * walker's own NDRun.time and Gaussian._dep_count (ndrun.py:234-237: the clock advances on accepted moves only);
+ * wl[101][M] = WangLandau.hE[0] of every walker (wang_landau.py:17).  Null pointers are skipped.  *max_dep = the
+ * longest per-walker table; after the call nds_get_hill_table_raw covers that many records.                    */
+NDS_API int nds_get_mc_state(nds_engine* e, int64_t* accepted, double* time, int64_t* dep, double* wl, int64_t* max_dep);
+NDS_API int nds_set_mc_state(nds_engine* e, const int64_t* accepted, const double* time, const int64_t* dep,
+                             const double* wl);
+
+/* thermo[5][n_walkers] = (T, pe, ke, biase, totale) as nds_get_state returns them.  Under MC they follow the last
+ * event, not the state (mc.py:93-95; gaus.py:146): a resumed run writes them back after nds_begin.          */
+NDS_API int nds_set_thermo(nds_engine* e, const double* thermo);
+
 /* Harmonic.VR of every restraint as of the last refresh, [n_umb][n_walkers] (umb.py:32-33; refreshed by begin() and by
  * every deposition, gaus.py:138-146).  Kept only when umbrella AND metadynamics biases record frames (it feeds the
  * fix_VR column of thermo.dat); *n = 0 otherwise.  For checkpoints.                                          */

@@ -137,6 +137,11 @@ _PROTOTYPES = {
     "nds_get_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "nds_set_mtd_grid": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "nds_mtd_grid_outside": (C.c_int64, [C.c_void_p]),
+    "nds_get_mc_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "nds_set_mc_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_double)]),
+    "nds_set_thermo": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "nds_get_umb_vr": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64)]),
     "nds_set_umb_vr": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int64]),
     "nds_get_cv_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

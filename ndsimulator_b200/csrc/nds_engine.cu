@@ -76,6 +76,9 @@ struct nds_engine {
   virtual int get_mtd_grid(double* out, int64_t cap) = 0;
   virtual int set_mtd_grid(const double* in, int64_t n) = 0;
   virtual int64_t mtd_grid_outside() = 0;
+  virtual int get_mc_state(int64_t* accepted, double* time, int64_t* dep, double* wl, int64_t* max_dep) = 0;
+  virtual int set_mc_state(const int64_t* accepted, const double* time, const int64_t* dep, const double* wl) = 0;
+  virtual int set_thermo(const double* thermo) = 0;
   virtual int get_umb_vr(double* vr, int64_t cap, int64_t* n) = 0;
   virtual int set_umb_vr(const double* vr, int64_t n) = 0;
   virtual int get_cv_history(double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) = 0;
@@ -1482,6 +1485,62 @@ struct Engine : nds_engine {
     return 0;
   }
 
+  // Per-walker Monte Carlo bookkeeping for checkpoints: accepted moves, and -- with a metadynamics bias -- every walker's
+  // own clock and deposition count; Wang-Landau histograms of all walkers as [NDS_WL_GRID][M].  Null pointers are
+  // skipped.  get also makes the raw hill-table getters cover the longest table (n_hills = max deposition count).
+  int get_mc_state(int64_t* accepted, double* tm, int64_t* dep, double* wl, int64_t* max_dep) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_MC && cfg.method != NDS_METHOD_WL) return fail(this, "nds_get_mc_state: method is not mc / wl-mc");
+    CU(cudaStreamSynchronize(stream));
+    if (accepted) CU(cudaMemcpy(accepted, d_mc_accepted, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
+    if (max_dep) *max_dep = 0;
+    if (cfg.mtd_enabled) {
+      std::vector<long long> d((size_t)M);
+      CU(cudaMemcpy(d.data(), d_mc_dep, sizeof(long long) * (size_t)M, cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (long long v : d) mx = v > mx ? v : mx;
+      if (dep) for (int64_t i = 0; i < M; i++) dep[i] = d[(size_t)i];
+      if (tm) CU(cudaMemcpy(tm, d_mc_time, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost));
+      if (max_dep) *max_dep = mx;
+      n_hills = mx;
+    } else if (tm || dep) {
+      return fail(this, "nds_get_mc_state: clocks and deposition counts exist only with a metadynamics bias");
+    }
+    if (wl) {
+      if (!d_wl) return fail(this, "nds_get_mc_state: method is not wl-mc");
+      if (download(d_wl, wl, (int64_t)NDS_WL_GRID * M)) return 1;
+    }
+    return 0;
+  }
+  int set_mc_state(const int64_t* accepted, const double* tm, const int64_t* dep, const double* wl) override {
+    CU(cudaSetDevice(cfg.device));
+    if (cfg.method != NDS_METHOD_MC && cfg.method != NDS_METHOD_WL) return fail(this, "nds_set_mc_state: method is not mc / wl-mc");
+    CU(cudaStreamSynchronize(stream));
+    if (accepted) CU(cudaMemcpy(d_mc_accepted, accepted, sizeof(long long) * (size_t)M, cudaMemcpyHostToDevice));
+    if ((tm || dep) && !cfg.mtd_enabled) return fail(this, "nds_set_mc_state: clocks and deposition counts exist only with a metadynamics bias");
+    if (tm) CU(cudaMemcpy(d_mc_time, tm, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice));
+    if (dep) {
+      std::vector<long long> d((size_t)M);
+      for (int64_t i = 0; i < M; i++) {
+        if (dep[i] < 0 || dep[i] > cfg.mtd_capacity) return fail(this, "nds_set_mc_state: deposition count of walker %lld out of range", (long long)i);
+        d[(size_t)i] = dep[i];
+      }
+      CU(cudaMemcpy(d_mc_dep, d.data(), sizeof(long long) * (size_t)M, cudaMemcpyHostToDevice));
+    }
+    if (wl) {
+      if (!d_wl) return fail(this, "nds_set_mc_state: method is not wl-mc");
+      if (upload(wl, d_wl, (int64_t)NDS_WL_GRID * M)) return 1;
+    }
+    return 0;
+  }
+
+  // thermo[5][M] = (T, pe, ke, biase, totale): under MC these follow the last EVENT (mc.py:93-95 zeroes ke on the first
+  // accepted move, a deposition sets totale, gaus.py:146), so a resumed run has to get them back
+  int set_thermo(const double* thermo) override {
+    CU(cudaSetDevice(cfg.device));
+    return upload(thermo, d_thermo, (int64_t)5 * M);
+  }
+
   // one fused launch of k steps over slots [slot0, slot0 + nslots) (nslots == 0: every launched slot) on stream st;
   // rest = true: the variant without frames (walkers beyond the dump prefix of a split launch)
   cudaError_t launch_steps(int64_t k, int64_t slot0, int64_t nslots, cudaStream_t st, bool rest = false) {
@@ -2374,6 +2433,13 @@ int nds_table_checksum(nds_engine* e, int64_t first, int64_t n, uint64_t* sum) {
 int nds_get_mtd_grid(nds_engine* e, double* out, int64_t cap) { return e->get_mtd_grid(out, cap); }
 int nds_set_mtd_grid(nds_engine* e, const double* in, int64_t n) { return e->set_mtd_grid(in, n); }
 int64_t nds_mtd_grid_outside(nds_engine* e) { return e->mtd_grid_outside(); }
+int nds_get_mc_state(nds_engine* e, int64_t* accepted, double* time, int64_t* dep, double* wl, int64_t* max_dep) {
+  return e->get_mc_state(accepted, time, dep, wl, max_dep);
+}
+int nds_set_mc_state(nds_engine* e, const int64_t* accepted, const double* time, const int64_t* dep, const double* wl) {
+  return e->set_mc_state(accepted, time, dep, wl);
+}
+int nds_set_thermo(nds_engine* e, const double* thermo) { return e->set_thermo(thermo); }
 int nds_get_umb_vr(nds_engine* e, double* vr, int64_t cap, int64_t* n) { return e->get_umb_vr(vr, cap, n); }
 int nds_set_umb_vr(nds_engine* e, const double* vr, int64_t n) { return e->set_umb_vr(vr, n); }
 int nds_get_cv_history(nds_engine* e, double* ring, int64_t cap_elems, int64_t* n_samples, int64_t* window) {

@@ -279,10 +279,29 @@ class Engine:
 
     def checkpoint(self):
         """Everything needed to continue the run bit for bit on a fresh engine of the same config."""
-        if self.cfg.method in (_abi.NDS_METHOD_MC, _abi.NDS_METHOD_WL) and self.cfg.mtd_enabled:
-            raise NdsError("checkpoint of MC metadynamics (per-walker clocks and hill counts) is not implemented")
-        st = self.get_state(fields=("x", "v"))
+        st = self.get_state(fields=("x", "v", "thermo"))
         ck = dict(x=st["x"], v=st["v"], **self.get_clock())
+        if self.cfg.method in (_abi.NDS_METHOD_MC, _abi.NDS_METHOD_WL):
+            # Metropolis / Wang-Landau: accepted moves, ke / totale of the last event (they are not functions of (x, v):
+            # mc.py:93-95 zeroes ke on the first accepted move), per-walker clocks + tables, histograms
+            i64 = C.POINTER(C.c_int64)
+            acc = np.zeros(self.M, dtype=np.int64)
+            mtd, wl = bool(self.cfg.mtd_enabled), self.cfg.method == _abi.NDS_METHOD_WL
+            tm = np.zeros(self.M) if mtd else None
+            dep = np.zeros(self.M, dtype=np.int64) if mtd else None
+            hist = np.zeros((101, self.M)) if wl else None
+            mx = C.c_int64()
+            self._check(self.lib.nds_get_mc_state(self.h, acc.ctypes.data_as(i64), _p(tm),
+                                                  None if dep is None else dep.ctypes.data_as(i64), _p(hist), C.byref(mx)))
+            ck.update(mc_accepted=acc, mc_thermo=np.stack([st[k] for k in ("T", "pe", "ke", "biase", "totale")]))
+            if wl:
+                ck["mc_wl"] = hist
+            if mtd:
+                n = int(mx.value)
+                raw = np.empty(int(self.lib.nds_hill_table_size(self.h, n)))
+                self._check(self.lib.nds_get_hill_table_raw(self.h, _p(raw), raw.size))
+                ck.update(mc_time=tm, mc_dep=dep, hills_raw=raw, hills_n=n, vr=self.get_vr())
+            return ck
         if self.cfg.method == _abi.NDS_METHOD_COMMITTOR:
             basin, exit_step = self.get_commit()
             alive = np.empty(self.M, dtype=np.uint8)
@@ -327,6 +346,15 @@ class Engine:
             if "mtd_grid" in ck:
                 self.set_mtd_grid(ck["mtd_grid"])
             self.set_vr(ck["vr"])
+        if "mc_accepted" in ck:
+            i64 = C.POINTER(C.c_int64)
+            acc = np.ascontiguousarray(ck["mc_accepted"], dtype=np.int64)
+            tm = _f64(ck["mc_time"]) if "mc_time" in ck else None
+            dep = np.ascontiguousarray(ck["mc_dep"], dtype=np.int64) if "mc_dep" in ck else None
+            hist = _f64(ck["mc_wl"]) if "mc_wl" in ck else None
+            self._check(self.lib.nds_set_mc_state(self.h, acc.ctypes.data_as(i64), _p(tm),
+                                                  None if dep is None else dep.ctypes.data_as(i64), _p(hist)))
+            self._check(self.lib.nds_set_thermo(self.h, _p(_f64(ck["mc_thermo"]))))
         if "umb_vr" in ck:
             uv = _f64(ck["umb_vr"]).reshape(-1)
             self._check(self.lib.nds_set_umb_vr(self.h, _p(uv), uv.size))

@@ -372,3 +372,54 @@ def test_gpu_mc_follows_the_seeded_reference(name):
     eng.set_noise(_reference_uniforms(rec))
     eng.begin()
     _check_against_reference(eng, rec, every=40)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["mc", "mc_mtd", "wl", "wl_mtd", "mc_all_umb"])
+def test_gpu_mc_checkpoint_resume_is_exact(case):
+    """Metropolis / Wang-Landau ensembles continue bit for bit from a checkpoint on a fresh engine: accepted moves,
+    the per-walker clocks and hill tables of MC metadynamics, Wang-Landau histograms, and the event-driven ke / totale
+    (mc.py:93-95) come back; the Philox proposal stream is a function of (seed, walker, move index)."""
+    from ndsimulator_b200.engine import Engine
+    M, n, cut = 48, 600, 250
+    cfg = dict(M2, dt=0.5, steps=n, seed=5)
+    if case.startswith("wl"):
+        cfg.update(method="wl-mc", bounds=[1.5, 1.5], global_bounds=[48.0, 40.0])
+        cfg.pop("mc_bounds"), cfg.pop("mc_global_bounds")
+    if case.endswith("mtd"):
+        cfg.update(biases=["mtd"], mtd_w=0.02, mtd_sigma=[1.5, 1.5], mtd_dep_freq=10, mtd_biasf=8.0)
+    if case == "mc_all_umb":
+        cfg.update(propose_dim="all", biases=["umb"], umb_k=0.05, umb_r0=[25, 20])
+    spec = spec_from(cfg, n_walkers=M, steps_per_launch=64)
+    x0 = np.repeat(spec.x0.reshape(-1, 1), M, axis=1) + np.random.RandomState(1).normal(scale=0.4, size=(2, M))
+
+    def fresh():
+        e = Engine(spec.to_struct())
+        e.set_state(x0)
+        e.begin()
+        return e
+
+    a = fresh()
+    a.run(n)
+    b = fresh()
+    b.run(cut)
+    ck = b.checkpoint()
+    c = Engine(spec.to_struct())
+    c.restore(ck)
+    c.run(n - cut)
+    assert c.step == a.step == n
+    assert np.array_equal(c.get_mc(), a.get_mc()) and a.get_mc().sum() > 0
+    sa, sc = a.get_state(), c.get_state()
+    for k in ("x", "colv", "pe", "ke", "biase", "totale"):
+        assert np.array_equal(sa[k], sc[k]), k
+    if case.endswith("mtd"):
+        assert np.array_equal(a.get_vr(), c.get_vr())
+        counts = set()
+        for wk in (0, 17, M - 1):
+            (ca, ha), (cc, hc) = a.get_hills(wk), c.get_hills(wk)
+            assert np.array_equal(ha, hc) and np.array_equal(ca, cc) and len(ha) > 3
+            counts.add(len(ha))
+    if case.startswith("wl"):
+        for wk in (0, M - 1):
+            assert np.array_equal(a.get_wl_histogram(wk), c.get_wl_histogram(wk))
+        assert a.get_wl_histogram(0).sum() > 0
