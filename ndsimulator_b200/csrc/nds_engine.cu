@@ -674,7 +674,7 @@ struct Engine : nds_engine {
   int64_t grid_elems = 0;                  // 4 * nx * ny
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
-  R* d_gpart = nullptr;                    // partial sums of the record slices of one accumulation [16][grid]
+  bool cluster_ready = false;              // grid_accumulate_kernel may run clusters of GRID_SLICES CTAs
   R* d_vr_umb = nullptr;                   // Harmonic.VR per restraint [n_umb][M] (umbrella + metadynamics with frames)
   R* d_cvhist = nullptr;                   // Stat.colv ring [tao_d][M] (mtd_adapsig_hist)
   int64_t cv_n = 0;                        // samples taken so far (len(stat.colv))
@@ -706,7 +706,7 @@ struct Engine : nds_engine {
   ~Engine() override {
     cudaSetDevice(cfg.device);
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
-    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_gpart, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
@@ -2225,16 +2225,22 @@ struct Engine : nds_engine {
   // or -> the destination list (increment slots on the peers / the all-reduce buffer)
   int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add, bool mark_exchange = false) {
     const int tiles = ((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY);
-    int slices = (int)((n + 511) / 512);
-    if (slices < 1) slices = 1;
-    if (slices > 16) slices = 16;
-    if (!d_gpart) CU(cudaMalloc(&d_gpart, sizeof(R) * (size_t)grid_elems * 16));
-    grid_accumulate_kernel<R><<<(unsigned)(tiles * slices), GRID_TX * GRID_TY, 0, stream>>>(K, rec, n, slices, d_gpart);
-    CU(cudaGetLastError());
-    if (mark_exchange) exchange_mark(true);
-    grid_reduce_kernel<R><<<(unsigned)((grid_elems + 255) / 256), 256, 0, stream>>>(grid_elems, slices, d_gpart, dst, ndst, d_grid, add ? 1 : 0);
-    CU(cudaGetLastError());
-    launches += 2;
+    if (!cluster_ready) {  // clusters of GRID_SLICES = 16 CTAs: above the portable size of 8
+      CU(cudaFuncSetAttribute(grid_accumulate_kernel<R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cluster_ready = true;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(tiles * GRID_SLICES));
+    lc.blockDim = dim3(GRID_NT);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = GRID_SLICES; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (mark_exchange) exchange_mark(true);  // the kernel that writes to the peers
+    CU(cudaLaunchKernelEx(&lc, grid_accumulate_kernel<R>, K, rec, (long long)n, dst, ndst, d_grid, add ? 1 : 0));
+    launches += 1;
     return 0;
   }
 
