@@ -3,6 +3,7 @@
 // shared-memory copy of the grid.  Other bias combinations (umb + mtd, pe + mtd) run the generic md_block and read
 // the grid from global memory.
 #include "nds_variants.h"
+#include "nds_pair_kernel.cuh"
 
 namespace nds {
 namespace {
@@ -13,8 +14,9 @@ constexpr int MD = NDS_METHOD_MD, PHX = NDS_NOISE_PHILOX;
 const Variant* variants_grid(int* n) {
   static const Variant table[] = {
       // C5 with mtd_grid: 5-D Mueller + Proj5dto2d, Langevin, Philox noise
-      make_variant_wide<Spec<float, 5, NDS_POT_MUELLER5D, NDS_CV_PROJ5DTO2D, NDS_CV_PROJ5DTO2D, NDS_INT_LANGEVIN, GB, MD, PHX, 0>>(
-          "md_block_wide<f32,nd5,Mueller5d,Proj5dto2d,langevin,mtd-grid>"),
+      // (two lanes per walker up to NDS_PAIR_MAX walkers per launch, nds_pair_kernel.cuh; md_block_wide above that)
+      make_variant_pair<Spec<float, 5, NDS_POT_MUELLER5D, NDS_CV_PROJ5DTO2D, NDS_CV_PROJ5DTO2D, NDS_INT_LANGEVIN, GB, MD, PHX, 0>>(
+          "md_pair_grid|md_block_wide<f32,nd5,Mueller5d,Proj5dto2d,langevin,mtd-grid>"),
       // examples/2d-mtd.yaml with mtd_grid
       make_variant_wide<Spec<float, 2, NDS_POT_MUELLER2D, NDS_CV_ORIGINAL, NDS_CV_ORIGINAL, NDS_INT_LANGEVIN, GB, MD, PHX, 0>>(
           "md_block_wide<f32,nd2,Mueller2d,Original,langevin,mtd-grid>"),

@@ -1192,11 +1192,16 @@ struct Engine : nds_engine {
       if (!multi) {
         if (accumulate(rec, M, nullptr, 0, true)) return 1;
       } else if (d_slot_dst) {
-        // fused with the exchange: the increment goes straight into this rank's slot on EVERY peer over NVLink;
-        // after the barrier each rank adds the slots in rank order (bit-identical grids everywhere)
+        // the increment is pushed into this rank's slot on EVERY peer over NVLink; after the barrier each rank adds
+        // the slots in rank order (bit-identical grids everywhere)
         const int par = (int)(dep_count & 1);
         // (the exchange clock starts at the kernel that writes to the peers, not at the footprint computation)
-        if (accumulate(rec, M, d_slot_dst + par * n_peers, n_peers, false, true)) return 1;
+        if (accumulate(rec, M, d_ginc_list, 1, false)) return 1;
+        exchange_mark(true);
+        const long long n16 = grid_elems * (long long)sizeof(R) / 16;  // 4 reals per point: a multiple of 16 bytes
+        grid_push_kernel<R><<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(n16, d_ginc, d_slot_dst + par * n_peers, n_peers);
+        CU(cudaGetLastError());
+        launches++;
         if (peer_barrier()) return 1;
         grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
         CU(cudaGetLastError());
@@ -2223,7 +2228,7 @@ struct Engine : nds_engine {
 
   // footprint of n records on the grid: partial sums per record slice, then the slices in order -> grid += (add),
   // or -> the destination list (increment slots on the peers / the all-reduce buffer)
-  int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add, bool mark_exchange = false) {
+  int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add) {
     const int tiles = ((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY);
     if (!cluster_ready) {  // clusters of GRID_SLICES = 16 CTAs: above the portable size of 8
       CU(cudaFuncSetAttribute(grid_accumulate_kernel<R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -2238,7 +2243,6 @@ struct Engine : nds_engine {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = GRID_SLICES; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    if (mark_exchange) exchange_mark(true);  // the kernel that writes to the peers
     CU(cudaLaunchKernelEx(&lc, grid_accumulate_kernel<R>, K, rec, (long long)n, dst, ndst, d_grid, add ? 1 : 0));
     launches += 1;
     return 0;

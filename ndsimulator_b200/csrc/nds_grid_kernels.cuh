@@ -35,8 +35,8 @@ constexpr int GRID_SLICES = 8;             // record slices per tile = CTAs per 
 // memory, and after a cluster barrier CTA r adds row r of the tile over the slices through distributed shared
 // memory -- so results are reproducible and identical wherever they are recomputed.  Then
 //   add != 0: grid[p] += sum (single rank / rebuilding a grid from a table);
-//   add == 0: dst[r][p] = sum for r < ndst (this rank's increment slot on every peer over NVLink, or the local
-//             all-reduce buffer) -- every point is written, so slots never need clearing.
+//   add == 0: dst[r][p] = sum for r < ndst (the local increment buffer that grid_push_kernel / the all-reduce
+//             sends on) -- every point is written, so the buffer never needs clearing.
 // No partial grids in global memory, no second kernel.
 template <typename R> struct GridAccCfg {
   static constexpr int QN = sizeof(R) == 4 ? 128 : 64;  // records culled per pass and warp (queue capacity)
@@ -208,11 +208,22 @@ grid_accumulate_kernel(const __grid_constant__ Consts<R> K, const R* __restrict_
       if (add) grid[p] += v;
       else {
         for (int r = 0; r < ndst; r++) dst[r][p] = v;
-        if (ndst > 1) __threadfence_system();  // peer slots: visible before the barrier kernel signals
       }
     }
   }
   cluster.sync();  // nobody leaves while its shared memory may still be read
+}
+
+// This rank's increment -> its slot on every peer (stores over NVLink), float4 / double2 per thread.  Kept apart from
+// grid_accumulate_kernel: system-scope fences inside the cluster kernel stall whole clusters (2 GPUs: 104 vs 95 us
+// per stride, r02z).
+template <typename R>
+__global__ void grid_push_kernel(long long n16, const R* __restrict__ inc, R* const* __restrict__ dst, int ndst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const int4 v = reinterpret_cast<const int4*>(inc)[i];
+  for (int r = 0; r < ndst; r++) reinterpret_cast<int4*>(dst[r])[i] = v;
+  __threadfence_system();  // peer slots: visible before the barrier kernel signals
 }
 
 // grid += sum of nsrc increment buffers, in the given (rank) order: every rank ends with bit-identical grids

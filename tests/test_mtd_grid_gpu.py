@@ -146,11 +146,12 @@ def test_grid_in_shared_memory_equals_grid_in_global_memory(monkeypatch):
     x0 = np.stack([rng.uniform(8, 30, M), rng.uniform(-3, 3, M), rng.uniform(8, 30, M), rng.uniform(-3, 3, M),
                    np.full(M, 12.0)])
     out = {}
+    monkeypatch.setenv("NDS_NO_PAIR", "1")  # the thread-per-walker kernel (small ensembles default to md_pair_grid)
     for mode in ("smem", "global"):
         if mode == "global":
             monkeypatch.setenv("NDS_GRID_NO_SMEM", "1")
         eng = Engine(spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=100).to_struct())
-        assert eng.kernel_name == "md_block_wide<f32,nd5,Mueller5d,Proj5dto2d,langevin,mtd-grid>"
+        assert eng.kernel_name.endswith("md_block_wide<f32,nd5,Mueller5d,Proj5dto2d,langevin,mtd-grid>")
         eng.set_state(x0)
         eng.begin()
         eng.run(500)
@@ -160,6 +161,75 @@ def test_grid_in_shared_memory_equals_grid_in_global_memory(monkeypatch):
     assert np.array_equal(out["smem"][1], out["global"][1])
     assert out["smem"][2] == out["global"][2] == 0
     assert out["smem"][0]["biase"].max() > 0.05
+
+
+def c5_start(M, seed=2):
+    rng = np.random.RandomState(seed)
+    return np.stack([rng.uniform(8, 30, M), rng.uniform(-3, 3, M), rng.uniform(8, 30, M), rng.uniform(-3, 3, M),
+                     np.full(M, 12.0)])
+
+
+def test_pair_kernel_follows_the_thread_per_walker_kernel(monkeypatch):
+    """md_pair_grid (two lanes per walker, nds_pair_kernel.cuh) against md_block_wide: same Philox stream, same
+    physics, the force summed in a different order -- the states agree to fp32 rounding after 20 steps and stay close
+    over 5 depositions (Langevin dynamics contract); hills, VR and the grid follow.  An odd walker count leaves a
+    shadow pair in the last warp."""
+    M = 201
+    cfg = dict(C5, **GRID, seed=11)
+    x0 = c5_start(M)
+    out = {}
+    for mode in ("pair", "wide"):
+        if mode == "wide":
+            monkeypatch.setenv("NDS_NO_PAIR", "1")
+        eng = Engine(spec_from(cfg, n_walkers=M, precision="f32", steps_per_launch=100).to_struct())
+        assert eng.kernel_name.startswith("md_pair_grid|md_block_wide<f32,nd5,Mueller5d")
+        eng.set_state(x0)
+        eng.begin()
+        eng.run(20)
+        s20 = eng.get_state()
+        eng.run(480)
+        out[mode] = (s20, eng.get_state(), eng.get_hills(), eng.get_mtd_grid(), eng.mtd_grid_outside())
+    a, b = out["pair"], out["wide"]
+    d20 = {k: np.max(np.abs(a[0][k] - b[0][k])) for k in ("x", "v", "f", "fixf", "pe", "biase")}
+    d500 = {k: np.max(np.abs(a[1][k] - b[1][k])) for k in ("x", "v", "biase")}
+    print("pair vs wide after 20 steps:", d20, "after 500:", d500)
+    assert d20["x"] < 1e-4 and d20["v"] < 1e-5 and d20["pe"] < 1e-4
+    assert not np.array_equal(a[0]["x"], x0) and np.max(np.abs(a[0]["x"] - x0)) > 0.05  # the walkers did move
+    assert d500["x"] < 5e-2 and np.median(np.abs(a[1]["x"] - b[1]["x"])) < 1e-3
+    (ca, ha), (cb, hb) = a[2], b[2]
+    assert len(ha) == len(hb) == 5 * M
+    assert np.max(np.abs(ca - cb)) < 5e-2 and np.max(np.abs(ha - hb)) < 1e-4 * 0.05
+    assert np.max(np.abs(a[3] - b[3])) < 2e-3 * np.max(np.abs(b[3]))
+    assert a[4] == b[4] == 0
+    assert a[1]["biase"].max() > 0.05
+
+
+def test_pair_kernel_launch_boundaries_and_fp64(monkeypatch):
+    """(1) Launch boundaries at odd and even steps do not change the pair kernel's results (its launch entry
+    evaluates the force with the loop's own arithmetic; steps are drawn in (even, odd) pairs).  (2) Against the fp64
+    engine under the same Philox seed the walkers stay within fp32 distance over 60 steps."""
+    M = 64
+    cfg = dict(C5, **GRID, seed=5, mtd_dep_freq=1000)  # no deposition inside the window
+    x0 = c5_start(M, seed=7)
+
+    def run(prec, chunks):
+        eng = Engine(spec_from(cfg, n_walkers=M, precision=prec, steps_per_launch=1000).to_struct())
+        eng.set_state(x0)
+        eng.begin()
+        for c in chunks:
+            eng.run(c)
+        return eng.get_state()
+
+    one = run("f32", [60])
+    for chunks in ([7, 13, 40], [1, 1, 58], [30, 30]):
+        st = run("f32", chunks)
+        for k in ("x", "v", "f", "pe"):
+            assert np.array_equal(one[k], st[k]), (chunks, k)
+    ref = run("f64", [60])
+    # the fp64 engine extends every 21-bit field by a second Philox call: the two noise streams differ by the cell
+    # width (2^-21 relative in the radius variate), like the fp32 / fp64 pairs of tests/test_fuzz_gpu.py
+    assert np.max(np.abs(one["x"] - ref["x"])) < 1e-2
+    assert scaled_err(one["pe"], ref["pe"]) < 5e-3
 
 
 def test_grid_one_dimensional_colvar():
