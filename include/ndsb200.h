@@ -452,6 +452,12 @@ NDS_API int nds_noise_tail_counts(int device, int precision, uint64_t seed, int6
                                   int64_t calls_per_walker, const double* thresholds, int n_thresholds,
                                   uint64_t* counts, double* stats4);
 
+/* Map50to2d (colvars/misc.py:19-156): values c[2][n] (compute, :140-150) and Jacobians jac[2][50][n] (jacobian,
+ * :152-155) of the two 50-dimensional quadratic forms at n configurations x[50][n], fp64, on `device`.  Either
+ * output may be NULL.  No potential of the reference accepts ndim = 50 (potential.py:12 with mueller.py:59 /
+ * misc.py:53), so this evaluation is everything the reference itself can do with the colvar.                  */
+NDS_API int nds_map50to2d(int device, const double* x, int64_t n, double* c, double* jac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ as hand-written sm_100a CUDA (ndsimulator_b200/csrc) reached through the C ABI o
 There is no CPU fallback: constructing an engine without the built library or without a GPU raises.
 """
 from .config import parse as parse_config  # noqa: F401
-from .engine import Engine, NdsError  # noqa: F401
+from .engine import Engine, NdsError, map50to2d  # noqa: F401
 from .ndrun import NDRun  # noqa: F401
 from .plugin import B200Engine, register as register_reference_plugin  # noqa: F401  (method: b200 for the reference's NDRun)
 

@@ -180,6 +180,7 @@ _PROTOTYPES = {
                                  C.POINTER(C.c_uint32)]),
     "nds_noise_tail_counts": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_double),
                                         C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "nds_map50to2d": (C.c_int, [C.c_int, _dp, C.c_int64, _dp, _dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -42,6 +42,12 @@ def _builtin_name(name, package: str, table: dict, what: str) -> str:
         raise ValueError(
             f"user-defined Python {what} {name!r} cannot run on the B200 engine (no CPU fallback); "
             f"built-ins: {sorted(table)}")
+    if what == "colvar" and name.rsplit(".", 1)[-1] == "Map50to2d":
+        # colvars/misc.py:19-156: ndim = 50, and no potential of the reference accepts ndim = 50 (potential.py:12
+        # with mueller.py:59 / misc.py:53), so no reference run can use it either
+        raise ValueError("colvar Map50to2d needs ndim = 50, which no potential accepts (neither here nor in the "
+                         "reference); its values and Jacobians are served by ndsimulator_b200.map50to2d(x) / "
+                         "nds_map50to2d()")
     short = name
     for pre in (f"ndsimulator.{package}.", f"ndsimulator_b200.{package}."):
         if short.startswith(pre):

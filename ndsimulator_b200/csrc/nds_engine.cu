@@ -19,6 +19,7 @@
 #include "nds_variants.h"
 #include "nds_mc_kernel.cuh"
 #include "nds_grid_kernels.cuh"
+#include "nds_map50.cuh"
 
 namespace nds { constexpr int MTD_TILE_HOST = 2048; }  // >= mtd_tile_records<R>() of nds_mtd_kernel.cuh
 
@@ -674,6 +675,8 @@ struct Engine : nds_engine {
   int64_t grid_elems = 0;                  // 4 * nx * ny
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
+  unsigned int* d_ticket = nullptr;        // arrival counter of grid_exchange_kernel
+  int sm_count = 0;
   bool cluster_ready = false;              // grid_accumulate_kernel may run clusters of GRID_SLICES CTAs
   R* d_vr_umb = nullptr;                   // Harmonic.VR per restraint [n_umb][M] (umbrella + metadynamics with frames)
   R* d_cvhist = nullptr;                   // Stat.colv ring [tao_d][M] (mtd_adapsig_hist)
@@ -706,7 +709,7 @@ struct Engine : nds_engine {
   ~Engine() override {
     cudaSetDevice(cfg.device);
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
-    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
+    for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_ticket, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
                     (void*)d_umb_k, (void*)d_umb_r0, (void*)d_hills, (void*)d_alive,
                     (void*)d_basin, (void*)d_exit, (void*)d_frames, (void*)d_hist, (void*)d_noise, (void*)d_stage,
@@ -848,6 +851,7 @@ struct Engine : nds_engine {
         // the whole grid rides in shared memory when the wide variant was picked and it fits beside the static part
         int dev_smem = 0;
         CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+        CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c.device));
         grid_in_smem = variant_wide && (int64_t)sizeof(R) * grid_elems <= (int64_t)dev_smem - 1024 && !getenv("NDS_GRID_NO_SMEM");
       }
       if (c.mtd_adapsig_hist) {
@@ -1199,14 +1203,30 @@ struct Engine : nds_engine {
         if (accumulate(rec, M, d_ginc_list, 1, false)) return 1;
         exchange_mark(true);
         const long long n16 = grid_elems * (long long)sizeof(R) / 16;  // 4 reals per point: a multiple of 16 bytes
-        grid_push_kernel<R><<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(n16, d_ginc, d_slot_dst + par * n_peers, n_peers);
-        CU(cudaGetLastError());
-        launches++;
-        if (peer_barrier()) return 1;
-        grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
-        CU(cudaGetLastError());
-        exchange_mark(false);
-        launches++;
+        const unsigned gx = (unsigned)((n16 + 255) / 256);
+        if (device_barrier && gx <= (unsigned)sm_count && !getenv("NDS_NO_FUSED_EXCHANGE")) {
+          // push + barrier + apply in one launch (all CTAs co-resident: at most one per SM)
+          if (!d_ticket) {
+            CU(cudaMalloc(&d_ticket, sizeof(unsigned int)));
+            CU(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), stream));
+          }
+          barrier_epoch += 1;
+          grid_exchange_kernel<R><<<gx, 256, 0, stream>>>(n16, d_ginc, d_slot_dst + par * n_peers, d_slot_src + par * n_peers, n_peers,
+                                                       d_grid, d_peer_flags, peer_rank, barrier_epoch, 10000000000ull,
+                                                       d_flags_own + NDS_MAX_RANKS, d_ticket);
+          CU(cudaGetLastError());
+          exchange_mark(false);
+          launches++;
+        } else {
+          grid_push_kernel<R><<<gx, 256, 0, stream>>>(n16, d_ginc, d_slot_dst + par * n_peers, n_peers);
+          CU(cudaGetLastError());
+          launches++;
+          if (peer_barrier()) return 1;
+          grid_apply_kernel<R><<<ga, 256, 0, stream>>>(grid_elems, d_grid, d_slot_src + par * n_peers, n_peers);
+          CU(cudaGetLastError());
+          exchange_mark(false);
+          launches++;
+        }
       } else if (comm) {
         if (accumulate(rec, M, d_ginc_list, 1, false)) return 1;
         exchange_mark(true);
@@ -2507,6 +2527,28 @@ int nds_noise_tail_counts(int device, int precision, uint64_t seed, int64_t n_wa
   if (err != cudaSuccess) return fail(nullptr, "nds_noise_tail_counts: %s", cudaGetErrorString(err));
   for (int t = 0; t < n_thresholds; t++) counts[t] = h[t];
   return 0;
+}
+
+int nds_map50to2d(int device, const double* x, int64_t n, double* c, double* jac) {
+  if (n < 0) return fail(nullptr, "nds_map50to2d: negative count");
+  if (n == 0) return 0;
+  if (!x) return fail(nullptr, "nds_map50to2d: x is NULL");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "nds_map50to2d: no CUDA device");
+  double *dx = nullptr, *dc = nullptr, *dj = nullptr;
+  const size_t row = sizeof(double) * (size_t)n;
+  cudaError_t err = cudaMalloc(&dx, row * MAP50_ND);
+  if (err == cudaSuccess && c) err = cudaMalloc(&dc, row * 2);
+  if (err == cudaSuccess && jac) err = cudaMalloc(&dj, row * 2 * MAP50_ND);
+  if (err == cudaSuccess) err = cudaMemcpy(dx, x, row * MAP50_ND, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) {
+    static const Map50Table T = map50_table();
+    map50to2d_kernel<<<(unsigned)((n + 127) / 128), 128>>>(T, dx, (long long)n, dc, dj);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess && c) err = cudaMemcpy(c, dc, row * 2, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && jac) err = cudaMemcpy(jac, dj, row * 2 * MAP50_ND, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dc); cudaFree(dj);
+  return err == cudaSuccess ? 0 : fail(nullptr, "nds_map50to2d: %s", cudaGetErrorString(err));
 }
 
 }  // extern "C"

@@ -275,4 +275,66 @@ __global__ void peer_barrier_kernel(unsigned long long* const* __restrict__ flag
   __threadfence_system();
 }
 
+// ------------------------------------------------------------------- fused grid exchange (peer path, device barrier)
+// push + barrier + apply of one deposition stride in ONE kernel instead of three launches:
+//   (1) every CTA stores its part of this rank's increment into the rank's slot on EVERY peer (NVLink), fences;
+//   (2) the LAST CTA to get there (ticket counter) signals `epoch` into every peer's flag array;
+//   (3) every CTA waits until all peers' epochs have arrived in THIS rank's flag array, then adds the nranks slots of
+//       its part to the grid in rank order (bit-identical grids on every rank).
+// All CTAs are co-resident (the host launches this kernel only when the grid has at most one CTA per SM), so the
+// waiting CTAs cannot keep a pushing CTA off the machine.  NEVER launched for ranks that share one GPU.
+template <typename R>
+__global__ void __launch_bounds__(256)
+grid_exchange_kernel(long long n16, const R* __restrict__ inc, R* const* __restrict__ dst, const R* const* __restrict__ src,
+                     int nranks, R* grid, unsigned long long* const* __restrict__ flags, int rank,
+                     unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* err,
+                     unsigned int* ticket) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) {
+    const int4 v = reinterpret_cast<const int4*>(inc)[i];
+    for (int r = 0; r < nranks; r++) reinterpret_cast<int4*>(dst[r])[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    __threadfence();
+    if (t == gridDim.x - 1) {  // every CTA of this rank has pushed and fenced
+      *ticket = 0u;            // next launch (nobody reads it again in this one)
+      __threadfence_system();
+      for (int r = 0; r < nranks; r++) {
+        unsigned long long* out = flags[r] + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(out), "l"(epoch) : "memory");
+      }
+    }
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < nranks; r++) {
+      const unsigned long long* in = flags[rank] + r;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in) : "memory");
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicMax(err, epoch); break; }
+        __nanosleep(100);
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (i < n16) {
+    constexpr int NV = 16 / (int)sizeof(R);
+    union V { int4 q; R a[NV]; };
+    V g;
+    g.q = reinterpret_cast<const int4*>(grid)[i];
+    for (int r = 0; r < nranks; r++) {
+      V sv;
+      sv.q = __ldcg(reinterpret_cast<const int4*>(src[r]) + i);  // written by the peers: straight from L2
+#pragma unroll
+      for (int k = 0; k < NV; k++) g.a[k] += sv.a[k];
+    }
+    reinterpret_cast<int4*>(grid)[i] = g.q;
+  }
+}
+
 }  // namespace nds

@@ -106,15 +106,20 @@ md_pair_grid(const __grid_constant__ Consts<float> K, const __grid_constant__ Bl
       fx = fmaf(su, Gx, fx); fy = fmaf(su, Gy, fy);
     }
     // ---- my column of the bicubic Hermite interpolation (grid_combine)
-    float a[2], b[2], da[2], db[2], as[2], bs[2], das[2], dbs[2];
-    hermite_basis<float>(t, a, b, da, db);
+    // along t only the basis functions of MY column are needed: h01(t) = h00(1 - t), h11(t) = -h10(1 - t), so one
+    // set of formulas serves both lanes through tau = t (column i) or 1 - t (column i + 1)
+    float as[2], bs[2], das[2], dbs[2];
     hermite_basis<float>(sc, as, bs, das, dbs);
+    const float tau = half ? 1.f - t : t, ups = 1.f - tau, sgn = half ? -1.f : 1.f;
+    const float uu = ups * ups, stu = sgn * tau;
+    const float ap = fmaf(2.f, tau, 1.f) * uu, bp = stu * uu;
+    const float dap = -6.f * (stu * ups), dbp = ups * fmaf(-3.f, tau, 1.f);
     const float vp = as[0] * n0.x + bs[0] * n0.z + as[1] * n1.x + bs[1] * n1.z;
     const float yp = as[0] * n0.y + bs[0] * n0.w + as[1] * n1.y + bs[1] * n1.w;
     const float vps = das[0] * n0.x + dbs[0] * n0.z + das[1] * n1.x + dbs[1] * n1.z;
     const float yps = das[0] * n0.y + dbs[0] * n0.w + das[1] * n1.y + dbs[1] * n1.w;
-    const float dVt = (half ? da[1] : da[0]) * vp + (half ? db[1] : db[0]) * yp;
-    const float dVs = (half ? a[1] : a[0]) * vps + (half ? b[1] : b[0]) * yps;
+    const float dVt = dap * vp + dbp * yp;
+    const float dVs = ap * vps + bp * yps;
     // colvar-space force, my part: surface + bias (g = -dV/dc)
     const float P0 = fmaf(-dVt, K.grid_invh[0], fx), P1 = fmaf(-dVs, K.grid_invh[1], fy);
     // A needs the total along q0, B along q1: each sends the component it does not need

@@ -496,3 +496,24 @@ def noise_tail_counts(precision, seed, n_walkers, calls_per_walker, thresholds, 
         raise NdsError(lib.nds_last_error(None).decode())
     n = 6.0 * n_walkers * calls_per_walker
     return counts.astype(np.int64), dict(n=n, mean=stats[0] / n, m2=stats[1] / n, m4=stats[2] / n, max=stats[3])
+
+
+def map50to2d(x, jacobian=True, device=0):
+    """``Map50to2d`` (``colvars/misc.py:19-156``) at configurations ``x[50][n]`` (or one ``x[50]``) on the device:
+    -> ``dict(c=[2][n], J=[2][50][n])``.  The reference has no potential with ``ndim = 50``, so it cannot run a
+    trajectory with this colvar; this evaluation is the whole surface it offers (``compute`` / ``jacobian``)."""
+    lib = _abi.load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    single = x.ndim == 1
+    if single:
+        x = x.reshape(-1, 1)
+    if x.ndim != 2 or x.shape[0] != 50:
+        raise ValueError(f"Map50to2d takes x[50][n], got shape {x.shape}")
+    n = x.shape[1]
+    c = np.zeros((2, n))
+    J = np.zeros((2, 50, n)) if jacobian else None
+    if lib.nds_map50to2d(device, _p(x), n, _p(c), _p(J) if jacobian else None):
+        raise NdsError(lib.nds_last_error(None).decode())
+    if single:
+        return dict(c=c[:, 0], J=None if J is None else J[:, :, 0])
+    return dict(c=c, J=J)

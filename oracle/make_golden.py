@@ -558,9 +558,31 @@ def fes_projection():
     dump("fes_projection.json", out)
 
 
+def map50to2d():
+    """Map50to2d (colvars/misc.py:19-156): values and Jacobians of the reference at 24 configurations (unit and
+    10-unit scale, plus the coordinate axes that carry the off-diagonal couplings)."""
+    ref_stub.install()
+    from ndsimulator.colvars.misc import Map50to2d
+    cov = Map50to2d()
+    cov.ndim = 50  # Colvar.initialize would copy it from the run (colvar.py:11-13); no run can exist (SURVEY A19)
+    rng = np.random.RandomState(50)
+    pts = [rng.normal(size=50) for _ in range(8)] + [10.0 * rng.normal(size=50) for _ in range(8)]
+    for d in (0, 1, 2, 3, 4, 5, 8, 49):
+        e = np.zeros(50)
+        e[d] = 1.5
+        e[(d + 1) % 50] = -0.5
+        pts.append(e)
+    rec = dict(points=[], value=[], jac=[])
+    for x in pts:
+        rec["points"].append(tolist(x))
+        rec["value"].append(tolist(cov.compute(x)))
+        rec["jac"].append(tolist(cov.jacobian(x)))
+    dump("map50to2d.json", rec)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] in ("dump_files", "path_colvars", "committor", "mc_runs", "trajectories",
-                                             "fes_projection"):
+                                             "fes_projection", "map50to2d"):
         globals()[sys.argv[1]]()
         sys.exit(0)
     eval_points()
@@ -572,3 +594,4 @@ if __name__ == "__main__":
     path_colvars()
     mc_runs()
     fes_projection()
+    map50to2d()

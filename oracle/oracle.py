@@ -72,6 +72,7 @@ def lib():
                                       C.c_double, C.c_double, C.c_int64, _dp]
         L.oracle_rng_normals.argtypes = [C.c_uint32, C.c_int64, _dp]
         L.oracle_rng_uniforms.argtypes = [C.c_uint32, C.c_int64, _dp]
+        L.oracle_map50to2d.argtypes = [_dp, C.c_int64, _dp, _dp]
         L.oracle_colvar_dim.argtypes = [C.c_int, C.c_int]
         L.oracle_colvar_dim.restype = C.c_int
         _lib = L
@@ -249,3 +250,12 @@ def rng_uniforms(seed, n):
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def map50to2d(x):
+    """Map50to2d (colvars/misc.py:19-156) at x[50][n] through the dense C restatement -> dict(c=[2][n], J=[2][50][n])."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[1]
+    c, J = np.zeros((2, n)), np.zeros((2, 50, n))
+    lib().oracle_map50to2d(_p(x), n, _p(c), _p(J))
+    return dict(c=c, J=J)
