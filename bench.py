@@ -606,7 +606,9 @@ def bench_c5(ctx, grid, exchange, strides, warmup, M=8192, precision="f32"):
                                "ms_per_stride": pipe_ms / strides,
                                "note": "all strides in one nds_run call, L2 not flushed (state + grid are < 2 MB)"}
         ach = value / ctx.world * GRID_FLOPS_PER_WALKER_STEP / 1e12
-        rec["roofline"] = {"bound": "latency (8192 walkers = 64 CTAs of 4 warps on 148 SMs)", "achieved": ach,
+        rec["roofline"] = {"bound": "latency (8192 walkers = 16384 lanes of md_pair_grid = 512 warps on 592 "
+                                    "schedulers: one warp each, bound by the length of a step's dependent "
+                                    "instruction stream)", "achieved": ach,
                            "peak": ctx.fp32_peak_tflops(), "unit": "TFLOP/s", "frac": ach / ctx.fp32_peak_tflops(),
                            "traffic": None,
                            "note": f"{GRID_FLOPS_PER_WALKER_STEP:.0f} flop/walker-step (212 of SURVEY 8d + 97 of the "

@@ -676,6 +676,7 @@ struct Engine : nds_engine {
   R* d_grid = nullptr;
   R* d_ginc = nullptr;                     // increment of one stride (single slot: all-reduce path)
   unsigned int* d_ticket = nullptr;        // arrival counter of grid_exchange_kernel
+  unsigned long long* d_xtrace = nullptr;  // NDS_EXCHANGE_TRACE: phase times of grid_exchange_kernel
   int sm_count = 0;
   bool cluster_ready = false;              // grid_accumulate_kernel may run clusters of GRID_SLICES CTAs
   R* d_vr_umb = nullptr;                   // Harmonic.VR per restraint [n_umb][M] (umbrella + metadynamics with frames)
@@ -708,6 +709,15 @@ struct Engine : nds_engine {
 
   ~Engine() override {
     cudaSetDevice(cfg.device);
+    if (d_xtrace) {  // NDS_EXCHANGE_TRACE=1
+      unsigned long long h[8] = {0};
+      cudaStreamSynchronize(stream);
+      if (cudaMemcpy(h, d_xtrace, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[5] > 0)
+        fprintf(stderr, "[nds exchange trace] rank %d: %llu fused exchanges; mean ns from kernel entry: own push fenced %.0f, "
+                        "signal sent %.0f, all peers seen %.0f, slots added %.0f\n", peer_rank, h[5],
+                (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5]);
+      cudaFree(d_xtrace);
+    }
     if (comm && comm_owned && nccl_api().ok) nccl_api().CommDestroy(comm);
     for (void* p : {(void*)d_slab, (void*)d_grid, (void*)d_ginc, (void*)d_ticket, (void*)d_cvhist, (void*)d_vr_umb, (void*)d_slot_dst, (void*)d_slot_src, (void*)d_ginc_list,
                     (void*)d_grid_outside, (void*)d_peer_flags, (void*)d_eval,
@@ -1209,11 +1219,15 @@ struct Engine : nds_engine {
           if (!d_ticket) {
             CU(cudaMalloc(&d_ticket, sizeof(unsigned int)));
             CU(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), stream));
+            if (getenv("NDS_EXCHANGE_TRACE")) {  // phase times of the fused exchange, printed by the destructor
+              CU(cudaMalloc(&d_xtrace, sizeof(unsigned long long) * 8));
+              CU(cudaMemsetAsync(d_xtrace, 0, sizeof(unsigned long long) * 8, stream));
+            }
           }
           barrier_epoch += 1;
           grid_exchange_kernel<R><<<gx, 256, 0, stream>>>(n16, d_ginc, d_slot_dst + par * n_peers, d_slot_src + par * n_peers, n_peers,
                                                        d_grid, d_peer_flags, peer_rank, barrier_epoch, 10000000000ull,
-                                                       d_flags_own + NDS_MAX_RANKS, d_ticket);
+                                                       d_flags_own + NDS_MAX_RANKS, d_ticket, d_xtrace);
           CU(cudaGetLastError());
           exchange_mark(false);
           launches++;

@@ -220,10 +220,14 @@ grid_accumulate_kernel(const __grid_constant__ Consts<R> K, const R* __restrict_
 template <typename R>
 __global__ void grid_push_kernel(long long n16, const R* __restrict__ inc, R* const* __restrict__ dst, int ndst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n16) return;
-  const int4 v = reinterpret_cast<const int4*>(inc)[i];
-  for (int r = 0; r < ndst; r++) reinterpret_cast<int4*>(dst[r])[i] = v;
-  __threadfence_system();  // peer slots: visible before the barrier kernel signals
+  if (i < n16) {
+    const int4 v = reinterpret_cast<const int4*>(inc)[i];
+    for (int r = 0; r < ndst; r++) reinterpret_cast<int4*>(dst[r])[i] = v;
+  }
+  // peer slots visible before the barrier kernel signals: ONE system fence per CTA behind the block barrier (fences
+  // are cumulative); a fence per thread costs 13 us here (2 GPUs, NDS_EXCHANGE_TRACE)
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
 }
 
 // grid += sum of nsrc increment buffers, in the given (rank) order: every rank ends with bit-identical grids
@@ -288,24 +292,32 @@ __global__ void __launch_bounds__(256)
 grid_exchange_kernel(long long n16, const R* __restrict__ inc, R* const* __restrict__ dst, const R* const* __restrict__ src,
                      int nranks, R* grid, unsigned long long* const* __restrict__ flags, int rank,
                      unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* err,
-                     unsigned int* ticket) {
+                     unsigned int* ticket, unsigned long long* dbg) {
+  // dbg (NDS_EXCHANGE_TRACE=1): sums of globaltimer deltas from kernel entry, seen by CTA 0 -- [0] own push fenced,
+  // [1] this rank's signal sent (all its CTAs fenced), [2] all peers' signals seen, [3] slots added; [5] launches
+  unsigned long long dt0 = 0;
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dt0));
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n16) {
     const int4 v = reinterpret_cast<const int4*>(inc)[i];
     for (int r = 0; r < nranks; r++) reinterpret_cast<int4*>(dst[r])[i] = v;
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // ONE system fence per CTA behind the block barrier (fences are cumulative): a fence per thread made this phase
+    // 13 us on 2 GPUs (NDS_EXCHANGE_TRACE)
+    __threadfence_system();
+    unsigned long long dt1 = 0;
+    if (dbg && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dt1));
     const unsigned int t = atomicAdd(ticket, 1u);
-    __threadfence();
     if (t == gridDim.x - 1) {  // every CTA of this rank has pushed and fenced
       *ticket = 0u;            // next launch (nobody reads it again in this one)
-      __threadfence_system();
+      __threadfence_system();  // orders the other CTAs' fenced stores (seen through the ticket) before the signals
       for (int r = 0; r < nranks; r++) {
         unsigned long long* out = flags[r] + rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(out), "l"(epoch) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(out), "l"(epoch) : "memory");
       }
+      if (dbg) { unsigned long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts)); dbg[4] = ts; }
     }
     unsigned long long t0, t1, v;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -320,6 +332,13 @@ grid_exchange_kernel(long long n16, const R* __restrict__ inc, R* const* __restr
       }
     }
     __threadfence_system();
+    if (dbg && blockIdx.x == 0) {
+      unsigned long long dt3;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dt3));
+      const unsigned long long ts = *reinterpret_cast<volatile unsigned long long*>(dbg + 4);
+      atomicAdd(dbg + 0, dt1 - dt0); atomicAdd(dbg + 1, ts > dt0 ? ts - dt0 : 0ull); atomicAdd(dbg + 2, dt3 - dt0);
+      atomicAdd(dbg + 5, 1ull);
+    }
   }
   __syncthreads();
   if (i < n16) {
@@ -334,6 +353,14 @@ grid_exchange_kernel(long long n16, const R* __restrict__ inc, R* const* __restr
       for (int k = 0; k < NV; k++) g.a[k] += sv.a[k];
     }
     reinterpret_cast<int4*>(grid)[i] = g.q;
+  }
+  if (dbg && blockIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long dt4;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dt4));
+      atomicAdd(dbg + 3, dt4 - dt0);
+    }
   }
 }
 

@@ -821,7 +821,7 @@ __global__ void deposit_p2p_kernel(const __grid_constant__ Consts<R> K, long lon
                                    const unsigned char* alive, R* const* __restrict__ tables, int nranks,
                                    long long n_hills, int first) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= M) return;
+  if (w < M) {
   const bool live = alive ? alive[w] != 0 : true;
   R h = first ? K.mtd_w : K.mtd_w * nds_exp(-vr[w] / K.mtd_kBdT);
   if (!live) h = (R)0;
@@ -845,7 +845,11 @@ __global__ void deposit_p2p_kernel(const __grid_constant__ Consts<R> K, long lon
       for (int k = 0; k < rs; k++) dst[k] = rec[k];
     }
   }
-  __threadfence_system();  // records are visible to the peers before this kernel is reported complete
+  }
+  // records visible to the peers before the barrier kernel signals: one system fence per CTA behind the block
+  // barrier (fences are cumulative; a fence per thread is several microseconds slower, see grid_exchange_kernel)
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------- FES grid, histogram

@@ -145,42 +145,58 @@ md_pair_grid(const __grid_constant__ Consts<float> K, const __grid_constant__ Bl
   }
 
   const long long s_end = A.step0 + A.nsteps;
-  // steps go in pairs (even, odd): lane A draws the call of the even step, lane B that of the odd one
-  for (long long s2 = A.step0 & ~1LL; s2 < s_end; s2 += 2) {
+  // one MD.update (md.py:164-198) of this lane's dimensions with the noise xi (= c2 * normal)
+  auto step = [&](const float (&xi)[3]) {
+    // ---- first half kick + drift, md.py:164-178
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      v[k] = fmaf(K.hdtm, f[k], v[k]);
+      v[k] = fmaf(K.c1, v[k], xi[k]);
+      const float dx = v[k] * K.dt;
+      x[k] = x[k] + dx;
+    }
+    // ---- colvar, potential and bias at the new positions, md.py:179-188
+    force();
+    // ---- second half kick, md.py:190-198
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      v[k] = fmaf(K.hdtm, f[k], v[k]);
+      v[k] = fmaf(K.c1, v[k], xi[k]);
+    }
+  };
+  // the normals of the step pair (s2, s2 + 1): lane A draws the call of the even step, lane B that of the odd one,
+  // and each hands the partner the normals of the partner's dimensions -- A owes (z2, z3, -), B owes (z0, z1, z4)
+  auto draw = [&](long long s2, float (&xe)[3], float (&xo)[3]) {
     float z[NDS_NPC];
     normals6<float>(K.rk_step, (unsigned long long)(s2 + half), gid, z, K.bm_c2);  // c2 * xi (PRESCALED)
-    // partner's dimensions of my call: A owes (z2, z3, -), B owes (z0, z1, z4)
     const float r0 = __shfl_xor_sync(0xffffffffu, half ? z[0] : z[2], 1);
     const float r1 = __shfl_xor_sync(0xffffffffu, half ? z[1] : z[3], 1);
     const float r2 = __shfl_xor_sync(0xffffffffu, half ? z[4] : 0.f, 1);
-    // noise of my dimensions at the even step (drawn by A) and at the odd step (drawn by B)
-    float xe[3], xo[3];
-    xe[0] = half ? r0 : z[0]; xe[1] = half ? r1 : z[1]; xe[2] = half ? 0.f : z[4];
-    xo[0] = half ? z[2] : r0; xo[1] = half ? z[3] : r1; xo[2] = half ? 0.f : r2;
+    xe[0] = half ? r0 : z[0]; xe[1] = half ? r1 : z[1]; xe[2] = half ? 0.f : z[4];  // even step (drawn by A)
+    xo[0] = half ? z[2] : r0; xo[1] = half ? z[3] : r1; xo[2] = half ? 0.f : r2;    // odd step (drawn by B)
+  };
+  long long s = A.step0;
+  float xe[3], xo[3];
+  if (s < s_end && (s & 1)) {  // the launch starts on an odd step: second half of its pair
+    draw(s - 1, xe, xo);
+    step(xo);
+    s += 1;
+  }
+  // whole pairs, software-pipelined: the Philox / Box-Muller chain of the NEXT pair is independent of this pair's
+  // physics, so it fills the issue slots the dependent FP32 chain leaves empty (one warp per scheduler)
+  if (s + 1 < s_end) draw(s, xe, xo);
+  while (s + 1 < s_end) {
+    float ne[3], no[3];
+    draw(s + 2, ne, no);  // (one pair beyond the launch at the end: drawn, never used)
+    step(xe);
+    step(xo);
 #pragma unroll
-    for (int sub = 0; sub < 2; sub++) {
-      const long long s = s2 + sub;
-      if (s < A.step0 || s >= s_end) continue;  // warp-uniform
-      float xi[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) xi[k] = sub ? xo[k] : xe[k];
-      // ---- first half kick + drift, md.py:164-178
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        v[k] = fmaf(K.hdtm, f[k], v[k]);
-        v[k] = fmaf(K.c1, v[k], xi[k]);
-        const float dx = v[k] * K.dt;
-        x[k] = x[k] + dx;
-      }
-      // ---- colvar, potential and bias at the new positions, md.py:179-188
-      force();
-      // ---- second half kick, md.py:190-198
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        v[k] = fmaf(K.hdtm, f[k], v[k]);
-        v[k] = fmaf(K.c1, v[k], xi[k]);
-      }
-    }
+    for (int k = 0; k < 3; k++) { xe[k] = ne[k]; xo[k] = no[k]; }
+    s += 2;
+  }
+  if (s < s_end) {  // the launch ends on an even step: first half of its pair
+    draw(s, xe, xo);
+    step(xe);
   }
 
   // ---- launch exit: gather the pair's state, observables at the final positions (md.py:210-217,226-229)
