@@ -75,7 +75,10 @@ md_pair_grid(const __grid_constant__ Consts<float> K, const __grid_constant__ Bl
   // total force on this lane's dimensions at the pair's current positions (potential + bias)
   auto force = [&]() {
     // ---- colvar of my group (five.py:50-57), the partner's through one shuffle
-    const float ss = x[0] * x[0] + x[1] * x[1] + cz * (x[2] * x[2]);
+    // (sums of two or more products are written as explicit fmaf chains: force() is inlined at several places, the
+    // compiler is free to pick which product of a*b + c*d it fuses, and results must not depend on which copy ran --
+    // launch boundaries may fall anywhere)
+    const float ss = fmaf(x[1], x[1], fmaf(x[0], x[0], cz * (x[2] * x[2])));
     const float iq = nds_rsqrt(ss), q = ss * iq;
     const float qp = __shfl_xor_sync(0xffffffffu, q, 1);
     const float q0 = half ? qp : q, q1 = half ? q : qp;
@@ -114,12 +117,12 @@ md_pair_grid(const __grid_constant__ Consts<float> K, const __grid_constant__ Bl
     const float uu = ups * ups, stu = sgn * tau;
     const float ap = fmaf(2.f, tau, 1.f) * uu, bp = stu * uu;
     const float dap = -6.f * (stu * ups), dbp = ups * fmaf(-3.f, tau, 1.f);
-    const float vp = as[0] * n0.x + bs[0] * n0.z + as[1] * n1.x + bs[1] * n1.z;
-    const float yp = as[0] * n0.y + bs[0] * n0.w + as[1] * n1.y + bs[1] * n1.w;
-    const float vps = das[0] * n0.x + dbs[0] * n0.z + das[1] * n1.x + dbs[1] * n1.z;
-    const float yps = das[0] * n0.y + dbs[0] * n0.w + das[1] * n1.y + dbs[1] * n1.w;
-    const float dVt = dap * vp + dbp * yp;
-    const float dVs = ap * vps + bp * yps;
+    const float vp = fmaf(bs[1], n1.z, fmaf(as[1], n1.x, fmaf(bs[0], n0.z, as[0] * n0.x)));
+    const float yp = fmaf(bs[1], n1.w, fmaf(as[1], n1.y, fmaf(bs[0], n0.w, as[0] * n0.y)));
+    const float vps = fmaf(dbs[1], n1.z, fmaf(das[1], n1.x, fmaf(dbs[0], n0.z, das[0] * n0.x)));
+    const float yps = fmaf(dbs[1], n1.w, fmaf(das[1], n1.y, fmaf(dbs[0], n0.w, das[0] * n0.y)));
+    const float dVt = fmaf(dbp, yp, dap * vp);
+    const float dVs = fmaf(bp, yps, ap * vps);
     // colvar-space force, my part: surface + bias (g = -dV/dc)
     const float P0 = fmaf(-dVt, K.grid_invh[0], fx), P1 = fmaf(-dVs, K.grid_invh[1], fy);
     // A needs the total along q0, B along q1: each sends the component it does not need
@@ -152,8 +155,7 @@ md_pair_grid(const __grid_constant__ Consts<float> K, const __grid_constant__ Bl
     for (int k = 0; k < 3; k++) {
       v[k] = fmaf(K.hdtm, f[k], v[k]);
       v[k] = fmaf(K.c1, v[k], xi[k]);
-      const float dx = v[k] * K.dt;
-      x[k] = x[k] + dx;
+      x[k] = fmaf(v[k], K.dt, x[k]);
     }
     // ---- colvar, potential and bias at the new positions, md.py:179-188
     force();

@@ -204,7 +204,7 @@ def test_pair_kernel_follows_the_thread_per_walker_kernel(monkeypatch):
     assert a[1]["biase"].max() > 0.05
 
 
-def test_pair_kernel_launch_boundaries_and_fp64(monkeypatch):
+def test_pair_kernel_launch_boundaries_and_fp64():
     """(1) Launch boundaries at odd and even steps do not change the pair kernel's results (its launch entry
     evaluates the force with the loop's own arithmetic; steps are drawn in (even, odd) pairs).  (2) Against the fp64
     engine under the same Philox seed the walkers stay within fp32 distance over 60 steps."""
@@ -221,7 +221,7 @@ def test_pair_kernel_launch_boundaries_and_fp64(monkeypatch):
         return eng.get_state()
 
     one = run("f32", [60])
-    for chunks in ([7, 13, 40], [1, 1, 58], [30, 30]):
+    for chunks in ([7, 13, 40], [1, 1, 58], [30, 30], [2, 3, 5, 6, 44], [59, 1]):
         st = run("f32", chunks)
         for k in ("x", "v", "f", "pe"):
             assert np.array_equal(one[k], st[k]), (chunks, k)
