@@ -15,8 +15,12 @@
 // on both lanes: the cell search and the Hermite basis of the interpolation (~45 instructions).  The noise STREAM
 // is the one of md_block (one Philox4x32-10 call per walker and step, normals 0..4 of the call for dimensions 0..4),
 // so results agree with md_block_wide up to the order of the floating-point sums of the force.
-// Launch entry and exit (forces at the current positions, VR refresh after a deposition, observables, state
-// write-back) reuse the generic eval_all on both lanes of the pair; lane A stores.
+// The Philox / Box-Muller chain of the NEXT pair of steps is drawn in the same basic block as this pair's physics: the
+// independent integer chain fills the bubbles of the dependent FP32 chain (41.9 -> 37.5 us per 100 steps).
+// Launch entry evaluates the force with the loop's own arithmetic (sums of products are explicit fmaf chains, so
+// every inlined copy rounds alike and launch boundaries do not change results) and refreshes VR after a deposition
+// through grid_interp; launch exit (observables, state write-back) reuses the generic eval_all on both lanes of the
+// pair; lane A stores.
 #pragma once
 #include <cstdlib>
 #include "nds_variants.h"
