@@ -678,7 +678,7 @@ struct Engine : nds_engine {
   unsigned int* d_ticket = nullptr;        // arrival counter of grid_exchange_kernel
   unsigned long long* d_xtrace = nullptr;  // NDS_EXCHANGE_TRACE: phase times of grid_exchange_kernel
   int sm_count = 0;
-  bool cluster_ready = false;              // grid_accumulate_kernel may run clusters of GRID_SLICES CTAs
+  bool cluster_ready = false;              // grid_accumulate_kernel opted in to clusters of GRID_SLICES > 8 CTAs
   R* d_vr_umb = nullptr;                   // Harmonic.VR per restraint [n_umb][M] (umbrella + metadynamics with frames)
   R* d_cvhist = nullptr;                   // Stat.colv ring [tao_d][M] (mtd_adapsig_hist)
   int64_t cv_n = 0;                        // samples taken so far (len(stat.colv))
@@ -2264,7 +2264,7 @@ struct Engine : nds_engine {
   // or -> the destination list (increment slots on the peers / the all-reduce buffer)
   int accumulate(const R* rec, int64_t n, R* const* dst, int ndst, bool add) {
     const int tiles = ((K.grid_nx + GRID_TX - 1) / GRID_TX) * ((K.grid_ny + GRID_TY - 1) / GRID_TY);
-    if (!cluster_ready) {  // clusters of GRID_SLICES = 16 CTAs: above the portable size of 8
+    if (GRID_SLICES > 8 && !cluster_ready) {  // clusters above the portable size of 8 CTAs need the opt-in
       CU(cudaFuncSetAttribute(grid_accumulate_kernel<R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       cluster_ready = true;
     }
