@@ -322,7 +322,9 @@ NDS_API int nds_set_peer_tables(nds_engine* e, void* const* tables, int nranks, 
 /* device-side barrier of the peer-memory exchange: one warp per rank signals its arrival into every peer's
  * window and waits for theirs (no host round trip, no callback).  ONLY for one rank per GPU: ranks that share
  * a GPU must keep the callback barrier (their waiting kernels are not guaranteed to be co-resident).  A rank
- * that does not arrive within 10 s makes nds_sync() / nds_wait() fail instead of hanging the GPU.        */
+ * that does not arrive within 10 s makes nds_sync() / nds_wait() fail instead of hanging the GPU.
+ * With mtd_grid the device barrier is part of ONE exchange kernel per deposition stride: it stores the rank's
+ * grid increment into its slot on every peer, signals, waits for the peers and adds the slots in rank order.  */
 NDS_API int nds_set_peer_barrier(nds_engine* e, int on_device);
 
 /* native NCCL exchange (SURVEY.md section 8b `nds_set_comm`): a C caller gets the multi-GPU hill exchange
