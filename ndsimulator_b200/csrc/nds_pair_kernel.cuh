@@ -28,7 +28,10 @@
 namespace nds {
 
 constexpr int NDS_PAIR_BLOCK = 128;        // threads per CTA = 64 walkers
-constexpr long long NDS_PAIR_MAX = 65536;  // walkers per launch up to which the pair kernel is chosen
+// walkers per launch up to which the pair kernel is chosen: it runs 2 x 212 instructions per walker-step against
+// md_block_wide's ~300, so it only pays while the GPU is short of warps -- measured per 100 steps, pair / wide:
+// 8192 walkers 37.5 / 48.4 us, 16384: 40.7 / 45.5, 32768: 65.0 / 57.0, 65536: 106 / 91 (exp_pair_threshold.py)
+constexpr long long NDS_PAIR_MAX = 16384;
 
 template <class S>
 __global__ void __launch_bounds__(NDS_PAIR_BLOCK)
